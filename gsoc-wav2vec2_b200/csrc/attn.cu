@@ -1,0 +1,346 @@
+// Non-causal multi-head attention forward for sm_100a (head size 64):
+//     ctx[b, t, h*64:(h+1)*64] = softmax_k( q[b,t,h,:] . k[b,k,h,:]  (+ key mask) ) . v[b,k,h,:]
+// Reference: TransformerAttention.get_context, encoder.py:34-47 (scores, additive mask, softmax, PV, head
+// merge) with the head split of encoder.py:49-54 and the key mask of encoder.py:256-263 (-10000 on padded
+// keys, which underflows to an exact 0 probability in fp32 -> implemented as exclusion via kv_len).
+// The q scaling of encoder.py:28 is folded into the q projection weights by the host.
+//
+// Layout: one packed activation  qkv[b, t, 0:3d] = [q | k | v]  (bf16, written by the fused QKV GEMM).
+// Head h of q/k/v is a 64-column slice, so every operand tile is ONE 3-D TMA box {64, 128, 1} of the
+// same tensor map - no head-split / transpose kernels, and the context is written straight into its
+// merged [b, t, d] position.
+//
+// One CTA = 128 queries of one (b, h).  Loop over 128-key chunks:
+//     S = Q K^T        tcgen05.mma 128x128x16 (x4), both operands K-major SW128         -> TMEM S
+//     softmax warps:   2 passes over S in TMEM (max, then exp2 / sum), P -> bf16 -> smem (SW128 image)
+//     PV = P V         tcgen05.mma 128x64x16 (x8), A = P (K-major), B = V (MN-major SW128) -> TMEM PV
+//     O = O * alpha + PV in registers (one query row per thread), final 1/l scaling and store.
+// Two CTAs are resident per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap the
+// other's softmax.  PASSES = 3 (parity mode) adds the hi/lo cross terms for both contractions.
+#include "host_util.h"
+#include "w2v2_common.cuh"
+#include "../../include/w2v2.h"
+
+namespace w2v2 {
+
+constexpr int AT_BM = 128;      // queries per CTA
+constexpr int AT_BN = 128;      // keys per chunk
+constexpr int AT_DH = 64;       // head size
+constexpr int AT_THREADS = 224; // warps 0-3 softmax, 4 TMA, 5 MMA, 6 TMEM allocator
+constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
+
+template <int PASSES>
+struct AttnSmem {
+  static constexpr int NPL = (PASSES == 3) ? 2 : 1;         // planes (hi, lo)
+  static constexpr int KV_STAGES = (PASSES == 3) ? 1 : 2;
+  static constexpr int Q_OFF = 0;
+  static constexpr int KV_OFF = Q_OFF + NPL * AT_TILE;
+  static constexpr int KV_STAGE_BYTES = 2 * NPL * AT_TILE;  // K and V, each NPL planes
+  static constexpr int P_OFF = KV_OFF + KV_STAGES * KV_STAGE_BYTES;
+  static constexpr int P_BYTES = NPL * 2 * AT_TILE;         // [128][128] bf16 = two [128][64] halves per plane
+  static constexpr int BAR_OFF = P_OFF + P_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+};
+
+struct AttnParams {
+  int T;               // frames per utterance
+  int d;               // hidden size (H * 64)
+  const int* kv_len;   // [B] or null
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(AT_THREADS, (PASSES == 1) ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
+                const AttnParams p) {
+  using S = AttnSmem<PASSES>;
+  constexpr int KV_STAGES = S::KV_STAGES;
+  constexpr int TMEM_COLS = 256;  // S: columns [0,128), PV: columns [128,192)
+  constexpr float LOG2E = 1.4426950408889634f;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;             // [KV_STAGES]
+  uint64_t* kv_empty = bars + 3;            // [KV_STAGES]
+  uint64_t* s_full = bars + 5;
+  uint64_t* s_empty = bars + 6;
+  uint64_t* p_full = bars + 7;
+  uint64_t* p_empty = bars + 8;
+  uint64_t* pv_full = bars + 9;
+  uint64_t* pv_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = lane_id();
+  const int q0 = blockIdx.x * AT_BM;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int kv_len = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
+  const int nchunks = (max(kv_len, 1) + AT_BN - 1) / AT_BN;
+
+  if (warp == 4 && elect_one()) {
+    tma_prefetch_desc(&tm_hi);
+    if (PASSES == 3) tma_prefetch_desc(&tm_lo);
+  }
+  if (warp == 5 && elect_one()) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(s_empty, 4);
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
+    mbar_init(pv_full, 1);
+    mbar_init(pv_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 6) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base;
+  const uint32_t tmem_pv = tmem_base + 128;
+
+  if (warp == 4) {
+    // ---------------------------------------------------------------- TMA producer
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, S::NPL * AT_TILE);
+      tma_load_3d(smem + S::Q_OFF, &tm_hi, q_full, h * AT_DH, q0, b);
+      if (PASSES == 3) tma_load_3d(smem + S::Q_OFF + AT_TILE, &tm_lo, q_full, h * AT_DH, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        uint8_t* kbuf = smem + S::KV_OFF + stage * S::KV_STAGE_BYTES;
+        uint8_t* vbuf = kbuf + S::NPL * AT_TILE;
+        mbar_arrive_expect_tx(&kv_full[stage], S::KV_STAGE_BYTES);
+        tma_load_3d(kbuf, &tm_hi, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
+        tma_load_3d(vbuf, &tm_hi, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
+        if (PASSES == 3) {
+          tma_load_3d(kbuf + AT_TILE, &tm_lo, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
+          tma_load_3d(vbuf + AT_TILE, &tm_lo, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
+        }
+        if (++stage == KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = idesc_bf16(AT_BM, AT_BN, 0, 0);   // S = Q K^T : A, B K-major
+      constexpr uint32_t idesc_pv = idesc_bf16(AT_BM, AT_DH, 0, 1);  // PV: A = P K-major, B = V MN-major
+      const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
+      const uint32_t p_addr = smem_u32(smem + S::P_OFF);
+      mbar_wait(q_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nchunks; ++j) {
+        const uint32_t par = j & 1;
+        const uint32_t k_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES);
+        const uint32_t v_addr = k_addr + S::NPL * AT_TILE;
+        mbar_wait(&kv_full[stage], phase);
+        mbar_wait(s_empty, par ^ 1);
+        tc_fence_after();
+        // ---- S = Q K^T
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+          const uint32_t qa = q_addr + ((pass == 1) ? AT_TILE : 0);
+          const uint32_t ka = k_addr + ((pass == 2) ? AT_TILE : 0);
+          const uint64_t dq = desc_kmajor_sw128(qa), dk = desc_kmajor_sw128(ka);
+#pragma unroll
+          for (int k = 0; k < AT_DH / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (pass | k) != 0);
+        }
+        umma_commit(s_full);
+        // ---- PV = P V
+        mbar_wait(p_full, par);
+        mbar_wait(pv_empty, par ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int pass = 0; pass < PASSES; ++pass) {
+          const uint32_t pa = p_addr + ((pass == 1) ? 2 * AT_TILE : 0);
+          const uint32_t va = v_addr + ((pass == 2) ? AT_TILE : 0);
+#pragma unroll
+          for (int ks = 0; ks < AT_BN / 16; ++ks) {
+            const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
+            const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
+            umma_f16(tmem_pv, dp, dv, idesc_pv, (pass | ks) != 0);
+          }
+        }
+        umma_commit(pv_full);
+        umma_commit(p_empty);
+        umma_commit(&kv_empty[stage]);
+        if (++stage == KV_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ---------------------------------------------------------------- softmax / output (one row per thread)
+    const int r = warp * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+    uint8_t* p_hi = smem + S::P_OFF;
+    uint8_t* p_lo = p_hi + 2 * AT_TILE;
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t swz = (uint32_t)(r & 7);
+    float o[AT_DH];
+#pragma unroll
+    for (int i = 0; i < AT_DH; ++i) o[i] = 0.0f;
+    float m_run = -INFINITY, l_run = 0.0f;
+
+    for (int j = 0; j < nchunks; ++j) {
+      const uint32_t par = j & 1;
+      const int key0 = j * AT_BN;
+      const bool partial = key0 + AT_BN > kv_len;
+      mbar_wait(s_full, par);
+      tc_fence_after();
+      // pass 1: running max
+      float mx = m_run;
+#pragma unroll 1
+      for (int piece = 0; piece < 4; ++piece) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_sel + piece * 32, rr);
+        tmem_ld_wait();
+        if (partial) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + piece * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+        }
+      }
+      const float alpha = ex2_approx((m_run - mx) * LOG2E);
+      m_run = mx;
+      const float mneg = -mx * LOG2E;
+      // pass 2: probabilities -> smem (bf16, SW128 K-major image), row sum
+      mbar_wait(p_empty, par ^ 1);
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int piece = 0; piece < 4; ++piece) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(tmem_s + lane_sel + piece * 32, rr);
+        tmem_ld_wait();
+        float pr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float e = ex2_approx(fmaf(__uint_as_float(rr[i]), LOG2E, mneg));
+          if (partial && key0 + piece * 32 + i >= kv_len) e = 0.0f;
+          pr[i] = e;
+          sum += e;
+        }
+        const uint32_t half_off = (uint32_t)(piece >> 1) * AT_TILE + row_off;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) hi[e] = split_bf16x2(pr[8 * q + 2 * e], pr[8 * q + 2 * e + 1], lo[e]);
+          const uint32_t chunk = (uint32_t)((piece & 1) * 4 + q);
+          const uint32_t off = half_off + ((chunk ^ swz) << 4);
+          *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (PASSES == 3) *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+      l_run = fmaf(l_run, alpha, sum);
+      tc_fence_before();          // S reads done -> MMA may overwrite S
+      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(s_empty);
+        mbar_arrive(p_full);
+      }
+      // O = O * alpha + PV
+      mbar_wait(pv_full, par);
+      tc_fence_after();
+#pragma unroll
+      for (int piece = 0; piece < 2; ++piece) {
+        uint32_t rr[32];
+        tmem_ld_32x32b_x32(tmem_pv + lane_sel + piece * 32, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[piece * 32 + i] = fmaf(o[piece * 32 + i], alpha, __uint_as_float(rr[i]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pv_empty);
+    }
+
+    const int t = q0 + r;
+    if (t < p.T) {
+      const float inv = 1.0f / l_run;
+      const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          hi[e] = split_bf16x2(o[8 * q + 2 * e] * inv, o[8 * q + 2 * e + 1] * inv, lo[e]);
+        *reinterpret_cast<uint4*>(p.out_hi + off + 8 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (PASSES == 3) *reinterpret_cast<uint4*>(p.out_lo + off + 8 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 6) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+template <int PASSES>
+static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int H, const int* kv_len, void* out_hi,
+                       void* out_lo, cudaStream_t stream) {
+  using S = AttnSmem<PASSES>;
+  const int d = H * AT_DH;
+  CUtensorMap tm_hi, tm_lo;
+  const uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
+  const uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
+  const uint32_t box[3] = {AT_DH, AT_BM, 1};
+  int rc = make_tmap(&tm_hi, qkv_hi, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  tm_lo = tm_hi;
+  if (PASSES == 3) {
+    rc = make_tmap(&tm_lo, qkv_lo, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  AttnParams p;
+  p.T = T;
+  p.d = d;
+  p.kv_len = kv_len;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  auto kern = attn_fwd_kernel<PASSES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
+  kern<<<grid, AT_THREADS, S::TOTAL, stream>>>(tm_hi, tm_lo, p);
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace w2v2
+
+extern "C" int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
+                             int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes,
+                             void* stream) {
+  using namespace w2v2;
+  W2V2_CHECK_ARG(qkv_hi && out_hi, "null pointer");
+  W2V2_CHECK_ARG(head_size == AT_DH, "only head_size == 64 is implemented (base: 768/12, large: 1024/16)");
+  W2V2_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
+  W2V2_CHECK_ARG(passes == 1 || (qkv_lo && out_lo), "3-pass mode needs the lo planes");
+  W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (passes == 1) return launch_attn<1>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, s);
+  return launch_attn<3>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, s);
+}

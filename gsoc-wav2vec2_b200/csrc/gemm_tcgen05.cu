@@ -1,0 +1,424 @@
+// Persistent warp-specialised bf16 GEMM for sm_100a:  D[rows, N] = A[rows, K] * W[N, K]^T  (+ epilogue)
+//
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected lane, tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16)
+//   warp 2      : TMEM allocator (2 accumulator stages of BLOCK_N fp32 columns)
+//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> bias / erf-GELU / residual / mask -> fp32 and/or bf16 hi,lo)
+//
+// The same kernel serves every dense contraction on the Wav2Vec2 path:
+//   * encoder Dense layers (reference: encoder.py:24-31,127-128; feature_extractor.py:94; modeling.py:254)
+//   * the strided Conv1D layers 1..6 as implicit GEMMs (reference: feature_extractor.py:55): in channels-last
+//     layout a k-tap, stride-s window is k*Cin CONTIGUOUS elements whose start advances by s*Cin per frame, so
+//     the A operand is a 3-D TMA tensor map {k*Cin, T_out, B} with an overlapping row stride - no im2col.
+// "Ragged" rows: each batch entry has rows_per_batch valid rows; tiles never straddle two entries, TMA
+// zero-fills rows past the entry and the epilogue masks the stores.
+//
+// PASSES = 3 is the parity mode: operands arrive as bf16 hi/lo planes and the kernel accumulates
+// A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into one fp32 TMEM accumulator (~16 mantissa bits per operand).
+#include "host_util.h"
+#include "w2v2_common.cuh"
+#include "../../include/w2v2.h"
+
+namespace w2v2 {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 256;
+
+struct GemmParams {
+  int num_kb;           // K / 64 (per pass)
+  int kb_split;         // k-blocks >= kb_split are fetched from (k - kb_split*64, row + 1)  [pair-row conv fallback]
+  int rows_per_batch;   // valid rows per batch entry
+  int tiles_per_batch;  // ceil(rows_per_batch / 128)
+  int batch;
+  int n_tiles;          // ceil(N / BLOCK_N)
+  int N;                // valid output columns == leading dimension of every output / residual
+  int gelu;
+  int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [batch*rows_per_batch, N] or null
+  const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
+  float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+
+template <int BLOCK_N>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
+  static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;  // + slack for 1024-byte alignment
+};
+
+template <int BLOCK_N, int PASSES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                         const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
+                         const GemmParams p) {
+  using S = GemmSmem<BLOCK_N>;
+  constexpr int ACC_STAGES = 2;
+  constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N) < 32 ? 32 : (ACC_STAGES * BLOCK_N);
+  static_assert((TMEM_COLS & (TMEM_COLS - 1)) == 0 && TMEM_COLS <= 512, "TMEM columns must be a power of two <= 512");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES);
+  uint64_t* empty_bar = full_bar + GEMM_STAGES;
+  uint64_t* tmem_full = empty_bar + GEMM_STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+
+  const int warp = threadIdx.x >> 5;
+  const int total_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
+  const int total_kb = PASSES * p.num_kb;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tmA_hi);
+    tma_prefetch_desc(&tmB_hi);
+    if (PASSES == 3) {
+      tma_prefetch_desc(&tmA_lo);
+      tma_prefetch_desc(&tmB_lo);
+    }
+  }
+  if (warp == 1 && elect_one()) {
+    for (int i = 0; i < GEMM_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < ACC_STAGES; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int b = m_tile / p.tiles_per_batch;
+        const int t0 = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M;
+        const int n0 = n_tile * BLOCK_N;
+        for (int it = 0; it < total_kb; ++it) {
+          const int pass = (PASSES == 1) ? 0 : it / p.num_kb;
+          const int kb = it - pass * p.num_kb;
+          const CUtensorMap* ma = (pass == 1) ? &tmA_lo : &tmA_hi;
+          const CUtensorMap* mb = (pass == 2) ? &tmB_lo : &tmB_hi;
+          int kc = kb * GEMM_BLOCK_K, trow = t0;
+          if (kb >= p.kb_split) {
+            kc = (kb - p.kb_split) * GEMM_BLOCK_K;
+            trow = t0 + 1;
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * S::STAGE_BYTES;
+          uint8_t* sb = sa + S::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          tma_load_3d(sa, ma, &full_bar[stage], kc, trow, b);
+          tma_load_2d(sb, mb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if (++stage == GEMM_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (elect_one()) {
+      constexpr uint32_t idesc = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int it = 0; it < total_kb; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t da = desc_kmajor_sw128(sa);
+          const uint64_t db = desc_kmajor_sw128(sa + S::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            // +32 bytes per UMMA_K step inside the swizzle row -> +2 in the (addr >> 4) field
+            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == GEMM_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (++acc == ACC_STAGES) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------------ epilogue
+    const int ew = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may read
+    const int lane = lane_id();
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int b = m_tile / p.tiles_per_batch;
+      const int t = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M + ew * 32 + lane;
+      const int n0 = n_tile * BLOCK_N;
+      const bool row_ok = t < p.rows_per_batch;
+      const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
+      const size_t orow = (size_t)b * p.rows_per_batch + t;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(taddr + c0, r);
+        tmem_ld_wait();
+        const int n = n0 + c0;
+        if (row_ok && n < p.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
+          if (p.bias != nullptr) {
+            if (full_chunk) {
+              const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(bp + j);
+                v[4 * j + 0] += bb.x;
+                v[4 * j + 1] += bb.y;
+                v[4 * j + 2] += bb.z;
+                v[4 * j + 3] += bb.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
+            }
+          }
+          if (p.gelu) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+          }
+          if (p.residual != nullptr) {
+            const float* rp = p.residual + orow * p.N + n;
+            if (full_chunk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp) + j);
+                v[4 * j + 0] += rr.x;
+                v[4 * j + 1] += rr.y;
+                v[4 * j + 2] += rr.z;
+                v[4 * j + 3] += rr.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n + j < p.N) v[j] += __ldg(rp + j);
+            }
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+          }
+          if (full_chunk) {
+            if (p.out_f32 != nullptr) {
+              float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.N + n);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            if (p.out_hi != nullptr) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) hi[j] = split_bf16x2(v[2 * j], v[2 * j + 1], lo[j]);
+              uint4* hp = reinterpret_cast<uint4*>(p.out_hi + orow * p.N + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) hp[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              if (p.out_lo != nullptr) {
+                uint4* lp = reinterpret_cast<uint4*>(p.out_lo + orow * p.N + n);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) lp[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (n + j >= p.N) continue;
+              if (p.out_f32 != nullptr) p.out_f32[orow * p.N + n + j] = v[j];
+              if (p.out_hi != nullptr) {
+                const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+                p.out_hi[orow * p.N + n + j] = h;
+                if (p.out_lo != nullptr) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------- host
+thread_local char g_last_error[512] = "";
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box, CUtensorMapSwizzle swz, CUtensorMapDataType dt) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) return fail(-2, "%s: cuTensorMapEncodeTiled entry point unavailable", __func__);
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = enc(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-3, "%s: cuTensorMapEncodeTiled failed (CUresult %ld, rank %ld)", __func__, (long)r, rank);
+  return 0;
+}
+
+template <int BLOCK_N, int PASSES>
+static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
+  using S = GemmSmem<BLOCK_N>;
+  CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  const uint64_t a_dims[3] = {(uint64_t)a->a_row_len, (uint64_t)a->a_rows, (uint64_t)a->batch};
+  const uint64_t a_strides[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)a->a_batch_stride * 2};
+  const uint32_t a_box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+  int rc = make_tmap(&tmA_hi, a->a_hi, 3, a_dims, a_strides, a_box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  tmA_lo = tmA_hi;
+  if (PASSES == 3) {
+    rc = make_tmap(&tmA_lo, a->a_lo, 3, a_dims, a_strides, a_box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  const uint64_t b_dims[2] = {(uint64_t)a->K, (uint64_t)a->w_rows};
+  const uint64_t b_strides[1] = {(uint64_t)a->K * 2};
+  const uint32_t b_box[2] = {GEMM_BLOCK_K, (uint32_t)BLOCK_N};
+  rc = make_tmap(&tmB_hi, a->w_hi, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  tmB_lo = tmB_hi;
+  if (PASSES == 3) {
+    rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+  }
+  GemmParams p;
+  p.num_kb = a->K / GEMM_BLOCK_K;
+  p.kb_split = a->kb_split > 0 ? a->kb_split : p.num_kb;
+  p.rows_per_batch = a->rows_per_batch;
+  p.tiles_per_batch = (a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.batch = a->batch;
+  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
+  p.N = a->N;
+  p.gelu = (a->flags & W2V2_GEMM_GELU) ? 1 : 0;
+  p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
+  p.bias = a->bias;
+  p.residual = a->residual;
+  p.row_valid = a->row_valid;
+  p.out_f32 = a->out_f32;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(a->out_lo);
+
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES>;
+  static bool attr_set = false;  // per template instantiation
+  if (!attr_set) {
+    W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_set = true;
+  }
+  int dev = 0, sms = 0;
+  W2V2_CUDA(cudaGetDevice(&dev));
+  W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int total_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
+  int grid = total_tiles < sms ? total_tiles : sms;
+  if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
+  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace w2v2
+
+extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
+  using namespace w2v2;
+  W2V2_CHECK_ARG(a != nullptr, "args is null");
+  W2V2_CHECK_ARG(a->a_hi && a->w_hi, "A / W pointers must be non-null");
+  W2V2_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3");
+  W2V2_CHECK_ARG(a->passes == 1 || (a->a_lo && a->w_lo), "3-pass mode needs the lo planes");
+  W2V2_CHECK_ARG(a->K > 0 && a->K % GEMM_BLOCK_K == 0, "K must be a positive multiple of 64");
+  W2V2_CHECK_ARG(a->N > 0 && a->rows_per_batch > 0 && a->batch > 0, "N, rows_per_batch, batch must be positive");
+  W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements (16 B)");
+  W2V2_CHECK_ARG(a->a_row_len >= a->K || a->kb_split > 0, "a_row_len must cover K");
+  W2V2_CHECK_ARG(a->out_f32 || a->out_hi, "at least one output is required");
+  W2V2_CHECK_ARG(a->out_lo == nullptr || a->out_hi != nullptr, "out_lo requires out_hi");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int bn = a->block_n;
+  if (bn == 0) bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;
+  W2V2_CHECK_ARG(a->w_rows >= ((a->N + bn - 1) / bn) * bn, "weight matrix must be padded to a multiple of block_n rows");
+  if (a->passes == 1) {
+    switch (bn) {
+      case 256: return launch_gemm<256, 1>(a, s);
+      case 128: return launch_gemm<128, 1>(a, s);
+      case 64: return launch_gemm<64, 1>(a, s);
+      case 32: return launch_gemm<32, 1>(a, s);
+    }
+  } else {
+    switch (bn) {
+      case 256: return launch_gemm<256, 3>(a, s);
+      case 128: return launch_gemm<128, 3>(a, s);
+      case 64: return launch_gemm<64, 3>(a, s);
+      case 32: return launch_gemm<32, 3>(a, s);
+    }
+  }
+  return fail(-1, "%s: unsupported block_n %ld", __func__, bn);
+}
+
+extern "C" const char* w2v2_last_error_string(void) { return w2v2::g_last_error; }
+extern "C" int w2v2_version(void) { return 100; }

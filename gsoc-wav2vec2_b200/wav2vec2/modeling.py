@@ -1,0 +1,470 @@
+"""B200-native Wav2Vec2 behind the reference's Python surface.
+
+``Wav2Vec2Model(config, input_shape)`` / ``Wav2Vec2ForCTC(config, input_shape)`` and
+``model(batch, attention_mask=None, training=False)`` mirror src/wav2vec2/modeling.py:105-255 of
+thevasudevgupta/gsoc-wav2vec2 (same constructor arguments, same call signature, same error and
+warning behaviour, same variable names), but the tensors are ``torch`` CUDA tensors and every op
+of the forward pass is a hand-written sm_100a kernel reached through the C ABI in
+``include/w2v2.h`` (see ``ops.py``).  There is no TensorFlow, no Triton, no eager fallback.
+
+Numerics: the reference computes in fp32.  ``precision="bf16x3"`` (default) feeds the tensor cores
+split-bf16 operands (hi*hi + lo*hi + hi*lo, fp32 accumulation, fp32 residual stream / LayerNorm /
+softmax statistics) and meets the reference's own 1e-3 / 4e-3 parity tolerances;
+``precision="bf16"`` is the single-pass throughput mode whose measured error is reported, not
+claimed to be 1e-3.
+"""
+import logging
+import math
+import os
+from dataclasses import replace
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .config import Wav2Vec2Config
+from .ops import Pair
+from .weights import hf_to_reference, reference_to_hf
+
+logger = logging.getLogger(__name__)
+
+_PRECISIONS = {"bf16": 1, "bf16x3": 3}
+
+
+def _default_precision():
+    return os.environ.get("W2V2_PRECISION", "bf16x3")
+
+
+# ------------------------------------------------------------------------------------------ variables
+def variable_shapes(cfg: Wav2Vec2Config, with_head: bool) -> Dict[str, tuple]:
+    """Reference variable inventory (names as produced by convert_torch_to_tf.py:12-18,38-44, minus
+    the ``:0`` suffix and the outer ``wav2vec2-ctc/`` scope).  Base + CTC head = 213 tensors."""
+    d, ff = cfg.hidden_size, cfg.intermediate_size
+    out = {"wav2vec2/masked_spec_embed": (d,)}
+    cin = 1
+    for i, (c, k) in enumerate(zip(cfg.filter_sizes, cfg.kernal_sizes)):
+        base = f"wav2vec2/feature_extractor/conv_layers/{i}/"
+        out[base + "conv/kernel"] = (k, cin, c)
+        if cfg.conv_bias:
+            out[base + "conv/bias"] = (c,)
+        if cfg.feature_extractor_norm_type == "layer" or i == 0:
+            out[base + "layer_norm/gamma"] = (c,)
+            out[base + "layer_norm/beta"] = (c,)
+        cin = c
+    fp = "wav2vec2/feature_projection/"
+    out[fp + "layer_norm/gamma"] = (cin,)
+    out[fp + "layer_norm/beta"] = (cin,)
+    out[fp + "projection/kernel"] = (cin, d)
+    out[fp + "projection/bias"] = (d,)
+    pc = "wav2vec2/encoder/pos_conv_embed/conv/"
+    out[pc + "weight_v"] = (cfg.num_conv_pos_embeddings, d // cfg.num_conv_pos_embedding_groups, d)
+    out[pc + "weight_g"] = (cfg.num_conv_pos_embeddings, 1, 1)
+    out[pc + "bias"] = (d,)
+    out["wav2vec2/encoder/layer_norm/gamma"] = (d,)
+    out["wav2vec2/encoder/layer_norm/beta"] = (d,)
+    for i in range(cfg.num_layers):
+        base = f"wav2vec2/encoder/layers/{i}/"
+        for n in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            out[base + f"attention/{n}/kernel"] = (d, d)
+            out[base + f"attention/{n}/bias"] = (d,)
+        out[base + "layer_norm/gamma"] = (d,)
+        out[base + "layer_norm/beta"] = (d,)
+        out[base + "feed_forward/intermediate_dense/kernel"] = (d, ff)
+        out[base + "feed_forward/intermediate_dense/bias"] = (ff,)
+        out[base + "feed_forward/output_dense/kernel"] = (ff, d)
+        out[base + "feed_forward/output_dense/bias"] = (d,)
+        out[base + "final_layer_norm/gamma"] = (d,)
+        out[base + "final_layer_norm/beta"] = (d,)
+    if with_head:
+        out["lm_head/kernel"] = (d, cfg.vocab_size)
+        out["lm_head/bias"] = (cfg.vocab_size,)
+    return out
+
+
+def _init_variable(name, shape, gen):
+    """Keras-style defaults: glorot-uniform kernels, zero biases/betas, unit gammas, uniform
+    masked_spec_embed (modeling.py:161-167), weight_g = per-tap norm of weight_v is set by caller."""
+    if name.endswith("gamma"):
+        return torch.ones(shape)
+    if name.endswith("beta") or name.endswith("bias"):
+        return torch.zeros(shape)
+    if name.endswith("masked_spec_embed"):
+        return torch.rand(shape, generator=gen) * 0.1 - 0.05
+    if name.endswith("weight_g"):
+        return torch.ones(shape)
+    receptive = int(math.prod(shape[:-2])) if len(shape) > 2 else 1
+    fan_in, fan_out = receptive * shape[-2], receptive * shape[-1]
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    return (torch.rand(shape, generator=gen) * 2.0 - 1.0) * lim
+
+
+class _Arena:
+    """Named activation buffers, allocated once per shape and reused across calls and layers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, key, shape, dtype):
+        t = self.bufs.get(key)
+        shape = tuple(int(s) for s in shape)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = torch.empty(shape, dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def pair(self, key, shape, lo):
+        return Pair(self.get(key + ".hi", shape, torch.bfloat16), self.get(key + ".lo", shape, torch.bfloat16) if lo else None)
+
+
+def _split(t: torch.Tensor, lo: bool) -> Pair:
+    """Weight packing helper (load time, not on the hot path): fp32 -> bf16 hi (+ lo)."""
+    t = t.contiguous().float()
+    hi = t.to(torch.bfloat16)
+    return Pair(hi, (t - hi.float()).to(torch.bfloat16) if lo else None)
+
+
+# ------------------------------------------------------------------------------------------ base class
+class _B200Model:
+    with_head = False
+
+    def _setup(self, config, input_shape, name, precision, device):
+        if not isinstance(config, Wav2Vec2Config):
+            raise ValueError("`config` must be an instace of `Wave2Vec2Config`")
+        self.config = config
+        self.name = name
+        self.input_shape = input_shape
+        self.precision = precision or _default_precision()
+        if self.precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        if device is None:
+            device = "cuda" if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)
+        self._check_supported(config)
+        gen = torch.Generator().manual_seed(0)
+        self.variables: Dict[str, torch.Tensor] = {}
+        for vname, shape in variable_shapes(config, self.with_head).items():
+            self.variables[vname] = _init_variable(vname, shape, gen).to(self.device)
+        pc = "wav2vec2/encoder/pos_conv_embed/conv/"
+        v = self.variables[pc + "weight_v"]
+        self.variables[pc + "weight_g"] = v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()  # tensorflow_addons.py:45-48
+        self.trainable = {k: True for k in self.variables}
+        self._packed = None
+        self._arena = None
+
+    @staticmethod
+    def _check_supported(cfg):
+        ks, ss, fs = list(cfg.kernal_sizes), list(cfg.strides), list(cfg.filter_sizes)
+        if ks[0] != 10 or ss[0] != 5 or fs[0] != 512:
+            raise ValueError("the sm_100a extractor kernel is built for conv layer 0 = (512 filters, kernel 10, stride 5)")
+        for i in range(1, len(fs)):
+            if (ks[i] * fs[i - 1]) % 64 or fs[i] % 8:
+                raise ValueError(f"conv layer {i}: kernel*in_channels must be a multiple of 64 and filters of 8")
+        if cfg.head_size != 64:
+            raise ValueError("the sm_100a attention kernel is built for head_size 64 (768/12, 1024/16)")
+        cpg = cfg.hidden_size // cfg.num_conv_pos_embedding_groups
+        if cpg % 16 or cpg > 64 or cfg.num_conv_pos_embeddings % 4 or cfg.num_conv_pos_embeddings > 128:
+            raise ValueError("positional conv: channels/group must be 16..64 (multiple of 16), taps <= 128 (multiple of 4)")
+        if cfg.hidden_size % 64 or cfg.intermediate_size % 64 or fs[-1] % 64:
+            raise ValueError("hidden_size, intermediate_size and the last filter size must be multiples of 64")
+        if cfg.is_gelu_approx:
+            raise ValueError("only the exact (erf) GELU of the reference default is implemented")
+
+    # ---------------------------------------------------------------- weights
+    def set_variables(self, values: Dict[str, torch.Tensor], strict=True):
+        """Assign variables by reference name (fp32, reference layouts)."""
+        missing = [k for k in self.variables if k not in values]
+        extra = [k for k in values if k not in self.variables]
+        if strict and missing:
+            raise KeyError(f"missing variables: {missing[:5]} ...")
+        for k, t in values.items():
+            if k in self.variables:
+                if tuple(t.shape) != tuple(self.variables[k].shape):
+                    raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(self.variables[k].shape)}")
+                self.variables[k] = t.detach().to(self.device, torch.float32).contiguous()
+        self._packed = None
+        return missing, extra
+
+    def load_hf_state_dict(self, state_dict, strict=True):
+        """Load a ``transformers`` Wav2Vec2 ``state_dict`` (rules of convert_torch_to_tf.py:88-123)."""
+        return self.set_variables(hf_to_reference(state_dict), strict=strict)
+
+    def hf_state_dict(self):
+        return reference_to_hf(self.variables)
+
+    def save_pretrained(self, save_dir):
+        """config.json + weights (modeling.py:22-27; safetensors instead of tf_model.h5: no h5py here)."""
+        from safetensors.torch import save_file
+        self.config.save_pretrained(save_dir)
+        save_file({k: v.detach().cpu().contiguous() for k, v in self.variables.items()},
+                  os.path.join(save_dir, "model.safetensors"))
+
+    @classmethod
+    def from_pretrained(cls, model_id, **config_kwargs):
+        """Local-directory loader (modeling.py:42-84).  Hub download is network I/O and out of scope:
+        a missing directory raises the reference's ValueError."""
+        from safetensors.torch import load_file
+        if not os.path.isdir(model_id):
+            raise ValueError(f"Couldn't download model weights from https://huggingface.co/{model_id}")
+        print(f"Loading weights locally from `{model_id}`")
+        input_shape = config_kwargs.pop("input_shape", (1, 2048))
+        precision = config_kwargs.pop("precision", None)
+        config = Wav2Vec2Config.from_json(os.path.join(model_id, "config.json"))
+        config = replace(config, **config_kwargs)
+        model = cls(config, input_shape=input_shape, precision=precision)
+        model.set_variables(load_file(os.path.join(model_id, "model.safetensors")))
+        print("Total number of loaded variables:", len(model.variables))
+        return model
+
+    def freeze_feature_extractor(self):
+        """modeling.py:211-214 - marks the conv stack non-trainable."""
+        for k in self.trainable:
+            if "/feature_extractor/" in k:
+                self.trainable[k] = False
+
+    # ---------------------------------------------------------------- packing (kernel layouts)
+    def _pack(self):
+        cfg, v, lo = self.config, self.variables, _PRECISIONS[self.precision] == 3
+        dev = self.device
+        P = {}
+        # conv 0: TF [10,1,C] -> [10][C] fp32
+        P["conv0.w"] = v["wav2vec2/feature_extractor/conv_layers/0/conv/kernel"].reshape(cfg.kernal_sizes[0], -1).contiguous()
+        for i in range(1, len(cfg.filter_sizes)):
+            kern = v[f"wav2vec2/feature_extractor/conv_layers/{i}/conv/kernel"]      # [k, cin, cout]
+            k, cin, cout = kern.shape
+            P[f"conv{i}.w"] = _split(kern.permute(2, 0, 1).reshape(cout, k * cin), lo)  # W[cout][j*cin+ci]
+        P["proj.w"] = _split(v["wav2vec2/feature_projection/projection/kernel"].t(), lo)
+        # positional conv: fold weight norm (tensorflow_addons.py:16-21), pack [G][k][cpg/8][cpg][8]
+        pc = "wav2vec2/encoder/pos_conv_embed/conv/"
+        wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
+        ss = wv.pow(2).sum(dim=(1, 2), keepdim=True)
+        kern = wv * torch.rsqrt(torch.clamp(ss, min=1e-12)) * wg                     # [k, cpg, d]
+        k, cpg, d = kern.shape
+        G = d // cpg
+        packed = kern.reshape(k, cpg // 8, 8, G, cpg).permute(3, 0, 1, 4, 2).contiguous()
+        P["pos.w"] = _split(packed, lo)
+        dh = cfg.head_size
+        scale = dh ** (-0.5)                                                         # encoder.py:28, folded
+        for i in range(cfg.num_layers):
+            base = f"wav2vec2/encoder/layers/{i}/attention/"
+            wq, wk, wv_ = (v[base + f"{n}_proj/kernel"] for n in ("q", "k", "v"))
+            bq, bk, bv = (v[base + f"{n}_proj/bias"] for n in ("q", "k", "v"))
+            P[f"l{i}.qkv.w"] = _split(torch.cat([wq.t() * scale, wk.t(), wv_.t()], 0), lo)   # [3d, d]
+            P[f"l{i}.qkv.b"] = torch.cat([bq * scale, bk, bv]).contiguous()
+            P[f"l{i}.out.w"] = _split(v[base + "out_proj/kernel"].t(), lo)
+            ff = f"wav2vec2/encoder/layers/{i}/feed_forward/"
+            P[f"l{i}.ff1.w"] = _split(v[ff + "intermediate_dense/kernel"].t(), lo)
+            P[f"l{i}.ff2.w"] = _split(v[ff + "output_dense/kernel"].t(), lo)
+        if self.with_head:
+            w = v["lm_head/kernel"].t().contiguous()                                 # [V, d]
+            V = w.shape[0]
+            Vp = ((V + 31) // 32) * 32
+            if Vp != V:
+                w = torch.cat([w, torch.zeros(Vp - V, w.shape[1], device=dev)], 0)
+            P["lm.w"] = _split(w, lo)
+        self._packed = P
+        return P
+
+    # ---------------------------------------------------------------- forward
+    def _frame_lengths(self, attention_mask, T):
+        """modeling.py:201-206: per-utterance frame count from the sample mask."""
+        n = attention_mask.to(self.device).to(torch.int64).sum(-1)
+        for k, s in zip(self.config.kernal_sizes, self.config.strides):
+            n = 1 + torch.div(n - k, s, rounding_mode="floor")
+        return torch.clamp(n, min=0, max=T).to(torch.int32).contiguous()
+
+    def _encode(self, batch, attention_mask, training):
+        cfg, v = self.config, self.variables
+        if not torch.cuda.is_available() or self.device.type != "cuda":
+            raise RuntimeError("Wav2Vec2 forward needs a CUDA device: the sm_100a kernels have no CPU fallback")
+        if training and cfg.dropout:
+            raise NotImplementedError("training-mode forward (dropout RNG) is not built yet; use dropout=0")
+        P = self._packed or self._pack()
+        if self._arena is None:
+            self._arena = _Arena(self.device)
+        A = self._arena
+        passes = _PRECISIONS[self.precision]
+        lo = passes == 3
+        x = batch.to(self.device, torch.float32).contiguous()
+        if x.dim() != 2:
+            raise ValueError("batch must have shape (batch_size, seqlen)")
+        B, L = x.shape
+        frames = cfg.conv_frames(L)
+        if frames[-1] < 1:
+            raise ValueError(f"input of {L} samples is shorter than the extractor's receptive field")
+        f32, C0 = torch.float32, cfg.filter_sizes[0]
+        eps = cfg.layer_norm_eps
+        fe = "wav2vec2/feature_extractor/conv_layers/"
+        layer_norm_convs = cfg.feature_extractor_norm_type == "layer"
+        nconv = len(cfg.filter_sizes)
+
+        # ---- extractor layer 0 (feature_extractor.py:54-59)
+        T0 = frames[0]
+        act = A.pair("c0", (B, T0, C0), lo)
+        if not layer_norm_convs:
+            stats = A.get("c0.stats", (B, 65), torch.float64)
+            fw = A.get("c0.fw", (B, 10, C0), f32)
+            fb = A.get("c0.fb", (B, C0), f32)
+            ops.wave_stats(x, stats)
+            ops.conv0_fold(P["conv0.w"], v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], stats, B, L, fw, fb, 1e-5)
+            ops.conv0(x, fw, 10 * C0, fb, C0, True, out_hi=act.hi, out_lo=act.lo, channels=C0)
+        else:
+            raw_elems = max(B * t * c for t, c in zip(frames, cfg.filter_sizes))
+            raw_flat = A.get("conv.raw", (raw_elems,), f32)   # pre-norm conv output, reused by every layer
+            raw = raw_flat[: B * T0 * C0].view(B * T0, C0)
+            ops.conv0(x, P["conv0.w"], 0, v.get(fe + "0/conv/bias") if cfg.conv_bias else None, 0, False, out_f32=raw, channels=C0)
+            ops.ln_rows(raw, v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], 1e-5, B * T0, C0, gelu=True,
+                        out_hi=act.hi, out_lo=act.lo)
+        # ---- extractor layers 1.. as implicit GEMMs
+        last_f32 = None
+        for i in range(1, nconv):
+            k, s = cfg.kernal_sizes[i], cfg.strides[i]
+            cin, cout, Tin, Tout = cfg.filter_sizes[i - 1], cfg.filter_sizes[i], frames[i - 1], frames[i]
+            last = i == nconv - 1
+            bias = v[fe + f"{i}/conv/bias"] if cfg.conv_bias else None
+            geo = dict(K=k * cin, N=cout, rows_per_batch=Tout, batch=B, a_row_len=k * cin, a_rows=Tout,
+                       a_row_stride=s * cin, a_batch_stride=Tin * cin, passes=passes)
+            if layer_norm_convs:
+                raw = raw_flat[: B * Tout * cout].view(B * Tout, cout)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, out_f32=raw, **geo)
+                g_, b_ = v[fe + f"{i}/layer_norm/gamma"], v[fe + f"{i}/layer_norm/beta"]
+                if last:
+                    last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
+                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=True, out_f32=last_f32)
+                else:
+                    nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
+                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=True, out_hi=nxt.hi, out_lo=nxt.lo)
+                    act = nxt
+            elif last:
+                last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, out_f32=last_f32, **geo)
+            else:
+                nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, out_hi=nxt.hi, out_lo=nxt.lo, **geo)
+                act = nxt
+        T, Cl, d = frames[-1], cfg.filter_sizes[-1], cfg.hidden_size
+        M = B * T
+
+        # ---- feature projection (feature_extractor.py:92-95) + frame mask (modeling.py:201-206, encoder.py:253)
+        kv_len = None
+        if attention_mask is not None:
+            kv_len = self._frame_lengths(attention_mask, T)
+        fp = "wav2vec2/feature_projection/"
+        pn = A.pair("proj.in", (M, Cl), lo)
+        ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo)
+        h_f32 = A.get("h.f32", (M, d), f32)
+        h = A.pair("h", (M, d), lo)
+        spec = training and cfg.apply_spec_augment
+        ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"],
+                 row_valid=None if spec else kv_len, out_f32=h_f32, out_hi=h.hi, out_lo=h.lo, passes=passes)
+        if spec:  # modeling.py:193-199 (training only; host-side RNG like the reference's numpy RNG)
+            from .spec_augment import apply_spec_augmentation
+            hv = apply_spec_augmentation(h_f32.view(B, T, d), v["wav2vec2/masked_spec_embed"], cfg.mask_time_prob,
+                                         cfg.mask_time_length)
+            if kv_len is not None:
+                keep = torch.arange(T, device=self.device)[None, :] < kv_len[:, None]
+                hv = torch.where(keep[:, :, None], hv, torch.zeros((), device=self.device))
+            h_f32.copy_(hv.reshape(M, d))
+            sp = ops.split_bf16(h_f32, lo)
+            h.hi.copy_(sp.hi)
+            if lo:
+                h.lo.copy_(sp.lo)
+
+        # ---- encoder (encoder.py:251-276)
+        enc = "wav2vec2/encoder/"
+        pre = cfg.attention_norm_type == "prenorm"
+        y = A.get("y.f32", (M, d), f32)
+        ops.posconv(h, P["pos.w"], v[enc + "pos_conv_embed/conv/bias"], h_f32, y, B, T, d,
+                    cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes)
+        xs_f32 = A.get("x.f32", (M, d), f32)      # residual stream
+        xs = A.pair("x", (M, d), lo)              # GEMM operand view of the (normalised) stream
+        if pre:
+            xs_f32, y = y, xs_f32                 # stream = h + posconv(h); LN happens inside the layers
+        else:
+            ops.ln_rows(y, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=xs_f32,
+                        out_hi=xs.hi, out_lo=xs.lo)
+        qkv = A.pair("qkv", (M, 3 * d), lo)
+        ctx = A.pair("ctx", (M, d), lo)
+        mid = A.pair("mid", (M, cfg.intermediate_size), lo)
+        x1_f32 = A.get("x1.f32", (M, d), f32)
+        H, dh, ffn = cfg.num_heads, cfg.head_size, cfg.intermediate_size
+        for i in range(cfg.num_layers):
+            lb = f"{enc}layers/{i}/"
+            g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
+            g2, b2 = v[lb + "final_layer_norm/gamma"], v[lb + "final_layer_norm/beta"]
+            if pre:
+                ops.ln_rows(xs_f32, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo)
+            ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi,
+                     out_lo=qkv.lo, passes=passes)
+            ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, passes)
+            if pre:
+                # x1 = x + out_proj(ctx)
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
+                         residual=xs_f32, out_f32=x1_f32, passes=passes)
+                ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo)
+            else:
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
+                         residual=xs_f32, out_f32=y, passes=passes)
+                ops.ln_rows(y, g1, b1, eps, M, d, out_f32=x1_f32, out_hi=xs.hi, out_lo=xs.lo)
+            ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M,
+                     bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, out_hi=mid.hi, out_lo=mid.lo,
+                     passes=passes)
+            if pre:
+                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
+                         bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=xs_f32, passes=passes)
+            else:
+                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
+                         bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=y, passes=passes)
+                ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32, out_hi=xs.hi, out_lo=xs.lo)
+        if pre:
+            out_f32 = A.get("enc.out", (M, d), f32)
+            ops.ln_rows(xs_f32, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=out_f32,
+                        out_hi=xs.hi, out_lo=xs.lo)
+            xs_f32 = out_f32
+        return xs_f32, xs, (B, T, d)
+
+    def _warn_mask(self, attention_mask):
+        # modeling.py:183-186
+        if self.config.is_robust and attention_mask is None:
+            logger.warning("You should pass `attention_mask` when working with Wav2Vec2 new checkpoints")
+        elif not self.config.is_robust and attention_mask is not None:
+            logger.warning("You should not pass `attention_mask` when working with checkpoints based on `wav2vec2-base`")
+
+
+class Wav2Vec2Model(_B200Model):
+    """reference: modeling.py:105-214.  ``model(batch [B,L]) -> [B, T', hidden]`` fp32."""
+    with_head = False
+
+    def __init__(self, config: Wav2Vec2Config, input_shape=(1, 246000), name="wav2vec2", precision=None, device=None):
+        self._setup(config, input_shape, name, precision, device)
+
+    @torch.no_grad()
+    def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
+        self._warn_mask(attention_mask)
+        x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
+        return x_f32.view(B, T, d).clone()
+
+    call = __call__
+
+
+class Wav2Vec2ForCTC(_B200Model):
+    """Wav2Vec2 with a CTC head (reference: modeling.py:217-255). ``model(batch) -> [B, T', vocab]``."""
+    with_head = True
+
+    def __init__(self, config: Wav2Vec2Config, input_shape=(1, 246000), name="wav2vec2-ctc", precision=None, device=None):
+        if not isinstance(config, Wav2Vec2Config):
+            raise ValueError("`config` must be an instace of `Wave2Vec2Config`.")
+        self._setup(config, input_shape, name, precision, device)
+        self.pad_id = config.pad_id
+
+    @torch.no_grad()
+    def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
+        self._warn_mask(attention_mask)
+        _, xs, (B, T, d) = self._encode(batch, attention_mask, training)
+        V = self.config.vocab_size
+        logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device)
+        ops.gemm(xs, self._packed["lm.w"], K=d, N=V, rows_per_batch=B * T, bias=self.variables["lm_head/bias"],
+                 out_f32=logits, passes=_PRECISIONS[self.precision], block_n=32)
+        return logits
+
+    call = __call__

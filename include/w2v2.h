@@ -1,0 +1,149 @@
+/* libw2v2_sm100.so - C ABI of the B200 (sm_100a) Wav2Vec2 forward / CTC kernels.
+ *
+ * The reference (thevasudevgupta/gsoc-wav2vec2) has NO native plugin/FFI layer: every op on its
+ * hot path is a Keras layer or tf.* call inside the un-vendored tensorflow==2.5 wheel.  Each entry
+ * point below therefore replaces one group of those op call sites (cited per function as
+ * reference file:line) underneath the reference's own Python surface
+ * (src/wav2vec2/__init__.py:1-4: Wav2Vec2Config / Wav2Vec2Model / Wav2Vec2ForCTC / CTCLoss).
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers owned by the caller (no hidden allocation, no ownership
+ *     transfer); activations are channels-last row-major [B, T, C] like the reference
+ *     (modeling.py:188); "hi"/"lo" are bf16 planes with value ~= hi + lo (lo may be NULL where
+ *     documented: single-pass bf16 mode);
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on that stream,
+ *     stateless and thread-safe;
+ *   - return 0 on success, < 0 on an argument error, > 0 = cudaError_t.  The message for the last
+ *     failure on the calling thread is w2v2_last_error_string().  There is no CPU fallback.
+ */
+#ifndef W2V2_H_
+#define W2V2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int w2v2_version(void);
+const char* w2v2_last_error_string(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense contraction  D[b, t, :] = epilogue( A[b, t, :K] . W[n, :K] )   (tcgen05 / TMA / TMEM)
+ * Replaces: tf.keras.layers.Dense at encoder.py:15-18,24-31 (q/k/v/out), encoder.py:99-104,127-128
+ * (FFN), feature_extractor.py:89,94 (projection), modeling.py:231,254 (lm_head); and
+ * tf.keras.layers.Conv1D for extractor layers 1..6 at feature_extractor.py:31-37,55 as an implicit
+ * GEMM (A rows = overlapping k*Cin windows of the channels-last input).
+ * ------------------------------------------------------------------------------------------- */
+#define W2V2_GEMM_GELU 1u /* exact-erf GELU after bias (feature_extractor.py:58, encoder.py:127) */
+
+typedef struct w2v2_gemm_args {
+  /* A operand: bf16 planes, logical shape [batch][a_rows][a_row_len], element strides given. */
+  const void* a_hi;
+  const void* a_lo;        /* NULL unless passes == 3 */
+  int64_t a_row_len;       /* elements addressable in one row (>= K; conv: k*Cin) */
+  int64_t a_rows;          /* rows addressable per batch entry (TMA bound; >= rows_per_batch) */
+  int64_t a_row_stride;    /* elements between consecutive rows (conv: stride*Cin - rows overlap) */
+  int64_t a_batch_stride;  /* elements between batch entries */
+  /* W operand: bf16 [w_rows][K] row-major ("K-major"), w_rows >= N rounded up to block_n. */
+  const void* w_hi;
+  const void* w_lo;        /* NULL unless passes == 3 */
+  int32_t w_rows;
+  int32_t K;               /* multiple of 64 */
+  int32_t N;               /* output columns; leading dimension of residual and outputs */
+  int32_t rows_per_batch;  /* output rows per batch entry */
+  int32_t batch;
+  int32_t passes;          /* 1 = bf16 operands; 3 = split-bf16 (hi*hi + lo*hi + hi*lo) */
+  int32_t kb_split;        /* 0, or: 64-wide k-blocks >= kb_split come from (k - 64*kb_split, row+1) */
+  int32_t block_n;         /* 0 = auto (256/128/64/32) */
+  int32_t max_ctas;        /* 0 = one persistent CTA per SM */
+  uint32_t flags;          /* W2V2_GEMM_* */
+  const float* bias;       /* [N] or NULL */
+  const float* residual;   /* fp32 [batch*rows_per_batch][N] or NULL, added after bias/GELU */
+  const int32_t* row_valid;/* [batch] or NULL: rows t >= row_valid[b] are stored as zeros
+                              (padded frames, encoder.py:253) */
+  float* out_f32;          /* any subset of the three outputs; out_lo requires out_hi */
+  void* out_hi;
+  void* out_lo;
+} w2v2_gemm_args;
+
+int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Extractor layer 0: Conv1D(k=10, s=5, Cin=1, no bias) + GroupNorm(groups == channels) + GELU.
+ * Replaces feature_extractor.py:31-37,40-47,54-59 and GroupNormalization._apply_normalization,
+ * tensorflow_addons.py:207-231 (per-(b,c) mean / biased variance over TIME, eps 1e-5).
+ *   1. w2v2_wave_stats : stats[b][0:10] = sum_t x[5t+j];  stats[b][10:65] = upper triangle of
+ *      G[i][j] = sum_t x[5t+i] x[5t+j]  (fp64, T0 = 1 + (L-10)/5 windows).
+ *   2. w2v2_conv0_fold : folds mean / rstd / gamma / beta into per-(b,c) weights [B][10][C] and
+ *      bias [B][C]  (sum_t y = w.s, sum_t y^2 = w^T G w because Cin == 1).
+ *   3. w2v2_conv0      : y = gelu?(bias + sum_j w[j][c] x[5t+j]) -> bf16 hi(/lo) or fp32, written once.
+ *      With weights_batch_stride == 0 and the raw kernel it is the plain conv (+bias) used by the
+ *      "layer"-norm extractor variant (feature_extractor.py:48-50), followed by w2v2_ln_rows.
+ * ------------------------------------------------------------------------------------------- */
+int w2v2_wave_stats(const float* wave, int batch, int num_samples, double* stats /*[batch][65]*/, void* stream);
+int w2v2_conv0_fold(const float* kernel /*[10][C] (TF layout [k,1,C])*/, const float* gamma, const float* beta,
+                    const double* stats, int batch, int num_samples, int channels, float eps,
+                    float* folded_w /*[batch][10][C]*/, float* folded_b /*[batch][C]*/, void* stream);
+int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, const float* weights,
+               int weights_batch_stride, const float* bias /*or NULL*/, int bias_batch_stride, int gelu,
+               float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* LayerNormalization over the last axis (biased variance) with optional GELU; fp32 in, outputs
+ * fp32 and/or bf16 hi(/lo).  Replaces tf.keras.layers.LayerNormalization at encoder.py:96-108,
+ * 116,121,126,132,232-234,268,275 and feature_extractor.py:50,86-88,93. */
+int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
+                 float* out_f32, void* out_hi, void* out_lo, void* stream);
+
+/* fp32 -> bf16 hi(/lo) planes (weight packing). */
+int w2v2_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-head attention core on the packed projection qkv[b][t][0:3d] = [q | k | v] (q pre-scaled):
+ * ctx[b][t][h*64:(h+1)*64] = softmax_k(q.k) v.  Replaces TransformerAttention.get_context and
+ * _prepare_either_qkv, encoder.py:34-54, and the additive key mask of encoder.py:256-263
+ * (kv_len[b] = number of real frames, or NULL).
+ * ------------------------------------------------------------------------------------------- */
+int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
+                  const int32_t* kv_len, void* out_hi, void* out_lo, int passes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Positional convolution + GELU + residual: out = resid + gelu(bias + grouped_conv_k(x)).
+ * Replaces PositionalConvEmbedding.call encoder.py:177-181, Conv1DWithWeightNorm.call
+ * tensorflow_addons.py:50-53 (weight norm folded into w by the host) and encoder.py:265.
+ * w_hi/w_lo: bf16 packed [groups][ktaps][cpg/8][cpg(out)][8(in)].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct w2v2_posconv_args {
+  const void* x_hi;      /* bf16 [batch][frames][hidden] */
+  const void* x_lo;      /* NULL unless passes == 3 */
+  const void* w_hi;
+  const void* w_lo;      /* NULL unless passes == 3 */
+  const float* bias;     /* [hidden] */
+  const float* resid;    /* fp32 [batch][frames][hidden] */
+  float* out_f32;        /* fp32 [batch][frames][hidden] */
+  int32_t batch, frames, hidden, groups, ktaps, passes;
+} w2v2_posconv_args;
+
+int w2v2_posconv(const w2v2_posconv_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CTC loss and its gradient w.r.t. the unnormalised logits.  Replaces tf.nn.ctc_loss as called by
+ * CTCLoss.call, losses.py:29-45: blank = pad_id, label_length = #labels != pad, logit_length =
+ * frames for every utterance, per-utterance negative log-likelihood scaled by `scale`
+ * (= 1 / division_factor); the caller sums over the batch (Keras SUM reduction, losses.py:6).
+ * workspace: w2v2_ctc_workspace_bytes(batch, frames, max_label_len) bytes.  grad_logits may be NULL.
+ * ------------------------------------------------------------------------------------------- */
+int64_t w2v2_ctc_workspace_bytes(int batch, int frames, int max_label_len);
+int w2v2_ctc_loss(const float* logits /*[batch][frames][vocab]*/, const int32_t* labels /*[batch][max_label_len]*/,
+                  int batch, int frames, int vocab, int max_label_len, int blank, float scale, void* workspace,
+                  int64_t* reserved, float* loss_per_sample /*[batch]*/, float* grad_logits, void* stream);
+
+/* Greedy CTC decode, device part: ids[r] = argmax_k logits[r][k] (first maximum), the input of
+ * Wav2Vec2Processor.decode (processor.py:71-89; tests/test_wav2vec2.py:159-165). */
+int w2v2_frame_argmax(const float* logits, int64_t rows, int vocab, int32_t* ids, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2V2_H_ */

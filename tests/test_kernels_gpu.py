@@ -1,0 +1,222 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) against torch fp32 / the oracle."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import w2v2_oracle as O          # noqa: E402  (checker only)
+from wav2vec2 import ops                      # noqa: E402
+from wav2vec2.config import Wav2Vec2Config    # noqa: E402
+from wav2vec2.ops import Pair                 # noqa: E402
+
+DEV = "cuda"
+
+
+def _pair(x, lo):
+    hi = x.to(torch.bfloat16)
+    return Pair(hi.contiguous(), (x - hi.float()).to(torch.bfloat16).contiguous() if lo else None)
+
+
+def _eff(p: Pair, passes):
+    return p.hi.float() if passes == 1 else p.hi.float() + p.lo.float()
+
+
+def _ref_gemm(a: Pair, w: Pair, passes):
+    """What the kernel computes: hi*hi (+ lo*hi + hi*lo) with fp32 accumulation (fp64 here)."""
+    ah, wh = a.hi.double(), w.hi.double()
+    r = ah @ wh.t()
+    if passes == 3:
+        r = r + a.lo.double() @ wh.t() + ah @ w.lo.double().t()
+    return r.float()
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("N,block_n", [(256, 256), (384, 128), (192, 64), (32, 32), (512, 0)])
+def test_gemm_plain(passes, N, block_n):
+    torch.manual_seed(0)
+    M, K = 300, 192
+    a = _pair(torch.randn(M, K, device=DEV), passes == 3)
+    w = _pair(torch.randn(N, K, device=DEV) / math.sqrt(K), passes == 3)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, K=K, N=N, rows_per_batch=M, out_f32=out, passes=passes, block_n=block_n)
+    torch.cuda.synchronize()
+    ref = _ref_gemm(a, w, passes)
+    err = (out - ref).abs().max().item()
+    print(f"gemm N={N} bn={block_n} passes={passes}: max err {err:.3e}")
+    assert err < 2e-4
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+def test_gemm_epilogue(passes):
+    torch.manual_seed(1)
+    B, T, K, N = 3, 200, 128, 256
+    lo = passes == 3
+    a = _pair(torch.randn(B * T, K, device=DEV), lo)
+    w = _pair(torch.randn(N, K, device=DEV) / math.sqrt(K), lo)
+    bias = torch.randn(N, device=DEV)
+    resid = torch.randn(B * T, N, device=DEV)
+    valid = torch.tensor([200, 57, 0], dtype=torch.int32, device=DEV)
+    o32 = torch.full((B * T, N), float("nan"), device=DEV)
+    ohi = torch.zeros(B * T, N, dtype=torch.bfloat16, device=DEV)
+    olo = torch.zeros(B * T, N, dtype=torch.bfloat16, device=DEV)
+    ops.gemm(a, w, K=K, N=N, rows_per_batch=T, batch=B, bias=bias, residual=resid, row_valid=valid, gelu=True,
+             out_f32=o32, out_hi=ohi, out_lo=olo, passes=passes)
+    torch.cuda.synchronize()
+    ref = O.gelu_erf((_ref_gemm(a, w, passes) + bias).cpu()).to(DEV) + resid
+    keep = (torch.arange(T, device=DEV)[None, :] < valid[:, None]).reshape(-1, 1)
+    ref = torch.where(keep, ref, torch.zeros((), device=DEV))
+    assert (o32 - ref).abs().max().item() < 3e-4
+    assert (ohi.float() + olo.float() - o32).abs().max().item() < 2e-4      # hi + lo carries ~16 bits
+    assert (ohi.float() - o32).abs().max().item() < 0.05
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("k,s,Tin", [(3, 2, 301), (2, 2, 290), (3, 2, 64)])
+def test_gemm_as_strided_conv(passes, k, s, Tin):
+    """Extractor layers 1..6 (feature_extractor.py:55) as an implicit GEMM with overlapping rows."""
+    torch.manual_seed(2)
+    B, C = 2, 512
+    lo = passes == 3
+    Tout = 1 + (Tin - k) // s
+    x = _pair(torch.randn(B, Tin, C, device=DEV), lo)
+    kern = torch.randn(k, C, C, device=DEV) / math.sqrt(k * C)             # TF layout [k, cin, cout]
+    w = _pair(kern.permute(2, 0, 1).reshape(C, k * C).contiguous(), lo)
+    out = torch.full((B, Tout, C), float("nan"), device=DEV)
+    geo = dict(K=k * C, N=C, rows_per_batch=Tout, batch=B, a_row_len=k * C, a_rows=Tout, a_row_stride=s * C,
+               a_batch_stride=Tin * C, passes=passes)
+    ops.gemm(x, w, gelu=True, out_f32=out, **geo)
+    torch.cuda.synchronize()
+    w_eff = _eff(w, passes).reshape(C, k, C).permute(1, 2, 0)              # back to [k, cin, cout]
+    ref = O.gelu_erf(O.conv1d_valid(_eff(x, passes).cpu(), w_eff.cpu(), None, stride=s)).to(DEV)
+    err = (out - ref).abs().max().item()
+    print(f"conv-as-gemm k={k} s={s} Tin={Tin} passes={passes}: max err {err:.3e}")
+    # 3-pass drops the lo*lo term (~2^-16 relative): tolerance covers it
+    assert err < (2e-3 if passes == 1 else 2e-4)
+    if k == 3 and Tin % 2 == 0:
+        # pair-row addressing (kb_split): frames (2t, 2t+1) from row t, frame 2t+2 from row t+1 - same numbers
+        out2 = torch.full((B, Tout, C), float("nan"), device=DEV)
+        geo2 = dict(geo, a_row_len=2 * C, a_rows=Tin // 2, a_row_stride=2 * C, kb_split=2 * C // 64)
+        ops.gemm(x, w, gelu=True, out_f32=out2, **geo2)
+        torch.cuda.synchronize()
+        assert (out2 - out).abs().max().item() < 1e-5
+
+
+def test_ln_rows():
+    torch.manual_seed(3)
+    for d in (512, 768, 1024):
+        x = torch.randn(1000, d, device=DEV) * 3 + 1
+        g, b = torch.randn(d, device=DEV), torch.randn(d, device=DEV)
+        o32 = torch.empty_like(x)
+        ohi = torch.empty(1000, d, dtype=torch.bfloat16, device=DEV)
+        olo = torch.empty_like(ohi)
+        ops.ln_rows(x, g, b, 1e-5, 1000, d, out_f32=o32, out_hi=ohi, out_lo=olo)
+        ref = O.layer_norm(x.cpu().double(), g.cpu().double(), b.cpu().double(), 1e-5).float().to(DEV)
+        assert (o32 - ref).abs().max().item() < 2e-5
+        assert (ohi.float() + olo.float() - o32).abs().max().item() < 1e-4
+        ops.ln_rows(x, g, b, 1e-5, 1000, d, gelu=True, out_f32=o32)
+        assert (o32 - O.gelu_erf(ref.cpu()).to(DEV)).abs().max().item() < 3e-5
+
+
+@pytest.mark.parametrize("L", [46797, 16000, 1210])
+def test_conv0_groupnorm_gelu(L):
+    """Layer 0: conv + GroupNorm over time + GELU from waveform statistics (tensorflow_addons.py:207-231)."""
+    torch.manual_seed(4)
+    B, C = 3, 512
+    x = torch.randn(B, L)
+    x[1] = x[1] * 0.3 + 0.05
+    x[2, L // 2:] = 0.0                                         # zero padding enters the statistics (no mask in base)
+    kern = torch.randn(10, 1, C) * 0.3
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    ref = O.gelu_erf(O.group_norm_per_channel(O.conv1d_valid(x[:, :, None], kern, None, stride=5), gamma, beta, 1e-5))
+    T0 = ref.shape[1]
+    xd = x.to(DEV)
+    stats = torch.empty(B, 65, dtype=torch.float64, device=DEV)
+    fw, fb = torch.empty(B, 10, C, device=DEV), torch.empty(B, C, device=DEV)
+    ops.wave_stats(xd, stats)
+    ops.conv0_fold(kern.reshape(10, C).to(DEV), gamma.to(DEV), beta.to(DEV), stats, B, L, fw, fb)
+    hi = torch.empty(B, T0, C, dtype=torch.bfloat16, device=DEV)
+    lo = torch.empty_like(hi)
+    ops.conv0(xd, fw, 10 * C, fb, C, True, out_hi=hi, out_lo=lo)
+    torch.cuda.synchronize()
+    got = (hi.float() + lo.float()).cpu()
+    err = (got - ref).abs().max().item()
+    print(f"conv0 L={L}: max err {err:.3e} (|ref| max {ref.abs().max():.2f})")
+    assert err < 2e-4
+    assert (hi.float().cpu() - ref).abs().max().item() < 0.04   # bf16 rounding of O(5) values
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("T", [145, 768, 49])
+def test_attention(passes, T):
+    torch.manual_seed(5)
+    B, H, dh = 2, 4, 64
+    d = H * dh
+    lo = passes == 3
+    qkv = _pair(torch.randn(B, T, 3 * d, device=DEV) * 1.5, lo)
+    kv_len = torch.tensor([T, max(1, T - 37)], dtype=torch.int32, device=DEV)
+    out = Pair(torch.zeros(B, T, d, dtype=torch.bfloat16, device=DEV), torch.zeros(B, T, d, dtype=torch.bfloat16, device=DEV))
+    ops.attn_fwd(qkv, B, T, H, dh, kv_len, out, passes)
+    torch.cuda.synchronize()
+    x = _eff(qkv, passes).double().cpu()
+    q, k, v = (t.reshape(B, T, H, dh).permute(0, 2, 1, 3) for t in x.split(d, dim=-1))
+    s = q @ k.transpose(-1, -2)
+    mask = torch.arange(T)[None, :] >= kv_len.cpu()[:, None]
+    s = s + mask[:, None, None, :] * -10000.0                   # encoder.py:256-263
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, T, d).float()
+    got = (out.hi.float() + (out.lo.float() if lo else 0)).cpu()
+    err = (got - ref).abs().max().item()
+    print(f"attention T={T} passes={passes}: max err {err:.3e}")
+    assert err < (2e-2 if passes == 1 else 3e-4)
+
+
+@pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("T,d,groups", [(145, 768, 16), (768, 768, 16), (300, 1024, 16)])
+def test_posconv(passes, T, d, groups):
+    torch.manual_seed(6)
+    B, k = 2, 128
+    lo = passes == 3
+    cpg = d // groups
+    x32 = torch.randn(B, T, d, device=DEV)
+    x = _pair(x32, lo)
+    kern = torch.randn(k, cpg, d, device=DEV) / math.sqrt(k * cpg)       # already weight-normalised, TF layout
+    wp = _pair(kern.reshape(k, cpg // 8, 8, groups, cpg).permute(3, 0, 1, 4, 2).contiguous(), lo)
+    bias = torch.randn(d, device=DEV) * 0.1
+    out = torch.full((B, T, d), float("nan"), device=DEV)
+    ops.posconv(x, wp, bias, x32, out, B, T, d, groups, k, passes)
+    torch.cuda.synchronize()
+    w_eff = _eff(wp, passes).permute(1, 2, 4, 0, 3).reshape(k, cpg, d)    # undo the packing
+    xe = _eff(x, passes).cpu()
+    conv = O.conv1d_valid(F.pad(xe, (0, 0, k // 2, k // 2)), w_eff.cpu(), bias.cpu(), 1, groups)[:, :-1]
+    ref = x32.cpu() + O.gelu_erf(conv)
+    err = (out.cpu() - ref).abs().max().item()
+    print(f"posconv T={T} d={d} passes={passes}: max err {err:.3e}")
+    assert err < (3e-3 if passes == 1 else 3e-4)
+
+
+def test_ctc_loss_and_grad():
+    torch.manual_seed(7)
+    cfg = Wav2Vec2Config()
+    B, T, V = 3, 120, 32
+    logits = torch.randn(B, T, V) * 2
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 24))).int()
+    labels[1, 10:] = 0
+    labels[2, 5:7] = labels[2, 4]                               # repeated labels
+    loss, grad = ops.ctc_loss(logits.to(DEV), labels.to(DEV), cfg.pad_id, 1.0 / 4.0)
+    torch.cuda.synchronize()
+    ref_total, ref_per = O.ctc_loss(labels, logits, cfg, division_factor=4.0)
+    ref_total2, ref_grad = O.ctc_loss_and_grad(labels.long(), logits, cfg, division_factor=4.0)
+    assert abs(ref_total - ref_total2) < 1e-6 * abs(ref_total)
+    assert abs(loss.sum().item() - ref_total) < 1e-3             # tests/test_wav2vec2.py:235-237 tolerance
+    assert np.allclose(loss.cpu().numpy() * 4.0, np.array(ref_per), atol=1e-3)
+    assert (grad.cpu() - ref_grad.float()).abs().max().item() < 1e-4
+
+
+def test_frame_argmax():
+    torch.manual_seed(8)
+    x = torch.randn(4, 77, 32, device=DEV)
+    assert torch.equal(ops.frame_argmax(x).long(), x.argmax(-1))
