@@ -156,7 +156,9 @@ def test_attention(passes, T):
     B, H, dh = 2, 4, 64
     d = H * dh
     lo = passes == 3
-    qkv = _pair(torch.randn(B, T, 3 * d, device=DEV) * 1.5, lo)
+    raw = torch.randn(B, T, 3 * d, device=DEV) * 1.5
+    raw[:, :, :d] *= dh ** -0.5                                  # q arrives pre-scaled (encoder.py:28 folded into Wq)
+    qkv = _pair(raw, lo)
     kv_len = torch.tensor([T, max(1, T - 37)], dtype=torch.int32, device=DEV)
     out = Pair(torch.zeros(B, T, d, dtype=torch.bfloat16, device=DEV), torch.zeros(B, T, d, dtype=torch.bfloat16, device=DEV))
     ops.attn_fwd(qkv, B, T, H, dh, kv_len, out, passes)
@@ -170,7 +172,7 @@ def test_attention(passes, T):
     got = (out.hi.float() + (out.lo.float() if lo else 0)).cpu()
     err = (got - ref).abs().max().item()
     print(f"attention T={T} passes={passes}: max err {err:.3e}")
-    assert err < (2e-2 if passes == 1 else 3e-4)
+    assert err < (2e-2 if passes == 1 else 1e-4)
 
 
 @pytest.mark.parametrize("passes", [1, 3])
