@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""Headline benchmark: audio-seconds/s of the wav2vec2-base forward (Wav2Vec2ForCTC.__call__) at
+seq=246000, batch 32 per GPU, on N B200s of one node (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+  python bench.py --impl reference ...                            # CPU oracle port of the reference path
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # one rank per GPU (weak scaling, no collective
+                                                                  #  on the data path; NCCL only for barrier/max)
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline,
+breakdown_ms, logits_max_abs_err*).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "gsoc-wav2vec2_b200"))
+
+import torch  # noqa: E402
+
+SAMPLE_RATE = 16000
+CPU_SAMPLE_BATCH = 2
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def flops_forward(cfg, L):
+    """Algorithmic FLOPs (2*MAC) of one utterance, per component."""
+    fr = cfg.conv_frames(L)
+    T, d, ff = fr[-1], cfg.hidden_size, cfg.intermediate_size
+    convs, cin = [], 1
+    for t, c, k in zip(fr, cfg.filter_sizes, cfg.kernal_sizes):
+        convs.append(2.0 * t * c * cin * k)
+        cin = c
+    per_layer = {"qkv": 2.0 * T * d * 3 * d, "out": 2.0 * T * d * d, "attn": 4.0 * T * T * d, "ffn": 4.0 * T * d * ff}
+    other = {"proj": 2.0 * T * cin * d,
+             "posconv": 2.0 * T * d * (d // cfg.num_conv_pos_embedding_groups) * cfg.num_conv_pos_embeddings,
+             "lm_head": 2.0 * T * d * cfg.vocab_size}
+    total = sum(convs) + cfg.num_layers * sum(per_layer.values()) + sum(other.values())
+    return {"convs": convs, "per_layer": per_layer, "other": other, "total": total, "frames": fr}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of the reference path (oracle port; TensorFlow is not installable
+    here), all host threads, on a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    from oracle import w2v2_oracle as O
+    from wav2vec2.config import Wav2Vec2Config
+    cfg = Wav2Vec2Config()
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = O.random_params(cfg, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(CPU_SAMPLE_BATCH, args.seq, generator=g)
+    with torch.no_grad():
+        for _ in range(min(args.warmup, 1)):
+            O.wav2vec2_for_ctc(x, params, cfg)
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.wav2vec2_for_ctc(x, params, cfg)
+        dt = (time.perf_counter() - t0) / steps
+    val = CPU_SAMPLE_BATCH * args.seq / SAMPLE_RATE / dt
+    sample = f"oracle port (torch CPU fp32) on {CPU_SAMPLE_BATCH} x {args.seq} samples per step, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "audio-sec/s", "value": val, "unit": "audio-sec/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"wav2vec2-base inference, seq={args.seq}, CPU sample batch={CPU_SAMPLE_BATCH}"},
+        "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--seq", type=int, default=246000)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from wav2vec2 import Wav2Vec2Config, Wav2Vec2ForCTC, ops
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    cfg = Wav2Vec2Config()
+    B, L = args.batch, args.seq
+    model = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision=args.precision, device=dev).init_random(seed=0)
+    g = torch.Generator().manual_seed(rank)
+    x_host = torch.randn(B, L, generator=g).pin_memory()
+    x = x_host.to(dev)
+    T = cfg.num_frames(L)
+    out_host = torch.empty(B, T, cfg.vocab_size).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    for _ in range(W):
+        model(x)
+    barrier()
+    launches0 = ops.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(K):
+            logits = model(x)
+        e1.record()
+        barrier()
+    launches = ops.LAUNCHES - launches0
+    ms = e0.elapsed_time(e1)
+    # ---------------- end to end through the public API: pinned host input -> logits on the host, every step
+    xd = torch.empty_like(x)
+    for _ in range(2):
+        xd.copy_(x_host, non_blocking=True)
+        out_host.copy_(model(xd), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        xd.copy_(x_host, non_blocking=True)
+        out_host.copy_(model(xd), non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    # ---------------- per-kernel-class device times (CUDA events on the launching stream)
+    breakdown, gemm_ffn1 = profile_classes(model, x, cfg, steps=min(K, 5))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    audio_s = world * B * L / SAMPLE_RATE
+    value = audio_s / (ms / K / 1e3)
+    e2e = audio_s / (ms_e2e / K / 1e3)
+    peaks = _peaks()
+    fl = flops_forward(cfg, L)
+    ffn1_flops = 2.0 * B * T * cfg.hidden_size * cfg.intermediate_size
+    achieved = ffn1_flops / (gemm_ffn1 * 1e-3) / 1e12 if gemm_ffn1 else None
+    result = {
+        "metric": "audio-sec/s", "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32-equivalent operands)",
+        "data": "synthetic",
+        "config": {"workload": f"wav2vec2-base inference (Wav2Vec2ForCTC forward), batch={B}/GPU, seq={L} -> {T} frames",
+                   "global_batch": B * world, "seq_len": L, "parallelism": f"dp{world} (batch sharded, no collective)",
+                   "l2": "activations per step (> 3 GB) far exceed the 126 MB L2; no explicit flush needed",
+                   "weights": "random init (seeded), no checkpoint offline"},
+        "clocks": clk.summary(),
+        "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4},
+        "gpu_launches": launches,
+        "model_tflops": fl["total"] * B * world / (ms / K / 1e3) / 1e12,
+        "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}] + bias + erf-GELU",
+                     "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": (achieved / peaks["bf16_tflops"]) if achieved else None, "traffic": None,
+                     "peak_source": peaks["source"] + " (burst cuBLAS bf16; sustained %.0f)" % peaks["bf16_tflops_sustained"]},
+        "breakdown_ms": breakdown,
+    }
+    # conv0 (the HBM-bound kernel): algorithmic bytes = 4*L + 2*512*T0 per utterance
+    if breakdown.get("conv0"):
+        by = B * (4.0 * L + 2.0 * 512 * fl["frames"][0])
+        gbs = by / (breakdown["conv0"] * 1e-3) / 1e9
+        result["roofline_conv0"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+    if not args.no_cpu_baseline:
+        result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args))
+    print(json.dumps(result))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_classes(model, x, cfg, steps):
+    """Device time per kernel class: every C-ABI launch is bracketed by CUDA events on the launching stream."""
+    from wav2vec2 import ops
+    records = []
+    originals = {}
+
+    def wrap(name, label_fn):
+        fn = getattr(ops, name)
+        originals[name] = fn
+
+        def inner(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **kw)
+            e.record()
+            records.append((label_fn(*a, **kw), s, e))
+            return r
+        setattr(ops, name, inner)
+
+    d, ff = cfg.hidden_size, cfg.intermediate_size
+
+    def gemm_label(a, w, **kw):
+        K, N = kw["K"], kw["N"]
+        if "a_batch_stride" in kw:
+            return "conv1-6 (implicit GEMM)"
+        if K == d and N == ff:
+            return "gemm ffn1"
+        if K == ff and N == d:
+            return "gemm ffn2"
+        if N == 3 * d:
+            return "gemm qkv"
+        if K == d and N == d:
+            return "gemm out_proj"
+        if N == cfg.vocab_size:
+            return "gemm lm_head"
+        return "gemm proj"
+
+    wrap("gemm", gemm_label)
+    wrap("conv0", lambda *a, **kw: "conv0")
+    wrap("wave_stats", lambda *a, **kw: "conv0 stats+fold")
+    wrap("conv0_fold", lambda *a, **kw: "conv0 stats+fold")
+    wrap("ln_rows", lambda *a, **kw: "layernorm")
+    wrap("attn_fwd", lambda *a, **kw: "attention")
+    wrap("posconv", lambda *a, **kw: "posconv")
+    try:
+        for _ in range(steps):
+            model(x)
+        torch.cuda.synchronize()
+    finally:
+        for k, fn in originals.items():
+            setattr(ops, k, fn)
+    agg, cnt = {}, {}
+    for label, s, e in records:
+        agg[label] = agg.get(label, 0.0) + s.elapsed_time(e)
+        cnt[label] = cnt.get(label, 0) + 1
+    out = {k: v / steps for k, v in agg.items()}
+    ffn1 = agg.get("gemm ffn1", 0.0) / max(cnt.get("gemm ffn1", 1), 1)
+    return {k: round(v, 4) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}, ffn1
+
+
+def cpu_baseline_and_error(model, cfg, x_host, logits, args):
+    """cpu_baseline leg: the oracle port timed on the host cores on a bounded sample of the same workload, and the
+    logits error of the GPU path against it on those utterances (checker use of oracle/ only)."""
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import Wav2Vec2ForCTC
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nb = min(CPU_SAMPLE_BATCH, x_host.shape[0])
+    xs = x_host[:nb].clone()
+    params = {k: v.detach().cpu() for k, v in model.variables.items()}
+    with torch.no_grad():
+        O.wav2vec2_for_ctc(xs[:1, : min(args.seq, 32000)], params, cfg)       # thread-pool warm-up
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ref = O.wav2vec2_for_ctc(xs, params, cfg)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    val = nb * args.seq / SAMPLE_RATE / best
+    err_fast = (logits[:nb].float().cpu() - ref).abs().max().item()
+    out = {"cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": cores, "kind": "port",
+                            "sample": f"oracle port (torch CPU fp32, stand-in for the reference's TF-2 CPU path) on "
+                                      f"{nb} x {args.seq} samples, best of 3"},
+           f"logits_max_abs_err_{args.precision}": err_fast, "logits_max_abs": ref.abs().max().item()}
+    if args.precision == "bf16":
+        par = Wav2Vec2ForCTC(cfg, input_shape=tuple(xs.shape), precision="bf16x3", device=model.device)
+        par.set_variables(model.variables)
+        out["logits_max_abs_err_bf16x3"] = (par(xs.to(model.device)).float().cpu() - ref).abs().max().item()
+        out["argmax_agreement_bf16"] = (logits[:nb].argmax(-1).cpu() == ref.argmax(-1)).float().mean().item()
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -13,8 +13,10 @@
 // One CTA = 128 queries of one (b, h).  Loop over 128-key chunks:
 //     S = Q K^T        tcgen05.mma 128x128x16 (x4), both operands K-major SW128         -> TMEM S
 //     softmax warps:   2 passes over S in TMEM (max, then exp2 / sum), P -> bf16 -> smem (SW128 image)
-//     PV = P V         tcgen05.mma 128x64x16 (x8), A = P (K-major), B = V (MN-major SW128) -> TMEM PV
-//     O = O * alpha + PV in registers (one query row per thread), final 1/l scaling and store.
+//     O += P V         tcgen05.mma 128x64x16 (x8), A = P (K-major), B = V (MN-major SW128) -> TMEM O (accumulating)
+//     The running max used for the exponent is only advanced when a row's true max outgrows it by more than
+//     2^8 ("lazy rescaling"): then, and only then, O (TMEM) and the row sum are rescaled - rare after chunk 0.
+//     Final: O / l -> bf16 hi(/lo).
 // Two CTAs are resident per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap the
 // other's softmax.  PASSES = 3 (parity mode) adds the hi/lo cross terms for both contractions.
 #include "host_util.h"
@@ -26,7 +28,7 @@ namespace w2v2 {
 constexpr int AT_BM = 128;      // queries per CTA
 constexpr int AT_BN = 128;      // keys per chunk
 constexpr int AT_DH = 64;       // head size
-constexpr int AT_THREADS = 224; // warps 0-3 softmax, 4 TMA, 5 MMA, 6 TMEM allocator
+constexpr int AT_THREADS = 192; // warps 0-3 softmax, 4 TMEM allocator + TMA producer, 5 MMA issuer
 constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
 
 template <int PASSES>
@@ -39,7 +41,7 @@ struct AttnSmem {
   static constexpr int P_OFF = KV_OFF + KV_STAGES * KV_STAGE_BYTES;
   static constexpr int P_BYTES = NPL * 2 * AT_TILE;         // [128][128] bf16 = two [128][64] halves per plane
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
-  static constexpr int TOTAL = BAR_OFF + 128 + 1024;
+  static constexpr int TOTAL = BAR_OFF + 128;   // 2 x (TOTAL + 1 KB reserved) must fit in 228 KB
 };
 
 struct AttnParams {
@@ -56,11 +58,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 const AttnParams p) {
   using S = AttnSmem<PASSES>;
   constexpr int KV_STAGES = S::KV_STAGES;
-  constexpr int TMEM_COLS = 256;  // S: columns [0,128), PV: columns [128,192)
+  constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192)
   constexpr float LOG2E = 1.4426950408889634f;
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SW128 tiles need 1024-byte alignment (no slack is reserved)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;             // [KV_STAGES]
@@ -69,9 +72,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint64_t* s_empty = bars + 6;
   uint64_t* p_full = bars + 7;
   uint64_t* p_empty = bars + 8;
-  uint64_t* pv_full = bars + 9;
-  uint64_t* pv_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* pv_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
@@ -95,17 +97,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     mbar_init(s_empty, 4);
     mbar_init(p_full, 4);
     mbar_init(p_empty, 1);
-    mbar_init(pv_full, 1);
-    mbar_init(pv_empty, 4);
+    mbar_init(pv_done, 1);
     fence_barrier_init();
   }
-  if (warp == 6) tmem_alloc<TMEM_COLS>(tmem_slot);
+  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
-  const uint32_t tmem_pv = tmem_base + 128;
+  const uint32_t tmem_o = tmem_base + 128;
 
   if (warp == 4) {
     // ---------------------------------------------------------------- TMA producer
@@ -159,9 +160,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           for (int k = 0; k < AT_DH / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (pass | k) != 0);
         }
         umma_commit(s_full);
-        // ---- PV = P V
+        // ---- O += P V
         mbar_wait(p_full, par);
-        mbar_wait(pv_empty, par ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
@@ -171,10 +171,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           for (int ks = 0; ks < AT_BN / 16; ++ks) {
             const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
             const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
-            umma_f16(tmem_pv, dp, dv, idesc_pv, (pass | ks) != 0);
+            umma_f16(tmem_o, dp, dv, idesc_pv, (j | pass | ks) != 0);
           }
         }
-        umma_commit(pv_full);
+        umma_commit(pv_done);
         umma_commit(p_empty);
         umma_commit(&kv_empty[stage]);
         if (++stage == KV_STAGES) {
@@ -191,100 +191,136 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint8_t* p_lo = p_hi + 2 * AT_TILE;
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t swz = (uint32_t)(r & 7);
-    float o[AT_DH];
-#pragma unroll
-    for (int i = 0; i < AT_DH; ++i) o[i] = 0.0f;
-    float m_run = -INFINITY, l_run = 0.0f;
+    float m_used = -INFINITY;   // max the exponent is taken against (may lag the true running max by < 2^8)
+    float l_run = 0.0f;
+    const uint32_t s_addr = tmem_s + lane_sel;
+    const uint32_t o_addr = tmem_o + lane_sel;
 
     for (int j = 0; j < nchunks; ++j) {
       const uint32_t par = j & 1;
       const int key0 = j * AT_BN;
       const bool partial = key0 + AT_BN > kv_len;
+      uint32_t ra[32], rb[32];
       mbar_wait(s_full, par);
       tc_fence_after();
-      // pass 1: running max
-      float mx = m_run;
-#pragma unroll 1
-      for (int piece = 0; piece < 4; ++piece) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_sel + piece * 32, rr);
-        tmem_ld_wait();
+      // ---- pass 1: chunk max (4 independent chains, TMEM loads one piece ahead)
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      auto take_max = [&](const uint32_t (&rr)[32], int piece) {
         if (partial) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (key0 + piece * 32 + i < kv_len) mx = fmaxf(mx, __uint_as_float(rr[i]));
+            if (key0 + piece * 32 + i < kv_len) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(rr[i]));
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
+        }
+      };
+      tmem_ld_32x32b_x32(s_addr + 0, ra);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 32, rb);
+      take_max(ra, 0);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 64, ra);
+      take_max(rb, 1);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 96, rb);
+      take_max(ra, 2);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 0, ra);   // piece 0 again for pass 2 (in flight during the bookkeeping below)
+      take_max(rb, 3);
+      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (j == 0) {
+        m_used = cmax;
+      } else {
+        const bool grow = (cmax - m_used) * LOG2E > 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare: rescale O (TMEM) and l by 2^(m_used - m_new); rows that did not grow get alpha == 1
+          const float m_new = fmaxf(m_used, cmax);
+          const float alpha = ex2_approx((m_used - m_new) * LOG2E);
+          tmem_ld_wait();                      // drain the prefetched piece before reusing rb
+          mbar_wait(pv_done, par ^ 1);         // PV of chunk j-1 has landed in O
+          tc_fence_after();
+#pragma unroll
+          for (int piece = 0; piece < 2; ++piece) {
+            tmem_ld_32x32b_x32(o_addr + piece * 32, rb);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rb[i] = __float_as_uint(__uint_as_float(rb[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + piece * 32, rb);
+          }
+          tmem_st_wait();
+          l_run *= alpha;
+          m_used = m_new;
         }
       }
-      const float alpha = ex2_approx((m_run - mx) * LOG2E);
-      m_run = mx;
-      const float mneg = -mx * LOG2E;
-      // pass 2: probabilities -> smem (bf16, SW128 K-major image), row sum
+      const float mneg = -m_used * LOG2E;
+      // ---- pass 2: probabilities -> smem (bf16, SW128 K-major image), row sum
       mbar_wait(p_empty, par ^ 1);
-      float sum = 0.0f;
-#pragma unroll 1
-      for (int piece = 0; piece < 4; ++piece) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_s + lane_sel + piece * 32, rr);
-        tmem_ld_wait();
-        float pr[32];
+      float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      auto emit = [&](uint32_t (&rr)[32], int piece) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           float e = ex2_approx(fmaf(__uint_as_float(rr[i]), LOG2E, mneg));
           if (partial && key0 + piece * 32 + i >= kv_len) e = 0.0f;
-          pr[i] = e;
-          sum += e;
+          sum[i & 3] += e;
+          rr[i] = __float_as_uint(e);
         }
         const uint32_t half_off = (uint32_t)(piece >> 1) * AT_TILE + row_off;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) hi[e] = split_bf16x2(pr[8 * q + 2 * e], pr[8 * q + 2 * e + 1], lo[e]);
+          for (int e = 0; e < 4; ++e)
+            hi[e] = split_bf16x2(__uint_as_float(rr[8 * q + 2 * e]), __uint_as_float(rr[8 * q + 2 * e + 1]), lo[e]);
           const uint32_t chunk = (uint32_t)((piece & 1) * 4 + q);
           const uint32_t off = half_off + ((chunk ^ swz) << 4);
           *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (PASSES == 3) *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-      }
-      l_run = fmaf(l_run, alpha, sum);
-      tc_fence_before();          // S reads done -> MMA may overwrite S
+      };
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 32, rb);
+      emit(ra, 0);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 64, ra);
+      emit(rb, 1);
+      tmem_ld_wait();
+      tmem_ld_32x32b_x32(s_addr + 96, rb);
+      emit(ra, 2);
+      tmem_ld_wait();
+      tc_fence_before();          // all S reads retired -> the MMA warp may overwrite S
+      emit(rb, 3);
+      l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
       fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(s_empty);
         mbar_arrive(p_full);
       }
-      // O = O * alpha + PV
-      mbar_wait(pv_full, par);
-      tc_fence_after();
-#pragma unroll
-      for (int piece = 0; piece < 2; ++piece) {
-        uint32_t rr[32];
-        tmem_ld_32x32b_x32(tmem_pv + lane_sel + piece * 32, rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[piece * 32 + i] = fmaf(o[piece * 32 + i], alpha, __uint_as_float(rr[i]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pv_empty);
     }
 
+    // ---- epilogue: O / l
+    mbar_wait(pv_done, (nchunks - 1) & 1);
+    tc_fence_after();
     const int t = q0 + r;
-    if (t < p.T) {
-      const float inv = 1.0f / l_run;
-      const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
+    const float inv = 1.0f / l_run;
+    const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        uint32_t hi[4], lo[4];
+    for (int piece = 0; piece < 2; ++piece) {
+      uint32_t rr[32];
+      tmem_ld_32x32b_x32(o_addr + piece * 32, rr);
+      tmem_ld_wait();
+      if (t < p.T) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          hi[e] = split_bf16x2(o[8 * q + 2 * e] * inv, o[8 * q + 2 * e + 1] * inv, lo[e]);
-        *reinterpret_cast<uint4*>(p.out_hi + off + 8 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (PASSES == 3) *reinterpret_cast<uint4*>(p.out_lo + off + 8 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            hi[e] = split_bf16x2(__uint_as_float(rr[8 * q + 2 * e]) * inv, __uint_as_float(rr[8 * q + 2 * e + 1]) * inv, lo[e]);
+          *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 8 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          if (PASSES == 3)
+            *reinterpret_cast<uint4*>(p.out_lo + off + piece * 32 + 8 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
       }
     }
   }
@@ -292,7 +328,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 6) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
 template <int PASSES>

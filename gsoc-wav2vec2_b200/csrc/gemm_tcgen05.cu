@@ -3,7 +3,7 @@
 //   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
 //   warp 1      : MMA issuer     (one elected lane, tcgen05.mma cta_group::1 kind::f16, 128 x BLOCK_N x 16)
 //   warp 2      : TMEM allocator (2 accumulator stages of BLOCK_N fp32 columns)
-//   warps 4..7  : epilogue       (tcgen05.ld 32x32b -> bias / erf-GELU / residual / mask -> fp32 and/or bf16 hi,lo)
+//   warps 4..11 : epilogue       (tcgen05.ld 32x32b -> bias / erf-GELU / residual / mask -> fp32 and/or bf16 hi,lo)
 //
 // The same kernel serves every dense contraction on the Wav2Vec2 path:
 //   * encoder Dense layers (reference: encoder.py:24-31,127-128; feature_extractor.py:94; modeling.py:254)
@@ -24,7 +24,7 @@ namespace w2v2 {
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 
 struct GemmParams {
   int num_kb;           // K / 64 (per pass)
@@ -51,10 +51,14 @@ struct GemmSmem {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + 1024;  // + slack for 1024-byte alignment
+  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // bias slice per accumulator stage
+  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + slack for 1024-byte alignment
 };
 
-template <int BLOCK_N, int PASSES>
+// CLUSTER = 2: two CTAs on neighbouring SMs take two consecutive m-tiles of the SAME n-tile and share the
+// weight tile: each CTA fetches half of it and TMA-multicasts that half into both CTAs' smem, which cuts the
+// L2 -> SM traffic per 128x256x64 block from 48 KB to 32 KB (the kernel is L2-bandwidth bound otherwise).
+template <int BLOCK_N, int PASSES, int CLUSTER>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                          const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
@@ -71,10 +75,18 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   uint64_t* tmem_full = empty_bar + GEMM_STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
+  float* s_bias = reinterpret_cast<float*>(smem + S::RING_BYTES + S::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
-  const int total_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
   const int total_kb = PASSES * p.num_kb;
+  // work item = (group of CLUSTER consecutive m-tiles, n-tile); n fastest so the A rows stay hot in L2
+  const int crank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / CLUSTER;
+  const int num_clusters = gridDim.x / CLUSTER;
+  const int total_m_tiles = p.batch * p.tiles_per_batch;
+  const int total_work = ((total_m_tiles + CLUSTER - 1) / CLUSTER) * p.n_tiles;
+  constexpr uint16_t kMask = (uint16_t)((1u << CLUSTER) - 1);
+  constexpr int B_SLICE_ROWS = BLOCK_N / CLUSTER;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA_hi);
@@ -87,17 +99,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 1 && elect_one()) {
     for (int i = 0; i < GEMM_STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], CLUSTER);  // every CTA of the cluster must have released the slot
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -106,9 +118,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
+        const int n_tile = w % p.n_tiles;
+        const int m_tile = min((w / p.n_tiles) * CLUSTER + crank, total_m_tiles - 1);  // clamp: idle half still feeds B
         const int b = m_tile / p.tiles_per_batch;
         const int t0 = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M;
         const int n0 = n_tile * BLOCK_N;
@@ -127,7 +139,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           tma_load_3d(sa, ma, &full_bar[stage], kc, trow, b);
-          tma_load_2d(sb, mb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          if (CLUSTER == 1)
+            tma_load_2d(sb, mb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+          else  // my slice of the weight tile, delivered to every CTA of the cluster
+            tma_load_2d_mcast(sb + crank * (B_SLICE_ROWS * 128), mb, &full_bar[stage], kb * GEMM_BLOCK_K,
+                              n0 + crank * B_SLICE_ROWS, kMask);
           if (++stage == GEMM_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -143,7 +159,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int w = cluster_id; w < total_work; w += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -158,7 +174,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             // +32 bytes per UMMA_K step inside the swizzle row -> +2 in the (addr >> 4) field
             umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (CLUSTER == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          else umma_commit_mcast(&empty_bar[stage], kMask);   // ... in every CTA that multicasts into it
           if (++stage == GEMM_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -172,108 +189,129 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------------ epilogue
-    const int ew = warp - 4;  // == warp % 4 : TMEM lane quadrant this warp may read
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    // warp w reads TMEM lane quadrant (w % 4); the two warps sharing a quadrant take alternate 32-column
+    // chunks.  Per tile: bias slice -> smem (issued before the accumulator is ready), residual lines
+    // prefetched to L2, then a software pipeline: tcgen05.ld of chunk c+1 is in flight while chunk c is
+    // processed and stored.
+    const int ew = warp & 3;
+    const int grp = (warp - 4) >> 2;
     const int lane = lane_id();
+    const int et = threadIdx.x - 128;  // 0..255
+    constexpr int NCH = BLOCK_N / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+    for (int w = cluster_id; w < total_work; w += num_clusters) {
+      const int n_tile = w % p.n_tiles;
+      const int m_raw = (w / p.n_tiles) * CLUSTER + crank;
+      const int m_tile = min(m_raw, total_m_tiles - 1);
       const int b = m_tile / p.tiles_per_batch;
       const int t = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M + ew * 32 + lane;
       const int n0 = n_tile * BLOCK_N;
-      const bool row_ok = t < p.rows_per_batch;
+      const bool row_ok = t < p.rows_per_batch && m_raw < total_m_tiles;
       const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
       const size_t orow = (size_t)b * p.rows_per_batch + t;
+      float* sb = s_bias + acc * BLOCK_N;
+      if (et < BLOCK_N) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.0f;
+      if (p.residual != nullptr && row_ok) {
+#pragma unroll
+        for (int c = grp; c < NCH; c += 2)
+          if (n0 + c * 32 < p.N)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + orow * p.N + n0 + c * 32));
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias slice visible to all epilogue warps
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c0, r);
-        tmem_ld_wait();
+
+      auto process = [&](uint32_t (&r)[32], int c0) {
         const int n = n0 + c0;
-        if (row_ok && n < p.N) {
-          float v[32];
+        if (!(row_ok && n < p.N)) return;
+        float v[32];
+        const float4* bp = reinterpret_cast<const float4*>(sb + c0);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
-          if (p.bias != nullptr) {
-            if (full_chunk) {
-              const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = bp[j];
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+        }
+        const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
+        if (p.gelu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(bp + j);
-                v[4 * j + 0] += bb.x;
-                v[4 * j + 1] += bb.y;
-                v[4 * j + 2] += bb.z;
-                v[4 * j + 3] += bb.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) v[j] += __ldg(p.bias + n + j);
-            }
-          }
-          if (p.gelu) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
-          }
-          if (p.residual != nullptr) {
-            const float* rp = p.residual + orow * p.N + n;
-            if (full_chunk) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp) + j);
-                v[4 * j + 0] += rr.x;
-                v[4 * j + 1] += rr.y;
-                v[4 * j + 2] += rr.z;
-                v[4 * j + 3] += rr.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n + j < p.N) v[j] += __ldg(rp + j);
-            }
-          }
-          if (zero_row) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-          }
+          for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+        }
+        if (p.residual != nullptr) {
+          const float* rp = p.residual + orow * p.N + n;
           if (full_chunk) {
-            if (p.out_f32 != nullptr) {
-              float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.N + n);
+            float4 rr[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.out_hi != nullptr) {
-              uint32_t hi[16], lo[16];
+            for (int j = 0; j < 8; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(rp) + j);
 #pragma unroll
-              for (int j = 0; j < 16; ++j) hi[j] = split_bf16x2(v[2 * j], v[2 * j + 1], lo[j]);
-              uint4* hp = reinterpret_cast<uint4*>(p.out_hi + orow * p.N + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) hp[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              if (p.out_lo != nullptr) {
-                uint4* lp = reinterpret_cast<uint4*>(p.out_lo + orow * p.N + n);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) lp[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-              }
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j + 0] += rr[j].x;
+              v[4 * j + 1] += rr[j].y;
+              v[4 * j + 2] += rr[j].z;
+              v[4 * j + 3] += rr[j].w;
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (n + j >= p.N) continue;
-              if (p.out_f32 != nullptr) p.out_f32[orow * p.N + n + j] = v[j];
-              if (p.out_hi != nullptr) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-                p.out_hi[orow * p.N + n + j] = h;
-                if (p.out_lo != nullptr) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-              }
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += __ldg(rp + j);
+          }
+        }
+        if (zero_row) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+        }
+        if (full_chunk) {
+          if (p.out_f32 != nullptr) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out_hi != nullptr) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) hi[j] = split_bf16x2(v[2 * j], v[2 * j + 1], lo[j]);
+            uint4* hp = reinterpret_cast<uint4*>(p.out_hi + orow * p.N + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hp[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+            if (p.out_lo != nullptr) {
+              uint4* lp = reinterpret_cast<uint4*>(p.out_lo + orow * p.N + n);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) lp[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
             }
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (n + j >= p.N) continue;
+            if (p.out_f32 != nullptr) p.out_f32[orow * p.N + n + j] = v[j];
+            if (p.out_hi != nullptr) {
+              const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
+              p.out_hi[orow * p.N + n + j] = h;
+              if (p.out_lo != nullptr) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
+            }
+          }
+        }
+      };
+
+      uint32_t ra[32], rb[32];
+      int c = grp;
+      if (c < NCH) tmem_ld_32x32b_x32(taddr + c * 32, ra);
+#pragma unroll 1
+      for (; c < NCH; c += 4) {
+        tmem_ld_wait();
+        const bool has_b = (c + 2 < NCH);
+        if (has_b) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, rb);
+        process(ra, c * 32);
+        if (has_b) {
+          tmem_ld_wait();
+          if (c + 4 < NCH) tmem_ld_32x32b_x32(taddr + (c + 4) * 32, ra);
+          process(rb, (c + 2) * 32);
         }
       }
       tc_fence_before();
@@ -287,7 +325,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();  // no CTA exits while a peer may still signal it
   tc_fence_after();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
@@ -326,7 +364,7 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   return 0;
 }
 
-template <int BLOCK_N, int PASSES>
+template <int BLOCK_N, int PASSES, int CLUSTER>
 static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -342,7 +380,7 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   }
   const uint64_t b_dims[2] = {(uint64_t)a->K, (uint64_t)a->w_rows};
   const uint64_t b_strides[1] = {(uint64_t)a->K * 2};
-  const uint32_t b_box[2] = {GEMM_BLOCK_K, (uint32_t)BLOCK_N};
+  const uint32_t b_box[2] = {GEMM_BLOCK_K, (uint32_t)(BLOCK_N / CLUSTER)};
   rc = make_tmap(&tmB_hi, a->w_hi, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   tmB_lo = tmB_hi;
@@ -367,7 +405,7 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(a->out_lo);
 
-  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES>;
+  auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES, CLUSTER>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -376,11 +414,25 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   int dev = 0, sms = 0;
   W2V2_CUDA(cudaGetDevice(&dev));
   W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const int total_tiles = p.batch * p.tiles_per_batch * p.n_tiles;
-  int grid = total_tiles < sms ? total_tiles : sms;
+  const int total_m_tiles = p.batch * p.tiles_per_batch;
+  const int total_work = ((total_m_tiles + CLUSTER - 1) / CLUSTER) * p.n_tiles;
+  int grid = total_work * CLUSTER < sms ? total_work * CLUSTER : sms;
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
-  W2V2_CUDA(cudaGetLastError());
+  grid -= grid % CLUSTER;
+  if (grid < CLUSTER) grid = CLUSTER;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = S::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  W2V2_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
   return 0;
 }
 
@@ -402,19 +454,22 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   int bn = a->block_n;
   if (bn == 0) bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;
   W2V2_CHECK_ARG(a->w_rows >= ((a->N + bn - 1) / bn) * bn, "weight matrix must be padded to a multiple of block_n rows");
+  // clusters of 2 (weight-tile multicast) for the wide tiles whenever there are at least two m-tiles
+  const long m_tiles = (long)a->batch * ((a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
+  const bool pair = (bn >= 128) && m_tiles >= 2 && a->cluster != 1;
   if (a->passes == 1) {
     switch (bn) {
-      case 256: return launch_gemm<256, 1>(a, s);
-      case 128: return launch_gemm<128, 1>(a, s);
-      case 64: return launch_gemm<64, 1>(a, s);
-      case 32: return launch_gemm<32, 1>(a, s);
+      case 256: return pair ? launch_gemm<256, 1, 2>(a, s) : launch_gemm<256, 1, 1>(a, s);
+      case 128: return pair ? launch_gemm<128, 1, 2>(a, s) : launch_gemm<128, 1, 1>(a, s);
+      case 64: return launch_gemm<64, 1, 1>(a, s);
+      case 32: return launch_gemm<32, 1, 1>(a, s);
     }
   } else {
     switch (bn) {
-      case 256: return launch_gemm<256, 3>(a, s);
-      case 128: return launch_gemm<128, 3>(a, s);
-      case 64: return launch_gemm<64, 3>(a, s);
-      case 32: return launch_gemm<32, 3>(a, s);
+      case 256: return pair ? launch_gemm<256, 3, 2>(a, s) : launch_gemm<256, 3, 1>(a, s);
+      case 128: return pair ? launch_gemm<128, 3, 2>(a, s) : launch_gemm<128, 3, 1>(a, s);
+      case 64: return launch_gemm<64, 3, 1>(a, s);
+      case 32: return launch_gemm<32, 3, 1>(a, s);
     }
   }
   return fail(-1, "%s: unsupported block_n %ld", __func__, bn);

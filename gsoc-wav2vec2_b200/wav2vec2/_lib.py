@@ -24,7 +24,7 @@ class GemmArgs(C.Structure):
         ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
         ("w_rows", C.c_int32), ("K", C.c_int32), ("N", C.c_int32), ("rows_per_batch", C.c_int32),
         ("batch", C.c_int32), ("passes", C.c_int32), ("kb_split", C.c_int32), ("block_n", C.c_int32),
-        ("max_ctas", C.c_int32), ("flags", C.c_uint32),
+        ("max_ctas", C.c_int32), ("cluster", C.c_int32), ("flags", C.c_uint32),
         ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_valid", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
     ]

@@ -185,6 +185,29 @@ class _B200Model:
         self._packed = None
         return missing, extra
 
+    def init_random(self, seed=0):
+        """Seeded random weights at a realistic scale for benchmarks / smoke tests (no checkpoints offline):
+        fan-in scaled normal kernels, norm gains 1 + 0.1 N(0,1), biases / offsets 0.1 N(0,1)."""
+        gen = torch.Generator().manual_seed(seed)
+        new = {}
+        for k, t in self.variables.items():
+            shape = tuple(t.shape)
+            if k.endswith("gamma"):
+                w = 1.0 + 0.1 * torch.randn(shape, generator=gen)
+            elif k.endswith("beta") or k.endswith("bias"):
+                w = 0.1 * torch.randn(shape, generator=gen)
+            elif k.endswith("weight_g"):
+                w = 1.0 + 0.5 * torch.rand(shape, generator=gen)
+            elif k.endswith("masked_spec_embed"):
+                w = torch.rand(shape, generator=gen)
+            else:
+                w = torch.randn(shape, generator=gen) / math.sqrt(float(math.prod(shape[:-1])))
+                if "conv_layers" in k:
+                    w = w * math.sqrt(2.0)
+            new[k] = w
+        self.set_variables(new)
+        return self
+
     def load_hf_state_dict(self, state_dict, strict=True):
         """Load a ``transformers`` Wav2Vec2 ``state_dict`` (rules of convert_torch_to_tf.py:88-123)."""
         return self.set_variables(hf_to_reference(state_dict), strict=strict)

@@ -12,6 +12,12 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+LAUNCHES = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -44,14 +50,14 @@ def split_bf16(x: torch.Tensor, with_lo: bool) -> Pair:
     _need_cuda(x)
     hi = torch.empty(x.shape, dtype=BF16, device=x.device)
     lo = torch.empty(x.shape, dtype=BF16, device=x.device) if with_lo else None
-    _lib.check(_lib.load().w2v2_split_bf16(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), "w2v2_split_bf16")
+    _count(); _lib.check(_lib.load().w2v2_split_bf16(_ptr(x), x.numel(), _ptr(hi), _ptr(lo), _stream()), "w2v2_split_bf16")
     return Pair(hi, lo)
 
 
 def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 1,
          a_row_len: Optional[int] = None, a_rows: Optional[int] = None, a_row_stride: Optional[int] = None,
          a_batch_stride: Optional[int] = None, bias=None, residual=None, row_valid=None, gelu=False,
-         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0):
+         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major."""
     _need_cuda(a.hi, w.hi, bias, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
@@ -63,22 +69,22 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
     args.w_rows = w.hi.shape[0]
     args.K, args.N, args.rows_per_batch, args.batch = K, N, rows_per_batch, batch
-    args.passes, args.kb_split, args.block_n, args.max_ctas = passes, kb_split, block_n, max_ctas
+    args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
     args.flags = _lib.GEMM_GELU if gelu else 0
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
-    _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
+    _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
 
 
 def wave_stats(wave: torch.Tensor, stats: torch.Tensor):
     _need_cuda(wave, stats)
     B, L = wave.shape
-    _lib.check(_lib.load().w2v2_wave_stats(_ptr(wave), B, L, _ptr(stats), _stream()), "w2v2_wave_stats")
+    _count(); _lib.check(_lib.load().w2v2_wave_stats(_ptr(wave), B, L, _ptr(stats), _stream()), "w2v2_wave_stats")
 
 
 def conv0_fold(kernel, gamma, beta, stats, B, L, folded_w, folded_b, eps=1e-5):
     C_ = kernel.shape[-1]
-    _lib.check(_lib.load().w2v2_conv0_fold(_ptr(kernel), _ptr(gamma), _ptr(beta), _ptr(stats), B, L, C_, eps,
+    _count(); _lib.check(_lib.load().w2v2_conv0_fold(_ptr(kernel), _ptr(gamma), _ptr(beta), _ptr(stats), B, L, C_, eps,
                                            _ptr(folded_w), _ptr(folded_b), _stream()), "w2v2_conv0_fold")
 
 
@@ -86,20 +92,20 @@ def conv0(wave, weights, w_batch_stride, bias, b_batch_stride, gelu, out_f32=Non
           channels=512):
     _need_cuda(wave, weights, bias, out_f32, out_hi, out_lo)
     B, L = wave.shape
-    _lib.check(_lib.load().w2v2_conv0(_ptr(wave), B, L, channels, _ptr(weights), w_batch_stride, _ptr(bias),
+    _count(); _lib.check(_lib.load().w2v2_conv0(_ptr(wave), B, L, channels, _ptr(weights), w_batch_stride, _ptr(bias),
                                       b_batch_stride, 1 if gelu else 0, _ptr(out_f32), _ptr(out_hi), _ptr(out_lo),
                                       _stream()), "w2v2_conv0")
 
 
 def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None):
     _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo)
-    _lib.check(_lib.load().w2v2_ln_rows(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,
+    _count(); _lib.check(_lib.load().w2v2_ln_rows(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,
                                         _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _stream()), "w2v2_ln_rows")
 
 
 def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1):
     _need_cuda(qkv.hi, out.hi, kv_len)
-    _lib.check(_lib.load().w2v2_attn_fwd(_ptr(qkv.hi), _ptr(qkv.lo) if passes == 3 else None, B, T, H, dh,
+    _count(); _lib.check(_lib.load().w2v2_attn_fwd(_ptr(qkv.hi), _ptr(qkv.lo) if passes == 3 else None, B, T, H, dh,
                                          _ptr(kv_len), _ptr(out.hi), _ptr(out.lo) if passes == 3 else None, passes,
                                          _stream()), "w2v2_attn_fwd")
 
@@ -111,7 +117,7 @@ def posconv(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps, pass
     args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
     args.bias, args.resid, args.out_f32 = _ptr(bias), _ptr(resid), _ptr(out_f32)
     args.batch, args.frames, args.hidden, args.groups, args.ktaps, args.passes = B, T, d, groups, ktaps, passes
-    _lib.check(_lib.load().w2v2_posconv(C.byref(args), _stream()), "w2v2_posconv")
+    _count(); _lib.check(_lib.load().w2v2_posconv(C.byref(args), _stream()), "w2v2_posconv")
 
 
 def ctc_loss(logits, labels, blank, scale, want_grad=True):
@@ -125,7 +131,7 @@ def ctc_loss(logits, labels, blank, scale, want_grad=True):
     ws = torch.empty(lib.w2v2_ctc_workspace_bytes(B, T, Lmax) // 4, dtype=torch.float32, device=logits.device)
     loss = torch.empty(B, dtype=torch.float32, device=logits.device)
     grad = torch.empty_like(logits) if want_grad else None
-    _lib.check(lib.w2v2_ctc_loss(_ptr(logits), _ptr(labels), B, T, V, Lmax, int(blank), float(scale), _ptr(ws), None,
+    _count(); _lib.check(lib.w2v2_ctc_loss(_ptr(logits), _ptr(labels), B, T, V, Lmax, int(blank), float(scale), _ptr(ws), None,
                                  _ptr(loss), _ptr(grad), _stream()), "w2v2_ctc_loss")
     return loss, grad
 
@@ -136,5 +142,5 @@ def frame_argmax(logits):
     V = logits.shape[-1]
     rows = logits.numel() // V
     ids = torch.empty(logits.shape[:-1], dtype=torch.int32, device=logits.device)
-    _lib.check(_lib.load().w2v2_frame_argmax(_ptr(logits), rows, V, _ptr(ids), _stream()), "w2v2_frame_argmax")
+    _count(); _lib.check(_lib.load().w2v2_frame_argmax(_ptr(logits), rows, V, _ptr(ids), _stream()), "w2v2_frame_argmax")
     return ids

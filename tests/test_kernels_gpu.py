@@ -50,6 +50,23 @@ def test_gemm_plain(passes, N, block_n):
     assert err < 2e-4
 
 
+@pytest.mark.parametrize("cluster", [0, 1])
+@pytest.mark.parametrize("M,K,N", [(128 * 37 + 5, 768, 768), (128 * 300, 256, 512), (129, 3072, 256)])
+def test_gemm_persistent_many_tiles(cluster, M, K, N):
+    """Many tiles per CTA (ring/phase wrap-around, accumulator double buffering), CTA-pair multicast vs single."""
+    torch.manual_seed(11)
+    a = _pair(torch.randn(M, K, device=DEV), False)
+    w = _pair(torch.randn(N, K, device=DEV) / math.sqrt(K), False)
+    bias = torch.randn(N, device=DEV)
+    out = torch.full((M, N), float("nan"), device=DEV)
+    ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, out_f32=out, cluster=cluster)
+    torch.cuda.synchronize()
+    ref = a.hi.float() @ w.hi.float().t() + bias
+    err = (out - ref).abs().max().item()
+    print(f"gemm M={M} K={K} N={N} cluster={cluster}: max err {err:.3e}")
+    assert err < 1e-3
+
+
 @pytest.mark.parametrize("passes", [1, 3])
 def test_gemm_epilogue(passes):
     torch.manual_seed(1)
