@@ -1,0 +1,235 @@
+// Shared pieces of the sm_100a bf16 GEMM kernels (gemm_tcgen05.cu: 1-SM tiles, gemm_2sm.cu: cta_group::2 pairs):
+// tile constants, kernel parameters and the warp-level epilogue.
+#pragma once
+#include "host_util.h"
+#include "w2v2_common.cuh"
+#include "../../include/w2v2.h"
+
+namespace w2v2 {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+constexpr int GEMM_STAGES_MAX = 4;
+constexpr int GEMM_EPI_STAGE_BYTES = 8 * 4096;  // 8 epilogue warps x (32 rows x 128 B) transpose buffers
+constexpr int GEMM_THREADS = 384;  // warpgroup 0: TMA / MMA / TMEM-alloc warps; warpgroups 1-2: epilogue
+constexpr int GEMM_REGS_CONTROL = 56;   // setmaxnreg split: 128 x 56 + 256 x 224 <= 64K registers
+constexpr int GEMM_REGS_EPILOGUE = 224;
+
+// epilogue recipe bits (template parameter EPI of the kernels; EPI < 0 = decide from GemmParams at run time)
+constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16;
+constexpr int EPI_RUNTIME = -1;
+
+struct GemmParams {
+  int num_kb;           // K / 64 (per pass)
+  int kb_split;         // k-blocks >= kb_split are fetched from (k - kb_split*64, row + 1)  [pair-row conv fallback]
+  int rows_per_batch;   // valid rows per batch entry
+  int tiles_per_batch;  // ceil(rows_per_batch / 128)
+  int batch;
+  int n_tiles;          // ceil(N / BLOCK_N)
+  int N;                // valid output columns == leading dimension of every output / residual
+  int gelu;
+  int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
+  int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
+  const float* bias;      // [N] or null
+  const float* residual;  // fp32 [batch*rows_per_batch, N] or null
+  const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
+  float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+};
+
+// Epilogue of one 128 x BLOCK_N accumulator tile for one warp (32 rows; lane = row).  The two warps that share a
+// TMEM lane quadrant take alternate PAIRS of 32-column chunks (grp = 0 / 1).
+//  * tcgen05.ld has a long latency while the tensor pipe is busy, so ALL of this warp's chunks are requested
+//    before a single wait (a serial ld/wait per chunk costs ~5.7k cycles per tile and caps K = 768 GEMMs at ~55 %
+//    of peak).  Once the slice sits in registers the accumulator stage is handed back to the MMA warp at once.
+//  * A thread owns one ROW, so direct stores would scatter 16-byte pieces over 32 different lines per
+//    instruction (measured: ~35 % of the kernel).  Instead every 32 x 128-byte block is transposed through a
+//    per-warp, XOR-swizzled smem buffer and written with 8 lanes per row: 4 full 128-byte lines per instruction.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t taddr, int grp, int n0, size_t orow,
+                                                   int rows_valid, bool zero_row, const float* sb, uint8_t* stage,
+                                                   uint32_t tmem_empty_cluster_addr) {
+  // compile-time epilogue recipe (EPI >= 0) or run-time flags (EPI < 0)
+  const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
+  const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
+  const bool f_f32 = (EPI >= 0) ? bool(EPI & EPI_F32) : (p.out_f32 != nullptr);
+  const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
+  const bool f_lo = (EPI >= 0) ? bool(EPI & EPI_LO) : (p.out_lo != nullptr);
+  constexpr int NCH = BLOCK_N / 32;
+  constexpr int NMINE = (NCH >= 4) ? NCH / 2 : NCH;  // chunks per warp (grp 1 idles when NCH < 4)
+  const int lane = lane_id();
+  // chunk index of my i-th chunk: pairs (0,1),(4,5),.. for grp 0 and (2,3),(6,7),.. for grp 1
+  auto chunk_of = [&](int i) { return 4 * (i >> 1) + 2 * grp + (i & 1); };
+  uint32_t r[NMINE][32];
+  if (p.debug != 3) {
+#pragma unroll
+    for (int i = 0; i < NMINE; ++i)
+      if (chunk_of(i) < NCH) tmem_ld_32x32b_x32(taddr + chunk_of(i) * 32, r[i]);
+    tmem_ld_wait();
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tmem_empty_cluster_addr);  // accumulator stage is free again
+  if (p.debug == 3) return;
+  if (p.debug == 1) {
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < NMINE; ++i) x ^= r[i][i];
+    if (__uint_as_float(x) == 1.2345e-30f) p.out_f32[0] = 0.0f;
+    return;
+  }
+  if (rows_valid <= 0) return;
+  const bool row_ok = lane < rows_valid;
+  const size_t orow0 = orow - lane;  // first row of this warp's block
+
+  // staged 32 x 128 B block -> global, 8 lanes per row (PIECES = 8) or 4 lanes per row (PIECES = 4: 64-byte rows)
+  auto flush = [&](uint8_t* gbase, size_t row_stride_bytes, int pieces) {
+    __syncwarp();
+    if (pieces == 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = 4 * k + (lane >> 3), pc = lane & 7;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((pc ^ (row & 7)) << 4));
+        if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + row * row_stride_bytes + pc * 16) = val;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int row = 8 * k + (lane >> 2), pc = lane & 3;
+        const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((pc ^ (row & 7)) << 4));
+        if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + row * row_stride_bytes + pc * 16) = val;
+      }
+    }
+    __syncwarp();
+  };
+  auto put = [&](int piece, uint4 val) {
+    *reinterpret_cast<uint4*>(stage + lane * 128 + ((piece ^ (lane & 7)) << 4)) = val;
+  };
+
+  // ---- pass A: bias / GELU / residual / mask, in place in r[][] (as fp32 bit patterns)
+#pragma unroll
+  for (int i = 0; i < NMINE; ++i) {
+    const int ch = chunk_of(i);
+    const int c0 = ch * 32;
+    const int n = n0 + c0;
+    if (ch >= NCH || n >= p.N) continue;
+    const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+      float4 rr[4];
+      const size_t off = orow * p.N + n + 16 * hf;
+      if (f_res && row_ok) {
+        if (full_chunk) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(p.residual + off) + j);
+        } else {
+          float* rf = reinterpret_cast<float*>(rr);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rf[j] = (n + 16 * hf + j < p.N) ? __ldg(p.residual + off + j) : 0.0f;
+        }
+      }
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 16 * hf + 4 * j);
+        v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
+        v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
+        v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
+        v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+      }
+      if (f_gelu) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+      }
+      if (f_res && row_ok) {
+        const float* rf = reinterpret_cast<const float*>(rr);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += rf[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
+    }
+  }
+  if (p.debug == 2) {
+    if (__uint_as_float(r[0][0] ^ r[NMINE - 1][31]) == 1.2345e-30f) p.out_f32[0] = 0.0f;
+    return;
+  }
+
+  // ---- pass B: stores
+#pragma unroll
+  for (int i = 0; i < NMINE; ++i) {
+    const int ch = chunk_of(i);
+    const int n = n0 + ch * 32;
+    if (ch >= NCH || n >= p.N) continue;
+    const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
+    if (!full_chunk) {
+      // ragged right edge (N not a multiple of 32, or unaligned N): scalar row-per-thread path
+      if (row_ok) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (n + j >= p.N) continue;
+          const float v = __uint_as_float(r[i][j]);
+          if (f_f32) p.out_f32[orow * p.N + n + j] = v;
+          if (f_hi) {
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            p.out_hi[orow * p.N + n + j] = h;
+            if (f_lo) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+          }
+        }
+      }
+      continue;
+    }
+    if (f_f32) {  // 32 fp32 columns = one 128-byte row segment
+#pragma unroll
+      for (int j = 0; j < 8; ++j) put(j, make_uint4(r[i][4 * j], r[i][4 * j + 1], r[i][4 * j + 2], r[i][4 * j + 3]));
+      flush(reinterpret_cast<uint8_t*>(p.out_f32 + orow0 * p.N + n), (size_t)p.N * 4, 8);
+    }
+    if (f_hi) {
+      // bf16: an even/odd chunk pair forms one 128-byte row segment; a lone chunk is a 64-byte segment
+      const bool pair_lo = (i & 1) == 0 && (i + 1 < NMINE) && (chunk_of(i + 1) < NCH) && (n + 64 <= p.N);
+      const bool pair_hi = (i & 1) == 1 && (n0 + chunk_of(i - 1) * 32 + 64 <= p.N);
+      if (pair_hi) continue;  // already written together with chunk i-1
+#pragma unroll
+      for (int plane = 0; plane < 2; ++plane) {
+        if (plane == 1 && !f_lo) continue;
+        __nv_bfloat16* dst = plane == 0 ? p.out_hi : p.out_lo;
+        const int nch = pair_lo ? 2 : 1;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (u >= nch) continue;
+          const int iu = (i + u < NMINE) ? i + u : i;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              h[e] = split_bf16x2(__uint_as_float(r[iu][8 * j + 2 * e]), __uint_as_float(r[iu][8 * j + 2 * e + 1]), l[e]);
+            put(4 * u + j, plane == 0 ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(l[0], l[1], l[2], l[3]));
+          }
+        }
+        flush(reinterpret_cast<uint8_t*>(dst + orow0 * p.N + n), (size_t)p.N * 2, pair_lo ? 8 : 4);
+      }
+    }
+  }
+}
+
+// Per-tile epilogue preamble, issued BEFORE the accumulator is ready so its latency hides behind the MMAs:
+// the bias slice goes to smem (one element per epilogue thread), this thread's residual lines are pulled into L2.
+template <int BLOCK_N, int EPI>
+__device__ __forceinline__ void gemm_epilogue_prepare(const GemmParams& p, int et, int grp, int n0, size_t orow,
+                                                      bool row_ok, float* sb) {
+  if (et < BLOCK_N) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.0f;
+  const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
+  if (f_res && row_ok) {
+#pragma unroll
+    for (int c = grp; c < BLOCK_N / 32; c += 2)
+      if (n0 + c * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + orow * p.N + n0 + c * 32));
+  }
+  asm volatile("bar.sync 1, 256;" ::: "memory");  // bias slice visible to all 8 epilogue warps
+}
+
+GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n);
+int launch_gemm_2sm(const w2v2_gemm_args* a, cudaStream_t stream);  // gemm_2sm.cu
+
+}  // namespace w2v2

@@ -15,44 +15,21 @@
 //
 // PASSES = 3 is the parity mode: operands arrive as bf16 hi/lo planes and the kernel accumulates
 // A_hi*W_hi + A_lo*W_hi + A_hi*W_lo into one fp32 TMEM accumulator (~16 mantissa bits per operand).
-#include "host_util.h"
-#include "w2v2_common.cuh"
-#include "../../include/w2v2.h"
+#include "gemm_common.cuh"
 
 namespace w2v2 {
-
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
-constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
-
-struct GemmParams {
-  int num_kb;           // K / 64 (per pass)
-  int kb_split;         // k-blocks >= kb_split are fetched from (k - kb_split*64, row + 1)  [pair-row conv fallback]
-  int rows_per_batch;   // valid rows per batch entry
-  int tiles_per_batch;  // ceil(rows_per_batch / 128)
-  int batch;
-  int n_tiles;          // ceil(N / BLOCK_N)
-  int N;                // valid output columns == leading dimension of every output / residual
-  int gelu;
-  int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
-  const float* bias;      // [N] or null
-  const float* residual;  // fp32 [batch*rows_per_batch, N] or null
-  const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
-  float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
-};
 
 template <int BLOCK_N>
 struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RING_BYTES = GEMM_STAGES * STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : 4;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // bias slice per accumulator stage
-  static constexpr int TOTAL = RING_BYTES + BAR_BYTES + BIAS_BYTES + 1024;  // + slack for 1024-byte alignment
+  static constexpr int EPI_OFF = RING_BYTES + BAR_BYTES + BIAS_BYTES;
+  static constexpr int TOTAL = EPI_OFF + GEMM_EPI_STAGE_BYTES + 1024;  // + slack for 1024-byte alignment
 };
 
 // CLUSTER = 2: two CTAs on neighbouring SMs take two consecutive m-tiles of the SAME n-tile and share the
@@ -71,8 +48,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES);
-  uint64_t* empty_bar = full_bar + GEMM_STAGES;
-  uint64_t* tmem_full = empty_bar + GEMM_STAGES;
+  uint64_t* empty_bar = full_bar + S::STAGES;
+  uint64_t* tmem_full = empty_bar + S::STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   float* s_bias = reinterpret_cast<float*>(smem + S::RING_BYTES + S::BAR_BYTES);
@@ -97,7 +74,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     }
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < GEMM_STAGES; ++i) {
+    for (int i = 0; i < S::STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], CLUSTER);  // every CTA of the cluster must have released the slot
     }
@@ -112,7 +89,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
+  if (warp < 4) {
+  // warpgroup 0 (TMA / MMA / TMEM-alloc warps) gives registers away ...
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CONTROL));
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one()) {
@@ -144,7 +123,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           else  // my slice of the weight tile, delivered to every CTA of the cluster
             tma_load_2d_mcast(sb + crank * (B_SLICE_ROWS * 128), mb, &full_bar[stage], kb * GEMM_BLOCK_K,
                               n0 + crank * B_SLICE_ROWS, kMask);
-          if (++stage == GEMM_STAGES) {
+          if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -176,7 +155,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           }
           if (CLUSTER == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           else umma_commit_mcast(&empty_bar[stage], kMask);   // ... in every CTA that multicasts into it
-          if (++stage == GEMM_STAGES) {
+          if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -188,7 +167,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         }
       }
     }
-  } else if (warp >= 4) {
+  }
+  } else {
+  // ... to the epilogue warpgroups, which keep their whole accumulator slice (128 registers) in flight
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_EPILOGUE));
+  {
     // ------------------------------------------------------------------ epilogue (8 warps)
     // warp w reads TMEM lane quadrant (w % 4); the two warps sharing a quadrant take alternate 32-column
     // chunks.  Per tile: bias slice -> smem (issued before the accumulator is ready), residual lines
@@ -198,7 +181,6 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
     const int grp = (warp - 4) >> 2;
     const int lane = lane_id();
     const int et = threadIdx.x - 128;  // 0..255
-    constexpr int NCH = BLOCK_N / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = cluster_id; w < total_work; w += num_clusters) {
@@ -209,119 +191,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       const int t = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M + ew * 32 + lane;
       const int n0 = n_tile * BLOCK_N;
       const bool row_ok = t < p.rows_per_batch && m_raw < total_m_tiles;
+      const int rows_valid = (m_raw < total_m_tiles) ? min(32, p.rows_per_batch - (t - lane)) : 0;
+      uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * 4096;
       const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
       const size_t orow = (size_t)b * p.rows_per_batch + t;
       float* sb = s_bias + acc * BLOCK_N;
-      if (et < BLOCK_N) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.0f;
-      if (p.residual != nullptr && row_ok) {
-#pragma unroll
-        for (int c = grp; c < NCH; c += 2)
-          if (n0 + c * 32 < p.N)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + orow * p.N + n0 + c * 32));
-      }
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias slice visible to all epilogue warps
+      gemm_epilogue_prepare<BLOCK_N, EPI_RUNTIME>(p, et, grp, n0, orow, row_ok, sb);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
 
-      auto process = [&](uint32_t (&r)[32], int c0) {
-        const int n = n0 + c0;
-        if (!(row_ok && n < p.N)) return;
-        float v[32];
-        const float4* bp = reinterpret_cast<const float4*>(sb + c0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = bp[j];
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-        }
-        const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
-        if (p.gelu) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) gelu_erf_x2(v[j], v[j + 1]);
-        }
-        if (p.residual != nullptr) {
-          const float* rp = p.residual + orow * p.N + n;
-          if (full_chunk) {
-            float4 rr[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(rp) + j);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j + 0] += rr[j].x;
-              v[4 * j + 1] += rr[j].y;
-              v[4 * j + 2] += rr[j].z;
-              v[4 * j + 3] += rr[j].w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) v[j] += __ldg(rp + j);
-          }
-        }
-        if (zero_row) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.0f;
-        }
-        if (full_chunk) {
-          if (p.out_f32 != nullptr) {
-            float4* op = reinterpret_cast<float4*>(p.out_f32 + orow * p.N + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out_hi != nullptr) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) hi[j] = split_bf16x2(v[2 * j], v[2 * j + 1], lo[j]);
-            uint4* hp = reinterpret_cast<uint4*>(p.out_hi + orow * p.N + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hp[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-            if (p.out_lo != nullptr) {
-              uint4* lp = reinterpret_cast<uint4*>(p.out_lo + orow * p.N + n);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) lp[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (n + j >= p.N) continue;
-            if (p.out_f32 != nullptr) p.out_f32[orow * p.N + n + j] = v[j];
-            if (p.out_hi != nullptr) {
-              const __nv_bfloat16 h = __float2bfloat16_rn(v[j]);
-              p.out_hi[orow * p.N + n + j] = h;
-              if (p.out_lo != nullptr) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v[j] - __bfloat162float(h));
-            }
-          }
-        }
-      };
-
-      uint32_t ra[32], rb[32];
-      int c = grp;
-      if (c < NCH) tmem_ld_32x32b_x32(taddr + c * 32, ra);
-#pragma unroll 1
-      for (; c < NCH; c += 4) {
-        tmem_ld_wait();
-        const bool has_b = (c + 2 < NCH);
-        if (has_b) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, rb);
-        process(ra, c * 32);
-        if (has_b) {
-          tmem_ld_wait();
-          if (c + 4 < NCH) tmem_ld_32x32b_x32(taddr + (c + 4) * 32, ra);
-          process(rb, (c + 2) * 32);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      gemm_epilogue_tile<BLOCK_N, EPI_RUNTIME>(p, taddr, grp, n0, orow, rows_valid, zero_row, sb, stage, smem_u32(&tmem_empty[acc]));
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+  }
   }
 
   tc_fence_before();
@@ -364,6 +251,28 @@ int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims
   return 0;
 }
 
+GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
+  GemmParams p;
+  p.num_kb = a->K / GEMM_BLOCK_K;
+  p.kb_split = a->kb_split > 0 ? a->kb_split : p.num_kb;
+  p.rows_per_batch = a->rows_per_batch;
+  p.tiles_per_batch = (a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
+  p.batch = a->batch;
+  p.n_tiles = (a->N + block_n - 1) / block_n;
+  p.N = a->N;
+  p.gelu = (a->flags & W2V2_GEMM_GELU) ? 1 : 0;
+  p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
+  p.debug = (int)(a->flags >> 8) & 3;
+  p.bias = a->bias;
+  p.residual = a->residual;
+  p.row_valid = a->row_valid;
+  p.out_f32 = a->out_f32;
+  p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(a->out_lo);
+
+  return p;
+}
+
 template <int BLOCK_N, int PASSES, int CLUSTER>
 static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
@@ -388,23 +297,7 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
     rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
-  GemmParams p;
-  p.num_kb = a->K / GEMM_BLOCK_K;
-  p.kb_split = a->kb_split > 0 ? a->kb_split : p.num_kb;
-  p.rows_per_batch = a->rows_per_batch;
-  p.tiles_per_batch = (a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
-  p.batch = a->batch;
-  p.n_tiles = (a->N + BLOCK_N - 1) / BLOCK_N;
-  p.N = a->N;
-  p.gelu = (a->flags & W2V2_GEMM_GELU) ? 1 : 0;
-  p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
-  p.bias = a->bias;
-  p.residual = a->residual;
-  p.row_valid = a->row_valid;
-  p.out_f32 = a->out_f32;
-  p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
-  p.out_lo = reinterpret_cast<__nv_bfloat16*>(a->out_lo);
-
+  GemmParams p = make_gemm_params(a, BLOCK_N);
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES, CLUSTER>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
@@ -459,14 +352,14 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   const bool pair = (bn >= 128) && m_tiles >= 2 && a->cluster != 1;
   if (a->passes == 1) {
     switch (bn) {
-      case 256: return pair ? launch_gemm<256, 1, 2>(a, s) : launch_gemm<256, 1, 1>(a, s);
+      case 256: return pair ? (a->cluster == 3 ? launch_gemm<256, 1, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 1, 1>(a, s);
       case 128: return pair ? launch_gemm<128, 1, 2>(a, s) : launch_gemm<128, 1, 1>(a, s);
       case 64: return launch_gemm<64, 1, 1>(a, s);
       case 32: return launch_gemm<32, 1, 1>(a, s);
     }
   } else {
     switch (bn) {
-      case 256: return pair ? launch_gemm<256, 3, 2>(a, s) : launch_gemm<256, 3, 1>(a, s);
+      case 256: return pair ? (a->cluster == 3 ? launch_gemm<256, 3, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 3, 1>(a, s);
       case 128: return pair ? launch_gemm<128, 3, 2>(a, s) : launch_gemm<128, 3, 1>(a, s);
       case 64: return launch_gemm<64, 3, 1>(a, s);
       case 32: return launch_gemm<32, 3, 1>(a, s);

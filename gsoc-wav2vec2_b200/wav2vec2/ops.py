@@ -57,7 +57,7 @@ def split_bf16(x: torch.Tensor, with_lo: bool) -> Pair:
 def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 1,
          a_row_len: Optional[int] = None, a_rows: Optional[int] = None, a_row_stride: Optional[int] = None,
          a_batch_stride: Optional[int] = None, bias=None, residual=None, row_valid=None, gelu=False,
-         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0):
+         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major."""
     _need_cuda(a.hi, w.hi, bias, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
@@ -70,7 +70,7 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.w_rows = w.hi.shape[0]
     args.K, args.N, args.rows_per_batch, args.batch = K, N, rows_per_batch, batch
     args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
-    args.flags = _lib.GEMM_GELU if gelu else 0
+    args.flags = (_lib.GEMM_GELU if gelu else 0) | (debug << 8)
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")

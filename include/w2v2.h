@@ -58,7 +58,8 @@ typedef struct w2v2_gemm_args {
   int32_t kb_split;        /* 0, or: 64-wide k-blocks >= kb_split come from (k - 64*kb_split, row+1) */
   int32_t block_n;         /* 0 = auto (256/128/64/32) */
   int32_t max_ctas;        /* 0 = one persistent CTA per SM */
-  int32_t cluster;         /* 0 = auto (CTA pairs multicast the weight tile), 1 = single-CTA clusters */
+  int32_t cluster;         /* 0 = auto (256-wide tiles: cta_group::2 CTA pairs), 1 = single CTAs,
+                              3 = 1-SM MMAs with pair-multicast weight tiles */
   uint32_t flags;          /* W2V2_GEMM_* */
   const float* bias;       /* [N] or NULL */
   const float* residual;   /* fp32 [batch*rows_per_batch][N] or NULL, added after bias/GELU */

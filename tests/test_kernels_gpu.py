@@ -50,7 +50,7 @@ def test_gemm_plain(passes, N, block_n):
     assert err < 2e-4
 
 
-@pytest.mark.parametrize("cluster", [0, 1])
+@pytest.mark.parametrize("cluster", [0, 1, 3])
 @pytest.mark.parametrize("M,K,N", [(128 * 37 + 5, 768, 768), (128 * 300, 256, 512), (129, 3072, 256)])
 def test_gemm_persistent_many_tiles(cluster, M, K, N):
     """Many tiles per CTA (ring/phase wrap-around, accumulator double buffering), CTA-pair multicast vs single."""
