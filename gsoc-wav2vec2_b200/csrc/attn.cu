@@ -12,7 +12,9 @@
 //
 // One CTA = 128 queries of one (b, h).  Loop over 128-key chunks:
 //     S = Q K^T        tcgen05.mma 128x128x16 (x4), both operands K-major SW128         -> TMEM S
-//     softmax warps:   2 passes over S in TMEM (max, then exp2 / sum), P -> bf16 -> smem (SW128 image)
+//     softmax warps:   the whole 128-column S row is pulled into registers with four tcgen05.ld in flight and ONE
+//                      wait (tcgen05.ld latency is long while the tensor pipe is busy), S is released at once so
+//                      the next chunk's Q K^T overlaps the exp2 / sum / bf16 packing; P -> smem (SW128 image)
 //     O += P V         tcgen05.mma 128x64x16 (x8), A = P (K-major), B = V (MN-major SW128) -> TMEM O (accumulating)
 //     The running max used for the exponent is only advanced when a row's true max outgrows it by more than
 //     2^8 ("lazy rescaling"): then, and only then, O (TMEM) and the row sum are rescaled - rare after chunk 0.
@@ -28,13 +30,15 @@ namespace w2v2 {
 constexpr int AT_BM = 128;      // queries per CTA
 constexpr int AT_BN = 128;      // keys per chunk
 constexpr int AT_DH = 64;       // head size
-constexpr int AT_THREADS = 192; // warps 0-3 softmax, 4 TMEM allocator + TMA producer, 5 MMA issuer
+constexpr int AT_THREADS = 256; // warpgroup 0 (warps 0-3): softmax; warpgroup 1: warp 4 TMEM alloc + TMA, warp 5 MMA, 6-7 idle
+constexpr int AT_REGS_SOFTMAX = 208;  // setmaxnreg split (2 CTAs/SM): 128 x 208 + 128 x 40 registers per CTA
+constexpr int AT_REGS_CONTROL = 40;
 constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
 
 template <int PASSES>
 struct AttnSmem {
   static constexpr int NPL = (PASSES == 3) ? 2 : 1;         // planes (hi, lo)
-  static constexpr int KV_STAGES = (PASSES == 3) ? 1 : 2;
+  static constexpr int KV_STAGES = 2;
   static constexpr int Q_OFF = 0;
   static constexpr int KV_OFF = Q_OFF + NPL * AT_TILE;
   static constexpr int KV_STAGE_BYTES = 2 * NPL * AT_TILE;  // K and V, each NPL planes
@@ -108,6 +112,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   const uint32_t tmem_s = tmem_base;
   const uint32_t tmem_o = tmem_base + 128;
 
+  if (warp >= 4) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CONTROL));
   if (warp == 4) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
@@ -141,16 +147,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
       const uint32_t p_addr = smem_u32(smem + S::P_OFF);
       mbar_wait(q_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nchunks; ++j) {
-        const uint32_t par = j & 1;
+      auto issue_qk = [&](int stage) {
         const uint32_t k_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES);
-        const uint32_t v_addr = k_addr + S::NPL * AT_TILE;
-        mbar_wait(&kv_full[stage], phase);
-        mbar_wait(s_empty, par ^ 1);
-        tc_fence_after();
-        // ---- S = Q K^T
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
           const uint32_t qa = q_addr + ((pass == 1) ? AT_TILE : 0);
@@ -160,6 +158,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           for (int k = 0; k < AT_DH / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (pass | k) != 0);
         }
         umma_commit(s_full);
+      };
+      // kv stage of chunk j is j % 2 with phase (j / 2) & 1
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      for (int j = 0; j < nchunks; ++j) {
+        const uint32_t par = j & 1;
+        const int stage = j & 1;
+        const uint32_t v_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES) + S::NPL * AT_TILE;
+        if (j + 1 < nchunks) {
+          // S(j) has been copied to registers -> overwrite it with Q K(j+1)^T while the softmax math runs
+          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          mbar_wait(s_empty, par);
+          tc_fence_after();
+          issue_qk((j + 1) & 1);
+        }
         // ---- O += P V
         mbar_wait(p_full, par);
         tc_fence_after();
@@ -177,13 +191,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         umma_commit(pv_done);
         umma_commit(p_empty);
         umma_commit(&kv_empty[stage]);
-        if (++stage == KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
     }
-  } else if (warp < 4) {
+  }
+  } else {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AT_REGS_SOFTMAX));
+  {
     // ---------------------------------------------------------------- softmax / output (one row per thread)
     const int r = warp * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
@@ -200,34 +213,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       const uint32_t par = j & 1;
       const int key0 = j * AT_BN;
       const bool partial = key0 + AT_BN > kv_len;
-      uint32_t ra[32], rb[32];
+      uint32_t sr[4][32];   // the whole S row of this chunk
       mbar_wait(s_full, par);
       tc_fence_after();
-      // ---- pass 1: chunk max (4 independent chains, TMEM loads one piece ahead)
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) tmem_ld_32x32b_x32(s_addr + pc * 32, sr[pc]);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the MMA warp may start Q K(j+1)^T
+      // ---- chunk max (masked keys excluded), 4 independent chains
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-      auto take_max = [&](const uint32_t (&rr)[32], int piece) {
-        if (partial) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + piece * 32 + i < kv_len) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
-        } else {
+      for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(rr[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (partial && key0 + pc * 32 + i >= kv_len) sr[pc][i] = 0xff800000u;  // -inf: exp2 -> 0
+          mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sr[pc][i]));
         }
-      };
-      tmem_ld_32x32b_x32(s_addr + 0, ra);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 32, rb);
-      take_max(ra, 0);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 64, ra);
-      take_max(rb, 1);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 96, rb);
-      take_max(ra, 2);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 0, ra);   // piece 0 again for pass 2 (in flight during the bookkeeping below)
-      take_max(rb, 3);
+      }
       const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (j == 0) {
         m_used = cmax;
@@ -237,66 +241,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           // rare: rescale O (TMEM) and l by 2^(m_used - m_new); rows that did not grow get alpha == 1
           const float m_new = fmaxf(m_used, cmax);
           const float alpha = ex2_approx((m_used - m_new) * LOG2E);
-          tmem_ld_wait();                      // drain the prefetched piece before reusing rb
           mbar_wait(pv_done, par ^ 1);         // PV of chunk j-1 has landed in O
           tc_fence_after();
 #pragma unroll
           for (int piece = 0; piece < 2; ++piece) {
-            tmem_ld_32x32b_x32(o_addr + piece * 32, rb);
+            uint32_t ob[32];
+            tmem_ld_32x32b_x32(o_addr + piece * 32, ob);
             tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) rb[i] = __float_as_uint(__uint_as_float(rb[i]) * alpha);
-            tmem_st_32x32b_x32(o_addr + piece * 32, rb);
+            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + piece * 32, ob);
           }
           tmem_st_wait();
+          tc_fence_before();
           l_run *= alpha;
           m_used = m_new;
         }
       }
       const float mneg = -m_used * LOG2E;
-      // ---- pass 2: probabilities -> smem (bf16, SW128 K-major image), row sum
-      mbar_wait(p_empty, par ^ 1);
+      // ---- probabilities (in place), row sum
       float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      auto emit = [&](uint32_t (&rr)[32], int piece) {
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float e = ex2_approx(fmaf(__uint_as_float(rr[i]), LOG2E, mneg));
-          if (partial && key0 + piece * 32 + i >= kv_len) e = 0.0f;
+          const float e = ex2_approx(fmaf(__uint_as_float(sr[pc][i]), LOG2E, mneg));
           sum[i & 3] += e;
-          rr[i] = __float_as_uint(e);
+          sr[pc][i] = __float_as_uint(e);
         }
-        const uint32_t half_off = (uint32_t)(piece >> 1) * AT_TILE + row_off;
+      }
+      l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+      // ---- P -> smem (bf16, SW128 K-major image) once the previous PV has consumed the buffer
+      mbar_wait(p_empty, par ^ 1);
+#pragma unroll
+      for (int pc = 0; pc < 4; ++pc) {
+        const uint32_t half_off = (uint32_t)(pc >> 1) * AT_TILE + row_off;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e)
-            hi[e] = split_bf16x2(__uint_as_float(rr[8 * q + 2 * e]), __uint_as_float(rr[8 * q + 2 * e + 1]), lo[e]);
-          const uint32_t chunk = (uint32_t)((piece & 1) * 4 + q);
+            hi[e] = split_bf16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e]);
+          const uint32_t chunk = (uint32_t)((pc & 1) * 4 + q);
           const uint32_t off = half_off + ((chunk ^ swz) << 4);
           *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           if (PASSES == 3) *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-      };
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 32, rb);
-      emit(ra, 0);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 64, ra);
-      emit(rb, 1);
-      tmem_ld_wait();
-      tmem_ld_32x32b_x32(s_addr + 96, rb);
-      emit(ra, 2);
-      tmem_ld_wait();
-      tc_fence_before();          // all S reads retired -> the MMA warp may overwrite S
-      emit(rb, 3);
-      l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+      }
       fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(s_empty);
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
     }
 
     // ---- epilogue: O / l
@@ -323,6 +317,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         }
       }
     }
+  }
   }
 
   tc_fence_before();
