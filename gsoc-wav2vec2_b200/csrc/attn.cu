@@ -222,14 +222,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(s_empty);  // S is in registers: the MMA warp may start Q K(j+1)^T
-      // ---- chunk max (masked keys excluded), 4 independent chains
+      // ---- chunk max, 4 independent 3-input chains; masked keys (ragged last chunk only) become -inf
+      if (partial) {
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (key0 + pc * 32 + i >= kv_len) sr[pc][i] = 0xff800000u;
+        }
+      }
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (partial && key0 + pc * 32 + i >= kv_len) sr[pc][i] = 0xff800000u;  // -inf: exp2 -> 0
-          mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(sr[pc][i]));
+        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            mx[c] = fmaxf(fmaxf(mx[c], __uint_as_float(sr[pc][i + 2 * c])), __uint_as_float(sr[pc][i + 2 * c + 1]));
         }
       }
       const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
@@ -259,18 +268,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         }
       }
       const float mneg = -m_used * LOG2E;
-      // ---- probabilities (in place), row sum
-      float sum[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      // ---- probabilities (in place), row sum; exponent argument and sum on the packed fp32x2 pipe
+      const uint64_t l2e2 = pack2(LOG2E, LOG2E), mneg2 = pack2(mneg, mneg);
+      uint64_t sum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = ex2_approx(fmaf(__uint_as_float(sr[pc][i]), LOG2E, mneg));
-          sum[i & 3] += e;
-          sr[pc][i] = __float_as_uint(e);
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t arg = fma2(pack2(__uint_as_float(sr[pc][i]), __uint_as_float(sr[pc][i + 1])), l2e2, mneg2);
+          float a0, a1;
+          unpack2(arg, a0, a1);
+          a0 = ex2_approx(a0);
+          a1 = ex2_approx(a1);
+          sum2[(i >> 1) & 3] = add2(sum2[(i >> 1) & 3], pack2(a0, a1));
+          sr[pc][i] = __float_as_uint(a0);
+          sr[pc][i + 1] = __float_as_uint(a1);
         }
       }
-      l_run += (sum[0] + sum[1]) + (sum[2] + sum[3]);
+      {
+        float s0, s1, s2, s3, s4, s5, s6, s7;
+        unpack2(sum2[0], s0, s1);
+        unpack2(sum2[1], s2, s3);
+        unpack2(sum2[2], s4, s5);
+        unpack2(sum2[3], s6, s7);
+        l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
+      }
       // ---- P -> smem (bf16, SW128 K-major image) once the previous PV has consumed the buffer
       mbar_wait(p_empty, par ^ 1);
 #pragma unroll
