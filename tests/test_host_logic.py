@@ -1,0 +1,162 @@
+"""Host-side logic of the drop-in surface (CPU only): config, variable inventory, checkpoint mapping, processor,
+spec-augment, mask derivation, persistence, error behaviour."""
+import dataclasses
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import w2v2_oracle as O
+from wav2vec2 import (CTCLoss, RobustWav2Vec2Config, Wav2Vec2Config, Wav2Vec2ForCTC, Wav2Vec2Model,
+                      Wav2Vec2Processor)
+from wav2vec2.modeling import variable_shapes
+from wav2vec2.spec_augment import _compute_mask_indices, apply_spec_augmentation
+from wav2vec2.weights import hf_to_reference, reference_to_hf
+
+SMALL = dict(hidden_size=128, num_heads=2, num_layers=2, intermediate_size=256, num_conv_pos_embedding_groups=2)
+
+
+def test_config_surface_matches_reference():
+    cfg = Wav2Vec2Config()
+    d = dataclasses.asdict(cfg)
+    # field names (incl. the historical `kernal_sizes`) and defaults of src/wav2vec2/config.py:6-38
+    assert list(d)[:10] == ["vocab_size", "dropout", "hidden_size", "num_heads", "num_layers", "intermediate_size",
+                            "is_gelu_approx", "layer_norm_eps", "survival_prob", "pad_id"]
+    assert d["kernal_sizes"] == [10, 3, 3, 3, 3, 2, 2] and d["strides"] == [5, 2, 2, 2, 2, 2, 2]
+    assert (cfg.hidden_size, cfg.num_heads, cfg.num_layers, cfg.intermediate_size, cfg.vocab_size) == (768, 12, 12, 3072, 32)
+    r = RobustWav2Vec2Config()
+    assert (r.hidden_size, r.num_heads, r.num_layers, r.intermediate_size) == (1024, 16, 24, 4096)
+    assert r.attention_norm_type == "prenorm" and r.feature_extractor_norm_type == "layer" and r.conv_bias and r.is_robust
+
+
+def test_config_validation_errors():
+    with pytest.raises(ValueError):
+        Wav2Vec2Config(strides=[5, 2])
+    with pytest.raises(ValueError):
+        Wav2Vec2Config(hidden_size=770)
+    with pytest.raises(AssertionError):
+        Wav2Vec2Config(attention_norm_type="sandwich")
+    with pytest.raises(AssertionError):
+        Wav2Vec2Config(feature_extractor_norm_type="batch")
+
+
+def test_config_json_roundtrip(tmp_path):
+    cfg = Wav2Vec2Config(num_layers=3, dropout=0.0)
+    cfg.save_pretrained(str(tmp_path))
+    assert Wav2Vec2Config.from_json(os.path.join(tmp_path, "config.json")) == cfg
+
+
+def test_variable_inventory_is_the_references():
+    shapes = variable_shapes(Wav2Vec2Config(), with_head=True)
+    assert len(shapes) == 213                                           # notebooks/wav2vec2_onnx.ipynb:125
+    assert sum(int(np.prod(s)) for s in shapes.values()) == 94396320
+    assert shapes == O.param_shapes(Wav2Vec2Config())
+    assert shapes["wav2vec2/encoder/pos_conv_embed/conv/weight_v"] == (128, 48, 768)
+    assert shapes["wav2vec2/feature_extractor/conv_layers/0/conv/kernel"] == (10, 1, 512)
+    assert "wav2vec2/feature_extractor/conv_layers/1/layer_norm/gamma" not in shapes     # group norm: layer 0 only
+    assert "wav2vec2/feature_extractor/conv_layers/6/conv/bias" in variable_shapes(RobustWav2Vec2Config(), True)
+
+
+def test_checkpoint_mapping_roundtrip_both_weight_norm_spellings():
+    cfg = Wav2Vec2Config(**SMALL)
+    params = O.random_params(cfg, seed=0)
+    for new_style in (True, False):
+        hf = reference_to_hf(params, new_style_weight_norm=new_style)
+        key = "wav2vec2.encoder.pos_conv_embed.conv." + ("parametrizations.weight.original1" if new_style else "weight_v")
+        assert key in hf and hf[key].shape == (128, 64, 128)            # HF layout [cout, cin/g, k]
+        assert hf["wav2vec2.encoder.layers.0.attention.q_proj.weight"].shape == (128, 128)
+        back = hf_to_reference(hf)
+        assert set(back) == set(params)
+        assert all(torch.equal(back[k], params[k]) for k in params)
+
+
+def test_model_constructor_and_errors():
+    with pytest.raises(ValueError):
+        Wav2Vec2Model({"hidden_size": 768})
+    with pytest.raises(ValueError):
+        Wav2Vec2ForCTC("not a config")
+    with pytest.raises(ValueError):
+        Wav2Vec2Model(Wav2Vec2Config(is_gelu_approx=True), device="cpu")
+    m = Wav2Vec2ForCTC(Wav2Vec2Config(**SMALL), input_shape=(1, 2048), device="cpu")
+    assert set(m.variables) == set(variable_shapes(m.config, True))
+    g = m.variables["wav2vec2/encoder/pos_conv_embed/conv/weight_g"]
+    v = m.variables["wav2vec2/encoder/pos_conv_embed/conv/weight_v"]
+    assert torch.allclose(g, v.pow(2).sum((1, 2), keepdim=True).sqrt())   # tensorflow_addons.py:45-48
+    m.freeze_feature_extractor()
+    assert not m.trainable["wav2vec2/feature_extractor/conv_layers/3/conv/kernel"]
+    assert m.trainable["wav2vec2/encoder/layers/0/attention/q_proj/kernel"]
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            m(torch.zeros(1, 2048))
+
+
+def test_save_and_load_pretrained(tmp_path):
+    m = Wav2Vec2ForCTC(Wav2Vec2Config(**SMALL), device="cpu").init_random(3)
+    m.save_pretrained(str(tmp_path))
+    m2 = Wav2Vec2ForCTC.from_pretrained(str(tmp_path), device="cpu") if False else None
+    from safetensors.torch import load_file
+    sd = load_file(os.path.join(tmp_path, "model.safetensors"))
+    assert set(sd) == set(m.variables) and all(torch.equal(sd[k], m.variables[k].cpu()) for k in sd)
+    with pytest.raises(ValueError, match="Couldn't download"):
+        Wav2Vec2ForCTC.from_pretrained(os.path.join(tmp_path, "missing"))
+
+
+def test_mask_warnings_match_reference(caplog):
+    m = Wav2Vec2Model(Wav2Vec2Config(**SMALL), device="cpu")
+    with caplog.at_level(logging.WARNING):
+        m._warn_mask(torch.ones(1, 10))
+    assert "should not pass `attention_mask`" in caplog.text                # modeling.py:185-186
+    r = Wav2Vec2Model(RobustWav2Vec2Config(**SMALL), device="cpu")
+    caplog.clear()
+    with caplog.at_level(logging.WARNING):
+        r._warn_mask(None)
+    assert "should pass `attention_mask`" in caplog.text                    # modeling.py:183-184
+
+
+def test_frame_lengths_from_mask():
+    m = Wav2Vec2Model(Wav2Vec2Config(**SMALL), device="cpu")
+    am = torch.ones(3, 20000, dtype=torch.int32)
+    am[0, -1000:] = 0
+    am[1, -132:] = 0
+    got = m._frame_lengths(am, 62)
+    want = O.frame_lengths(m.config, am.sum(-1))
+    assert got.tolist() == want.tolist() == [59, 61, 62]
+
+
+def test_processor_tokenizer_and_decode():
+    tok = Wav2Vec2Processor(is_tokenizer=True)
+    ids = tok("She had your dark suit - in greasy wash water all year.")
+    assert ids[:4] == [12, 11, 5, 4] and 4 in ids and 3 not in ids          # S H E | ; '-' -> space; no <unk>
+    assert tok.decode(ids) == "SHE HAD YOUR DARK SUIT IN GREASY WASH WATER AL YEAR"    # repeats collapse (LL -> L, || -> |)
+    assert tok.decode(ids, group_tokens=False) == "SHE HAD YOUR DARK SUIT   IN GREASY WASH WATER ALL YEAR"
+    assert tok.decode([0, 0, 11, 11, 0, 5, 5, 15, 0, 15, 8, 4, 4, 0]) == "HELLO"
+    vocab = tok.get_vocab()
+    assert len(vocab) == 32 and vocab["<pad>"] == 0 and vocab["|"] == 4
+    fe = Wav2Vec2Processor(is_tokenizer=False)
+    x = torch.randn(1, 5000) * 3 + 2
+    y = fe(x)
+    assert y.shape == (5000,) and abs(float(y.mean())) < 1e-5 and abs(float(y.var(unbiased=False)) - 1) < 1e-3
+
+
+def test_spec_augment_mask_properties():
+    np.random.seed(0)
+    m = _compute_mask_indices((4, 768), 0.05, 10, min_masks=2)
+    assert m.shape == (4, 768) and set(np.unique(m)) <= {0, 1}
+    spans = m.sum(-1)
+    assert ((spans >= 10) & (spans <= 40)).all()                             # 3-4 spans of 10 frames, may overlap
+    with pytest.raises(ValueError):
+        _compute_mask_indices((1, 5), 0.05, 10)
+    feats = torch.zeros(4, 768, 8)
+    out = apply_spec_augmentation(feats, torch.ones(8), 0.05, 10)
+    assert set(out.sum(-1).unique().tolist()) <= {0.0, 8.0}
+
+
+def test_ctc_loss_surface():
+    cfg = Wav2Vec2Config()
+    loss = CTCLoss(cfg, (32, 246000), division_factor=32)
+    assert loss._get_logit_length(246000) == 768                             # losses.py:47-56
+    if torch.cuda.is_available():
+        with pytest.raises(ValueError):
+            loss(torch.ones(2, 8, dtype=torch.int32).cuda(), torch.zeros(2, 100, 32).cuda())
