@@ -1,0 +1,53 @@
+"""Fits the erf-GELU evaluation used in the kernel epilogues: erfc(a/sqrt2) = exp2(a*R(a)), R a minimax-style polynomial on
+[0, c], and reports the fp32 max-abs / relative error of gelu(x) = max(x,0) - 0.5*|x|*erfc(|x|/sqrt2).  python tools/fit_gelu.py"""
+import numpy as np
+from scipy.special import erfc, erf, erfcx
+from numpy.polynomial import chebyshev as C, polynomial as P
+def target(a):  # log2(erfc(a/sqrt2)) computed stably
+    z = a/np.sqrt(2)
+    return (-z*z + np.log(erfcx(z)))/np.log(2)
+def fit(c, deg):
+    n = 3000
+    k = np.arange(n); t = np.cos(np.pi*(k+0.5)/n)
+    a = (t+1)/2*c
+    y = target(a)/np.maximum(a,1e-300)      # R(a) = P(a)/a
+    y[a<1e-9] = -np.sqrt(2/np.pi)/np.log(2)
+    V = C.chebvander(t, deg-1)
+    # weight: gelu abs error = 0.5*a*e*ln2*dP = 0.5*a*e*ln2*a*dR
+    e = erfc(a/np.sqrt(2))
+    wt = 0.5*a*a*e*np.log(2) + 1e-4
+    w = np.ones(n)
+    for it in range(80):
+        W = np.sqrt(w)*wt
+        coef, *_ = np.linalg.lstsq(V*W[:,None], y*W, rcond=None)
+        err = np.abs((V@coef - y)*wt)
+        w = w*(err/err.max()+1e-3); w/=w.sum()
+    p = C.cheb2poly(coef)
+    tt = np.array([-1.0, 2/c])
+    mono = np.zeros(1); powt = np.ones(1)
+    for q in p:
+        mono = P.polyadd(mono, q*powt); powt = P.polymul(powt, tt)
+    return mono   # R(a) monomial coefs, P(a) = a*R(a)
+def evalerr(mono, c):
+    xs = np.linspace(-14, 14, 2800001).astype(np.float32)
+    a = np.minimum(np.abs(xs), np.float32(c)).astype(np.float32)
+    r = np.full_like(a, np.float32(mono[-1]))
+    for q in mono[-2::-1]:
+        r = (r*a + np.float32(q)).astype(np.float32)
+    p = (r*a).astype(np.float32)
+    e = np.exp2(p.astype(np.float64)).astype(np.float32)
+    t = (np.abs(xs)*e).astype(np.float32)
+    g = (np.maximum(xs,0) - np.float32(0.5)*t).astype(np.float32)
+    ref = 0.5*xs.astype(np.float64)*(1+erf(xs.astype(np.float64)/np.sqrt(2)))
+    err = np.abs(g-ref)
+    rel = err/np.maximum(np.abs(ref), 1e-2)
+    return err.max(), xs[err.argmax()], rel.max()
+best=None
+for c in [5.0, 5.5, 6.0]:
+    for deg in [5,6,7,8,9,10]:
+        m = fit(c, deg)
+        r = evalerr(m,c)
+        print(c, deg, "abs %.2e at x=%.2f rel %.2e" % r)
+np.set_printoptions(precision=10)
+m = fit(5.5, 8); print(repr(m)); print(evalerr(m,5.5))
+m = fit(5.5, 6); print(repr(m)); print(evalerr(m,5.5))
