@@ -281,7 +281,7 @@ def profile_classes(model, x, cfg, steps):
     def gemm_label(a, w, **kw):
         K, N = kw["K"], kw["N"]
         if "a_batch_stride" in kw:
-            return "conv1-6 (implicit GEMM)"
+            return "conv0" if K == 64 else "conv1-6 (implicit GEMM)"
         if K == d and N == ff:
             return "gemm ffn1"
         if K == ff and N == d:
@@ -296,6 +296,7 @@ def profile_classes(model, x, cfg, steps):
 
     wrap("gemm", gemm_label)
     wrap("conv0", lambda *a, **kw: "conv0")
+    wrap("conv0_im2col", lambda *a, **kw: "conv0")
     wrap("wave_stats", lambda *a, **kw: "conv0 stats+fold")
     wrap("conv0_fold", lambda *a, **kw: "conv0 stats+fold")
     wrap("ln_rows", lambda *a, **kw: "layernorm")

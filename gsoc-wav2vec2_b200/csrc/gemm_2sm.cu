@@ -14,23 +14,181 @@ namespace w2v2 {
 // =====================================================================================================
 constexpr int GEMM2_STAGES = 5;
 constexpr int GEMM2_BLOCK_N = 256;
+constexpr int GEMM2_EPI_WARPS = 16;                                  // 4 TMEM lane quadrants x 4 column groups of 64
+constexpr int GEMM2_THREADS = 128 + GEMM2_EPI_WARPS * 32;            // + warpgroup 0: TMA / MMA / TMEM-alloc warps
+// setmaxnreg only redistributes what the CTA got at launch (640 threads x 96 regs): 128 x 32 + 512 x 112 = 61440
+constexpr int GEMM2_REGS_CONTROL = 32, GEMM2_REGS_EPILOGUE = 112;
 
 struct Gemm2Smem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;           // 16 KB
   static constexpr int B_BYTES = (GEMM2_BLOCK_N / 2) * GEMM_BLOCK_K * 2;     // 16 KB: this CTA's half of the n-tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int RING_BYTES = GEMM2_STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFF = RING_BYTES;                   // 16 epilogue warps x 2 KB TMA-store staging (1024-aligned)
+  static constexpr int EPI_WARP_BYTES = 2048;                  // 32 rows x 64 B, 64-byte swizzle
+  static constexpr int EPI_BYTES = GEMM2_EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = 2 * GEMM2_BLOCK_N * 4;
-  static constexpr int EPI_OFF = RING_BYTES + BAR_BYTES + BIAS_BYTES;
-  static constexpr int TOTAL = EPI_OFF + GEMM_EPI_STAGE_BYTES + 1024;
+  static constexpr int BIAS_OFF = BAR_OFF + BAR_BYTES;
+  static constexpr int BIAS_BYTES = 4 * GEMM2_BLOCK_N * 4;     // per accumulator stage: bias slice, then scale slices
+  static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + 1024;
 };
 
+// TMA bulk store of one staged [rows x 128 B] block (smem, SW128 image) to a 3-D tensor {N, rows_per_batch, batch}.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct Gemm2OutMaps {
+  CUtensorMap f32, hi, lo;  // {N, rows_per_batch, batch}; boxes {16 fp32 | 32 bf16, 32 rows, 1} = 64-byte rows, SW64
+};
+
+// Epilogue of one warp: TMEM lane quadrant `ew` (32 rows, lane = row) x column group `cg` (64 columns = 2 chunks).
+// Both chunks are requested from TMEM before one wait, the accumulator stage is released, then bias/scale,
+// erf-GELU, fp32 residual (coalesced block load through the staging block) and row masking run in registers.
+// Every output leaves through a 2 KB staging block (32 rows x 64 B, 64-byte swizzle) and a TMA bulk store per
+// 64-byte column slab (32 bf16 or 16 fp32 columns); rows past the utterance are clipped by the tensor map.
+template <int EPI>
+__device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const Gemm2OutMaps& om, uint32_t taddr, int cg,
+                                                    int n0, int t_warp0, int b, int rows_valid, bool zero_row,
+                                                    const float* sb, uint8_t* stage, uint32_t tmem_empty_cluster_addr) {
+  constexpr int BLOCK_N = GEMM2_BLOCK_N;
+  const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
+  const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
+  const bool f_f32 = (EPI >= 0) ? bool(EPI & EPI_F32) : (p.out_f32 != nullptr);
+  const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
+  const bool f_lo = (EPI >= 0) ? bool(EPI & EPI_LO) : (p.out_lo != nullptr);
+  const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
+  const int lane = lane_id();
+  const int c_base = 64 * cg;       // first column of this warp inside the tile
+  const int n = n0 + c_base;        // ... and in the output
+
+  uint32_t r[2][32];
+  if (p.debug != 3) {
+    tmem_ld_32x32b_x32(taddr + c_base, r[0]);
+    tmem_ld_32x32b_x32(taddr + c_base + 32, r[1]);
+    tmem_ld_wait();
+  }
+  tc_fence_before();
+  __syncwarp();
+  if (lane == 0) mbar_arrive_cluster(tmem_empty_cluster_addr);  // accumulator stage is free again
+  if (p.debug == 3) return;
+  if (p.debug == 1) {
+    if (__uint_as_float(r[0][0] ^ r[1][31]) == 1.2345e-30f) p.out_f32[0] = 0.0f;
+    return;
+  }
+  if (rows_valid <= 0 || n >= p.N) return;
+  const size_t orow0 = (size_t)b * p.rows_per_batch + t_warp0;
+
+  // staging block: row-major 64-byte rows, 16-byte slot s of row r lives at slot s ^ ((r >> 1) & 3)  (SWIZZLE_64B)
+  auto slot = [&](int row, int piece) { return stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4); };
+  auto stage_acquire = [&]() {  // the block may still be read by the previous bulk store of this warp
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+  };
+  auto stage_store = [&](const CUtensorMap* m, int col) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(m, stage, col, t_warp0, b);
+      bulk_commit();
+    }
+  };
+
+  // ---- pass A: scale / bias / GELU / residual / mask, in place, 16 columns (one 64-byte fp32 slab) at a time
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = q >> 1, hf = q & 1;
+    const int c0 = c_base + 16 * q;
+    if (n0 + c0 >= p.N) continue;
+    float4 rr[4];
+    if (f_res && lane < rows_valid) {
+      // this row's 64-byte residual slab (pulled into L2 by the per-tile prefetch)
+      const float4* gres = reinterpret_cast<const float4*>(p.residual + (orow0 + lane) * p.N + n0 + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) rr[j] = __ldg(gres + j);
+    }
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+      if (f_scale) {
+        const float4 sc = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 4 * j);
+        v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), sc.x, bb.x);
+        v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), sc.y, bb.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), sc.z, bb.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), sc.w, bb.w);
+      } else {
+        v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
+        v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
+        v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
+        v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+      }
+    }
+    if (f_gelu) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+    }
+    if (f_res && lane < rows_valid) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[4 * j + 0] += rr[j].x;
+        v[4 * j + 1] += rr[j].y;
+        v[4 * j + 2] += rr[j].z;
+        v[4 * j + 3] += rr[j].w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
+  }
+
+  // ---- pass B: outputs, one 64-byte column slab per bulk store
+  if (f_f32) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (n + 16 * q >= p.N) continue;
+      const int i = q >> 1, hf = q & 1;
+      stage_acquire();
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(slot(lane, j)) = make_uint4(r[i][16 * hf + 4 * j], r[i][16 * hf + 4 * j + 1],
+                                                              r[i][16 * hf + 4 * j + 2], r[i][16 * hf + 4 * j + 3]);
+      stage_store(&om.f32, n + 16 * q);
+    }
+  }
+  if (f_hi) {
+#pragma unroll
+    for (int plane = 0; plane < 2; ++plane) {
+      if (plane == 1 && !f_lo) continue;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        if (n + 32 * i >= p.N) continue;
+        stage_acquire();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            h[e] = split_bf16x2(__uint_as_float(r[i][8 * j + 2 * e]), __uint_as_float(r[i][8 * j + 2 * e + 1]), l[e]);
+          *reinterpret_cast<uint4*>(slot(lane, j)) = plane == 0 ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        stage_store(plane == 0 ? &om.hi : &om.lo, n + 32 * i);
+      }
+    }
+  }
+}
+
 template <int PASSES, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
-                     const GemmParams p) {
+                     const __grid_constant__ Gemm2OutMaps om, const GemmParams p) {
   using S = Gemm2Smem;
   constexpr int BLOCK_N = GEMM2_BLOCK_N;
   constexpr int ACC_STAGES = 2;
@@ -38,12 +196,12 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + GEMM2_STAGES;
   uint64_t* tmem_full = empty_bar + GEMM2_STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
-  float* s_bias = reinterpret_cast<float*>(smem + S::RING_BYTES + S::BAR_BYTES);
+  float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int total_kb = PASSES * p.num_kb;
@@ -68,8 +226,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       mbar_init(&empty_bar[i], 1);  // leader's multicast commit
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
-      mbar_init(&tmem_full[i], 1);    // leader's multicast commit
-      mbar_init(&tmem_empty[i], 16);  // 8 epilogue warps x 2 CTAs (used in the leader only)
+      mbar_init(&tmem_full[i], 1);                       // leader's multicast commit
+      mbar_init(&tmem_empty[i], 2 * GEMM2_EPI_WARPS);    // every epilogue warp of both CTAs (used in the leader only)
     }
     fence_barrier_init();
   }
@@ -79,86 +237,86 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (warp < 4) {
-  // warpgroup 0 (TMA / MMA / TMEM-alloc warps) gives registers away ...
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CONTROL));
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (elect_one()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int w = pair_id; w < total_work; w += num_pairs) {
-        const int n_tile = w % p.n_tiles;
-        const int m_tile = min((w / p.n_tiles) * 2 + crank, total_m_tiles - 1);
-        const int b = m_tile / p.tiles_per_batch;
-        const int t0 = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M;
-        const int n0 = n_tile * BLOCK_N + crank * (BLOCK_N / 2);
-        for (int it = 0; it < total_kb; ++it) {
-          const int pass = (PASSES == 1) ? 0 : it / p.num_kb;
-          const int kb = it - pass * p.num_kb;
-          const CUtensorMap* ma = (pass == 1) ? &tmA_lo : &tmA_hi;
-          const CUtensorMap* mb = (pass == 2) ? &tmB_lo : &tmB_hi;
-          int kc = kb * GEMM_BLOCK_K, trow = t0;
-          if (kb >= p.kb_split) {
-            kc = (kb - p.kb_split) * GEMM_BLOCK_K;
-            trow = t0 + 1;
-          }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * S::STAGE_BYTES;
-          uint8_t* sb = sa + S::A_BYTES;
-          const uint32_t lead_full = mapa_cluster(smem_u32(&full_bar[stage]), 0);
-          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);  // both CTAs' TMA bytes land here
-          tma_load_3d_2sm(sa, ma, lead_full, kc, trow, b);
-          tma_load_2d_2sm(sb, mb, lead_full, kb * GEMM_BLOCK_K, n0);
-          if (++stage == GEMM2_STAGES) {
-            stage = 0;
-            phase ^= 1;
+    // warpgroup 0 (TMA / MMA / TMEM-alloc warps) gives registers away ...
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM2_REGS_CONTROL));
+    if (warp == 0) {
+      // ---------------------------------------------------------------- TMA producer (both CTAs)
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = pair_id; w < total_work; w += num_pairs) {
+          const int n_tile = w % p.n_tiles;
+          const int m_tile = min((w / p.n_tiles) * 2 + crank, total_m_tiles - 1);
+          const int b = m_tile / p.tiles_per_batch;
+          const int t0 = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M;
+          const int n0 = n_tile * BLOCK_N + crank * (BLOCK_N / 2);
+          for (int it = 0; it < total_kb; ++it) {
+            const int pass = (PASSES == 1) ? 0 : it / p.num_kb;
+            const int kb = it - pass * p.num_kb;
+            const CUtensorMap* ma = (pass == 1) ? &tmA_lo : &tmA_hi;
+            const CUtensorMap* mb = (pass == 2) ? &tmB_lo : &tmB_hi;
+            int kc = kb * GEMM_BLOCK_K, trow = t0;
+            if (kb >= p.kb_split) {
+              kc = (kb - p.kb_split) * GEMM_BLOCK_K;
+              trow = t0 + 1;
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * S::STAGE_BYTES;
+            uint8_t* sb = sa + S::A_BYTES;
+            const uint32_t lead_full = mapa_cluster(smem_u32(&full_bar[stage]), 0);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);  // both CTAs' TMA bytes land here
+            tma_load_3d_2sm(sa, ma, lead_full, kc, trow, b);
+            tma_load_2d_2sm(sb, mb, lead_full, kb * GEMM_BLOCK_K, n0);
+            if (++stage == GEMM2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
         }
       }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (leader && elect_one()) {
-      constexpr uint32_t idesc = idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int w = pair_id; w < total_work; w += num_pairs) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int it = 0; it < total_kb; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+    } else if (warp == 1) {
+      // ---------------------------------------------------------------- MMA issuer (leader CTA only)
+      if (leader && elect_one()) {
+        constexpr uint32_t idesc = idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int w = pair_id; w < total_work; w += num_pairs) {
+          mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
-          const uint64_t da = desc_kmajor_sw128(sa);
-          const uint64_t db = desc_kmajor_sw128(sa + S::A_BYTES);
+          const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+          for (int it = 0; it < total_kb; ++it) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+            const uint64_t da = desc_kmajor_sw128(sa);
+            const uint64_t db = desc_kmajor_sw128(sa + S::A_BYTES);
 #pragma unroll
-          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
-          umma_commit_2sm_mcast(&empty_bar[stage], 3);  // slot free in both CTAs once these MMAs retire
-          if (++stage == GEMM2_STAGES) {
-            stage = 0;
-            phase ^= 1;
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+            umma_commit_2sm_mcast(&empty_bar[stage], 3);  // slot free in both CTAs once these MMAs retire
+            if (++stage == GEMM2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
           }
-        }
-        umma_commit_2sm_mcast(&tmem_full[acc], 3);  // both CTAs' epilogues may read their accumulator half
-        if (++acc == ACC_STAGES) {
-          acc = 0;
-          acc_phase ^= 1;
+          umma_commit_2sm_mcast(&tmem_full[acc], 3);  // both CTAs' epilogues may read their accumulator half
+          if (++acc == ACC_STAGES) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
       }
     }
-  }
   } else {
-  // ... to the epilogue warpgroups, which keep their whole accumulator slice (128 registers) in flight
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_EPILOGUE));
-  {
-    // ------------------------------------------------------------------ epilogue (8 warps per CTA)
-    const int ew = warp & 3;
-    const int grp = (warp - 4) >> 2;
+    // ... to the 16 epilogue warps
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GEMM2_REGS_EPILOGUE));
+    const int ew = warp & 3;          // TMEM lane quadrant
+    const int cg = (warp - 4) >> 2;   // column group (64 columns)
     const int lane = lane_id();
-    const int et = threadIdx.x - 128;
+    const int et = threadIdx.x - 128;  // 0..511
+    uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * S::EPI_WARP_BYTES;
+    const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int w = pair_id; w < total_work; w += num_pairs) {
@@ -166,27 +324,36 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int m_raw = (w / p.n_tiles) * 2 + crank;
       const int m_tile = min(m_raw, total_m_tiles - 1);
       const int b = m_tile / p.tiles_per_batch;
-      const int t = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M + ew * 32 + lane;
+      const int t_warp0 = (m_tile - b * p.tiles_per_batch) * GEMM_BLOCK_M + ew * 32;
       const int n0 = n_tile * BLOCK_N;
-      const bool row_ok = t < p.rows_per_batch && m_raw < total_m_tiles;
-      const int rows_valid = (m_raw < total_m_tiles) ? min(32, p.rows_per_batch - (t - lane)) : 0;
-      uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * 4096;
-      const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
-      const size_t orow = (size_t)b * p.rows_per_batch + t;
+      const int rows_valid = (m_raw < total_m_tiles) ? min(32, p.rows_per_batch - t_warp0) : 0;
+      const bool zero_row = p.row_valid != nullptr && t_warp0 + lane >= p.row_valid[b];
       float* sb = s_bias + acc * BLOCK_N;
-      gemm_epilogue_prepare<BLOCK_N, EPI>(p, et, grp, n0, orow, row_ok, sb);
-
+      // bias (threads 0..255) and scale (threads 256..511) slices of this tile -> smem, before the accumulator is ready
+      {
+        const int col = et & (BLOCK_N - 1);
+        const size_t boff = (size_t)b * p.bias_bstride + n0 + col;
+        if (et < BLOCK_N) sb[col] = (p.bias != nullptr && n0 + col < p.N) ? __ldg(p.bias + boff) : 0.0f;
+        else if (f_scale) sb[2 * BLOCK_N + col] = (n0 + col < p.N) ? __ldg(p.scale + boff) : 1.0f;
+        const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
+        if (f_res && lane < rows_valid && n0 + 64 * cg < p.N) {
+          const float* rp = p.residual + ((size_t)b * p.rows_per_batch + t_warp0 + lane) * p.N + n0 + 64 * cg;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      gemm_epilogue_tile<BLOCK_N, EPI>(p, taddr, grp, n0, orow, rows_valid, zero_row, sb, stage,
-                                  mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
+      gemm2_epilogue_warp<EPI>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage,
+                               mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
-  }
+    if (lane == 0) bulk_wait0();  // all bulk stores of this warp have completed before the CTA may exit
   }
 
   tc_fence_before();
@@ -214,6 +381,19 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
   tmB_lo = tmB_hi;
   if (PASSES == 3 && (rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   GemmParams p = make_gemm_params(a, GEMM2_BLOCK_N);
+  // output tensor maps {N, rows_per_batch, batch}: rows past an utterance are clipped by the TMA store
+  Gemm2OutMaps om;
+  memset(&om, 0, sizeof(om));
+  {
+    const uint64_t c_dims[3] = {(uint64_t)a->N, (uint64_t)a->rows_per_batch, (uint64_t)a->batch};
+    const uint64_t s16[2] = {(uint64_t)a->N * 2, (uint64_t)a->rows_per_batch * a->N * 2};
+    const uint64_t s32[2] = {(uint64_t)a->N * 4, (uint64_t)a->rows_per_batch * a->N * 4};
+    const uint32_t box16[3] = {32, 32, 1}, box32[3] = {16, 32, 1};   // 64-byte rows
+    if (a->out_f32 && (rc = make_tmap(&om.f32, a->out_f32, 3, c_dims, s32, box32, CU_TENSOR_MAP_SWIZZLE_64B,
+                                      CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+    if (a->out_hi && (rc = make_tmap(&om.hi, a->out_hi, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a->out_lo && (rc = make_tmap(&om.lo, a->out_lo, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
   auto kern = gemm_bf16_2sm_kernel<PASSES, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -229,7 +409,7 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
   grid -= grid % 2;
   if (grid < 2) grid = 2;
-  kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, p);
+  kern<<<grid, GEMM2_THREADS, S::TOTAL, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, om, p);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }
@@ -238,9 +418,13 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
 // anything else runs the generic run-time-flag instance.
 template <int PASSES>
 static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
-  const bool gelu = (a->flags & W2V2_GEMM_GELU) != 0, res = a->residual != nullptr;
+  const bool gelu = (a->flags & W2V2_GEMM_GELU) != 0, res = a->residual != nullptr, sc = a->scale != nullptr;
   const bool f32 = a->out_f32 != nullptr, hi = a->out_hi != nullptr, lo = a->out_lo != nullptr;
   constexpr int LO = (PASSES == 3) ? EPI_LO : 0;     // the model writes hi+lo planes exactly in 3-pass mode
+  if (sc) {
+    if (gelu && !res && !f32 && hi && lo == (PASSES == 3)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | EPI_GELU | EPI_HI | LO>(a, s);
+    return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
+  }
   if (lo == (PASSES == 3) || !hi) {
     if (gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_GELU | EPI_HI | LO>(a, s);
     if (gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_GELU | EPI_F32>(a, s);

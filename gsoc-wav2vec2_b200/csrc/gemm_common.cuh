@@ -16,7 +16,7 @@ constexpr int GEMM_REGS_CONTROL = 56;   // setmaxnreg split: 128 x 56 + 256 x 22
 constexpr int GEMM_REGS_EPILOGUE = 224;
 
 // epilogue recipe bits (template parameter EPI of the kernels; EPI < 0 = decide from GemmParams at run time)
-constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16;
+constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16, EPI_SCALE = 32;
 constexpr int EPI_RUNTIME = -1;
 
 struct GemmParams {
@@ -30,7 +30,9 @@ struct GemmParams {
   int gelu;
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
   int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
-  const float* bias;      // [N] or null
+  const float* bias;      // [N] (or [batch][N] with bias_bstride = N) or null
+  const float* scale;     // optional per-column scale applied before the bias, [N] or [batch][N]
+  int bias_bstride;       // elements between batch entries of bias / scale (0 = shared)
   const float* residual;  // fp32 [batch*rows_per_batch, N] or null
   const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
   float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
@@ -56,6 +58,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   const bool f_f32 = (EPI >= 0) ? bool(EPI & EPI_F32) : (p.out_f32 != nullptr);
   const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
   const bool f_lo = (EPI >= 0) ? bool(EPI & EPI_LO) : (p.out_lo != nullptr);
+  const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
   constexpr int NCH = BLOCK_N / 32;
   constexpr int NMINE = (NCH >= 4) ? NCH / 2 : NCH;  // chunks per warp (grp 1 idles when NCH < 4)
   const int lane = lane_id();
@@ -115,35 +118,65 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     const int n = n0 + c0;
     if (ch >= NCH || n >= p.N) continue;
     const bool full_chunk = (n + 32 <= p.N) && p.vec_ok;
+    if (f_res && full_chunk) {
+      // residual block (32 rows x 128 B): coalesced loads, 8 lanes per row, transposed through the staging buffer
+      const uint8_t* gres = reinterpret_cast<const uint8_t*>(p.residual + orow0 * p.N + n);
+      uint4 t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = 4 * k + (lane >> 3), pc = lane & 7;
+        t[k] = (row < rows_valid) ? __ldg(reinterpret_cast<const uint4*>(gres + (size_t)row * p.N * 4 + pc * 16))
+                                  : make_uint4(0u, 0u, 0u, 0u);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int row = 4 * k + (lane >> 3), pc = lane & 7;
+        *reinterpret_cast<uint4*>(stage + row * 128 + ((pc ^ (row & 7)) << 4)) = t[k];
+      }
+      __syncwarp();
+    }
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
-      float4 rr[4];
-      const size_t off = orow * p.N + n + 16 * hf;
-      if (f_res && row_ok) {
+      float rf[16];
+      if (f_res) {
         if (full_chunk) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(p.residual + off) + j);
+          for (int j = 0; j < 4; ++j) {
+            const float4 q = *reinterpret_cast<const float4*>(stage + lane * 128 + (((4 * hf + j) ^ (lane & 7)) << 4));
+            rf[4 * j + 0] = q.x;
+            rf[4 * j + 1] = q.y;
+            rf[4 * j + 2] = q.z;
+            rf[4 * j + 3] = q.w;
+          }
         } else {
-          float* rf = reinterpret_cast<float*>(rr);
+          const size_t off = orow * p.N + n + 16 * hf;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) rf[j] = (n + 16 * hf + j < p.N) ? __ldg(p.residual + off + j) : 0.0f;
+          for (int j = 0; j < 16; ++j) rf[j] = (row_ok && n + 16 * hf + j < p.N) ? __ldg(p.residual + off + j) : 0.0f;
         }
       }
       float v[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 16 * hf + 4 * j);
-        v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
-        v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
-        v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
-        v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+        if (f_scale) {
+          const float4 sc = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 16 * hf + 4 * j);
+          v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), sc.x, bb.x);
+          v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), sc.y, bb.y);
+          v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), sc.z, bb.z);
+          v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), sc.w, bb.w);
+        } else {
+          v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
+          v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
+          v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
+          v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+        }
       }
       if (f_gelu) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
       }
-      if (f_res && row_ok) {
-        const float* rf = reinterpret_cast<const float*>(rr);
+      if (f_res) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += rf[j];
       }
@@ -218,8 +251,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 // the bias slice goes to smem (one element per epilogue thread), this thread's residual lines are pulled into L2.
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void gemm_epilogue_prepare(const GemmParams& p, int et, int grp, int n0, size_t orow,
-                                                      bool row_ok, float* sb) {
-  if (et < BLOCK_N) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.0f;
+                                                      bool row_ok, float* sb, int b) {
+  const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
+  const size_t boff = (size_t)b * p.bias_bstride + n0 + et;
+  if (et < BLOCK_N) {
+    sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + boff) : 0.0f;
+    if (f_scale) sb[2 * BLOCK_N + et] = (n0 + et < p.N) ? __ldg(p.scale + boff) : 1.0f;  // scale slices follow the bias slices
+  }
   const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
   if (f_res && row_ok) {
 #pragma unroll

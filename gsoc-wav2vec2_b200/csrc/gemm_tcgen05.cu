@@ -27,7 +27,7 @@ struct GemmSmem {
   static constexpr int STAGES = (BLOCK_N == 256) ? 3 : 4;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
-  static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;  // bias slice per accumulator stage
+  static constexpr int BIAS_BYTES = 4 * BLOCK_N * 4;  // per accumulator stage: bias slice; scale slices follow
   static constexpr int EPI_OFF = RING_BYTES + BAR_BYTES + BIAS_BYTES;
   static constexpr int TOTAL = EPI_OFF + GEMM_EPI_STAGE_BYTES + 1024;  // + slack for 1024-byte alignment
 };
@@ -196,7 +196,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
       const size_t orow = (size_t)b * p.rows_per_batch + t;
       float* sb = s_bias + acc * BLOCK_N;
-      gemm_epilogue_prepare<BLOCK_N, EPI_RUNTIME>(p, et, grp, n0, orow, row_ok, sb);
+      gemm_epilogue_prepare<BLOCK_N, EPI_RUNTIME>(p, et, grp, n0, orow, row_ok, sb, b);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -264,6 +264,8 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.bias = a->bias;
+  p.scale = a->scale;
+  p.bias_bstride = a->bias_batch_stride;
   p.residual = a->residual;
   p.row_valid = a->row_valid;
   p.out_f32 = a->out_f32;
@@ -350,16 +352,17 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   // clusters of 2 (weight-tile multicast) for the wide tiles whenever there are at least two m-tiles
   const long m_tiles = (long)a->batch * ((a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   const bool pair = (bn >= 128) && m_tiles >= 2 && a->cluster != 1;
+  const bool can_2sm = (a->N % 8 == 0);
   if (a->passes == 1) {
     switch (bn) {
-      case 256: return pair ? (a->cluster == 3 ? launch_gemm<256, 1, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 1, 1>(a, s);
+      case 256: return pair ? (a->cluster == 3 || !can_2sm ? launch_gemm<256, 1, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 1, 1>(a, s);
       case 128: return pair ? launch_gemm<128, 1, 2>(a, s) : launch_gemm<128, 1, 1>(a, s);
       case 64: return launch_gemm<64, 1, 1>(a, s);
       case 32: return launch_gemm<32, 1, 1>(a, s);
     }
   } else {
     switch (bn) {
-      case 256: return pair ? (a->cluster == 3 ? launch_gemm<256, 3, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 3, 1>(a, s);
+      case 256: return pair ? (a->cluster == 3 || !can_2sm ? launch_gemm<256, 3, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 3, 1>(a, s);
       case 128: return pair ? launch_gemm<128, 3, 2>(a, s) : launch_gemm<128, 3, 1>(a, s);
       case 64: return launch_gemm<64, 3, 1>(a, s);
       case 32: return launch_gemm<32, 3, 1>(a, s);

@@ -40,7 +40,10 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
     for (int i = 0; i < C0_K; ++i) {
       acc[i] += v[i];
 #pragma unroll
-      for (int j = i; j < C0_K; ++j) acc[q++] = fmaf(v[i], v[j], acc[q]);
+      for (int j = i; j < C0_K; ++j) {
+        acc[q] = fmaf(v[i], v[j], acc[q]);
+        ++q;
+      }
     }
   }
   // <= 8 windows per thread were summed in fp32; everything above that is fp64.
@@ -66,8 +69,8 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
 // folded[b][j][c] = w[j][c] * gamma[c] * rstd[b,c];  fbias[b][c] = beta[c] - mean[b,c] * gamma[c] * rstd[b,c]
 __global__ void conv0_fold_kernel(const float* __restrict__ kernel /*[10][C]*/, const float* __restrict__ gamma,
                                   const float* __restrict__ beta, const double* __restrict__ stats, int C, int T0,
-                                  float eps, float* __restrict__ folded /*[B][10][C]*/,
-                                  float* __restrict__ fbias /*[B][C]*/) {
+                                  float eps, float* __restrict__ folded /*[B][10][C] or null*/,
+                                  float* __restrict__ fbias /*[B][C]*/, float* __restrict__ fscale /*[B][C] or null*/) {
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -90,9 +93,44 @@ __global__ void conv0_fold_kernel(const float* __restrict__ kernel /*[10][C]*/, 
   double var = sq / (double)T0 - mean * mean;  // biased variance (tf.nn.moments)
   if (var < 0.0) var = 0.0;
   const double scale = (double)gamma[c] / sqrt(var + (double)eps);
+  if (folded != nullptr) {
 #pragma unroll
-  for (int j = 0; j < C0_K; ++j) folded[((size_t)b * C0_K + j) * C + c] = (float)(w[j] * scale);
+    for (int j = 0; j < C0_K; ++j) folded[((size_t)b * C0_K + j) * C + c] = (float)(w[j] * scale);
+  }
   fbias[(size_t)b * C + c] = (float)((double)beta[c] - mean * scale);
+  if (fscale != nullptr) fscale[(size_t)b * C + c] = (float)scale;
+}
+
+// ------------------------------------------------------------------------------------ conv0 im2col
+// a[b][t][0:64] = bf16(x[b][5t + j]) for j < 10, zero above: one 128-byte row per frame (and per plane).
+__global__ void __launch_bounds__(256) conv0_im2col_kernel(const float* __restrict__ wave, int L, int T0,
+                                                           __nv_bfloat16* __restrict__ a_hi,
+                                                           __nv_bfloat16* __restrict__ a_lo) {
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= T0) return;
+  const float* x = wave + (size_t)b * L + (size_t)t * C0_S;
+  float v[12];
+#pragma unroll
+  for (int j = 0; j < C0_K; ++j) v[j] = __ldg(x + j);
+  v[10] = v[11] = 0.0f;
+  uint32_t hi[6], lo[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) hi[j] = split_bf16x2(v[2 * j], v[2 * j + 1], lo[j]);
+  const size_t row = ((size_t)b * T0 + t) * 64;
+  uint4* ph = reinterpret_cast<uint4*>(a_hi + row);
+  const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+  ph[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  ph[1] = make_uint4(hi[4], hi[5], 0u, 0u);
+#pragma unroll
+  for (int j = 2; j < 8; ++j) ph[j] = z;
+  if (a_lo != nullptr) {
+    uint4* pl = reinterpret_cast<uint4*>(a_lo + row);
+    pl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    pl[1] = make_uint4(lo[4], lo[5], 0u, 0u);
+#pragma unroll
+    for (int j = 2; j < 8; ++j) pl[j] = z;
+  }
 }
 
 // ------------------------------------------------------------------------------------ conv0 main
@@ -278,14 +316,26 @@ extern "C" int w2v2_wave_stats(const float* wave, int batch, int num_samples, do
   return 0;
 }
 
+extern "C" int w2v2_conv0_im2col(const float* wave, int batch, int num_samples, void* a_hi, void* a_lo, void* stream) {
+  W2V2_CHECK_ARG(wave && a_hi, "null pointer");
+  W2V2_CHECK_ARG(batch > 0 && num_samples >= C0_K, "need batch > 0 and at least 10 samples");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int T0 = 1 + (num_samples - C0_K) / C0_S;
+  dim3 grid((T0 + 255) / 256, batch);
+  conv0_im2col_kernel<<<grid, 256, 0, s>>>(wave, num_samples, T0, reinterpret_cast<__nv_bfloat16*>(a_hi),
+                                          reinterpret_cast<__nv_bfloat16*>(a_lo));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int w2v2_conv0_fold(const float* kernel, const float* gamma, const float* beta, const double* stats,
                                int batch, int num_samples, int channels, float eps, float* folded_w,
-                               float* folded_b, void* stream) {
-  W2V2_CHECK_ARG(kernel && gamma && beta && stats && folded_w && folded_b, "null pointer");
+                               float* folded_b, float* scale, void* stream) {
+  W2V2_CHECK_ARG(kernel && gamma && beta && stats && folded_b && (folded_w || scale), "null pointer");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int T0 = 1 + (num_samples - C0_K) / C0_S;
   dim3 grid((channels + 127) / 128, batch);
-  conv0_fold_kernel<<<grid, 128, 0, s>>>(kernel, gamma, beta, stats, channels, T0, eps, folded_w, folded_b);
+  conv0_fold_kernel<<<grid, 128, 0, s>>>(kernel, gamma, beta, stats, channels, T0, eps, folded_w, folded_b, scale);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -53,12 +53,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure)
-// instead of a hung GPU.  ~2^26 polls x (try_wait's own HW sleep) is many seconds.
+// Bounded wait: a protocol bug becomes a trapped launch (cudaErrorLaunchFailure) after ~2 s instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) __trap();
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 

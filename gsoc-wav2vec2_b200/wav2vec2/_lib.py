@@ -25,7 +25,8 @@ class GemmArgs(C.Structure):
         ("w_rows", C.c_int32), ("K", C.c_int32), ("N", C.c_int32), ("rows_per_batch", C.c_int32),
         ("batch", C.c_int32), ("passes", C.c_int32), ("kb_split", C.c_int32), ("block_n", C.c_int32),
         ("max_ctas", C.c_int32), ("cluster", C.c_int32), ("flags", C.c_uint32),
-        ("bias", C.c_void_p), ("residual", C.c_void_p), ("row_valid", C.c_void_p),
+        ("bias", C.c_void_p), ("scale", C.c_void_p), ("bias_batch_stride", C.c_int64),
+        ("residual", C.c_void_p), ("row_valid", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
     ]
 
@@ -49,7 +50,8 @@ SIGNATURES = {
     "w2v2_last_error_string": [],
     "w2v2_gemm_bf16": [C.POINTER(GemmArgs), _P],
     "w2v2_wave_stats": [_P, _I, _I, _P, _P],
-    "w2v2_conv0_fold": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P],
+    "w2v2_conv0_fold": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
+    "w2v2_conv0_im2col": [_P, _I, _I, _P, _P, _P],
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
     "w2v2_split_bf16": [_P, _L, _P, _P, _P],

@@ -56,10 +56,11 @@ def split_bf16(x: torch.Tensor, with_lo: bool) -> Pair:
 
 def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 1,
          a_row_len: Optional[int] = None, a_rows: Optional[int] = None, a_row_stride: Optional[int] = None,
-         a_batch_stride: Optional[int] = None, bias=None, residual=None, row_valid=None, gelu=False,
+         a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
+         row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major."""
-    _need_cuda(a.hi, w.hi, bias, residual, row_valid, out_f32, out_hi, out_lo)
+    _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
     args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if passes == 3 else None
     args.a_row_len = K if a_row_len is None else a_row_len
@@ -72,6 +73,7 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
     args.flags = (_lib.GEMM_GELU if gelu else 0) | (debug << 8)
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
+    args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
 
@@ -82,10 +84,16 @@ def wave_stats(wave: torch.Tensor, stats: torch.Tensor):
     _count(); _lib.check(_lib.load().w2v2_wave_stats(_ptr(wave), B, L, _ptr(stats), _stream()), "w2v2_wave_stats")
 
 
-def conv0_fold(kernel, gamma, beta, stats, B, L, folded_w, folded_b, eps=1e-5):
+def conv0_fold(kernel, gamma, beta, stats, B, L, folded_w, folded_b, eps=1e-5, scale=None):
     C_ = kernel.shape[-1]
     _count(); _lib.check(_lib.load().w2v2_conv0_fold(_ptr(kernel), _ptr(gamma), _ptr(beta), _ptr(stats), B, L, C_, eps,
-                                           _ptr(folded_w), _ptr(folded_b), _stream()), "w2v2_conv0_fold")
+                                           _ptr(folded_w), _ptr(folded_b), _ptr(scale), _stream()), "w2v2_conv0_fold")
+
+
+def conv0_im2col(wave, a: Pair):
+    _need_cuda(wave, a.hi, a.lo)
+    B, L = wave.shape
+    _count(); _lib.check(_lib.load().w2v2_conv0_im2col(_ptr(wave), B, L, _ptr(a.hi), _ptr(a.lo), _stream()), "w2v2_conv0_im2col")
 
 
 def conv0(wave, weights, w_batch_stride, bias, b_batch_stride, gelu, out_f32=None, out_hi=None, out_lo=None,

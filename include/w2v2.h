@@ -61,7 +61,10 @@ typedef struct w2v2_gemm_args {
   int32_t cluster;         /* 0 = auto (256-wide tiles: cta_group::2 CTA pairs), 1 = single CTAs,
                               3 = 1-SM MMAs with pair-multicast weight tiles */
   uint32_t flags;          /* W2V2_GEMM_* */
-  const float* bias;       /* [N] or NULL */
+  const float* bias;       /* [N] (or [batch][N], see bias_batch_stride) or NULL */
+  const float* scale;      /* NULL, or per-column scale applied to the accumulator before the bias:
+                              [N] or [batch][N]  (GroupNorm of extractor layer 0 folded as scale/shift) */
+  int64_t bias_batch_stride; /* elements between batch entries of bias / scale; 0 = shared by all entries */
   const float* residual;   /* fp32 [batch*rows_per_batch][N] or NULL, added after bias/GELU */
   const int32_t* row_valid;/* [batch] or NULL: rows t >= row_valid[b] are stored as zeros
                               (padded frames, encoder.py:253) */
@@ -87,7 +90,11 @@ int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
 int w2v2_wave_stats(const float* wave, int batch, int num_samples, double* stats /*[batch][65]*/, void* stream);
 int w2v2_conv0_fold(const float* kernel /*[10][C] (TF layout [k,1,C])*/, const float* gamma, const float* beta,
                     const double* stats, int batch, int num_samples, int channels, float eps,
-                    float* folded_w /*[batch][10][C]*/, float* folded_b /*[batch][C]*/, void* stream);
+                    float* folded_w /*[batch][10][C] or NULL*/, float* folded_b /*[batch][C]: shift*/,
+                    float* scale /*[batch][C] or NULL: gamma * rstd*/, void* stream);
+/* Tensor-core route for layer 0: windows of the waveform as zero-padded bf16 rows a[b][t][0:64] (taps 0..9 used), to be
+ * multiplied by the raw kernel W[C][64] with w2v2_gemm_bf16 (scale / bias per batch entry, GELU). */
+int w2v2_conv0_im2col(const float* wave, int batch, int num_samples, void* a_hi, void* a_lo, void* stream);
 int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, const float* weights,
                int weights_batch_stride, const float* bias /*or NULL*/, int bias_batch_stride, int gelu,
                float* out_f32, void* out_hi, void* out_lo, void* stream);

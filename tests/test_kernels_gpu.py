@@ -167,6 +167,39 @@ def test_conv0_groupnorm_gelu(L):
 
 
 @pytest.mark.parametrize("passes", [1, 3])
+def test_conv0_tensor_core_route(passes):
+    """Layer 0 as im2col + GEMM with the GroupNorm folded into a per-(b, c) scale / shift epilogue."""
+    torch.manual_seed(9)
+    B, C, L = 3, 512, 20011
+    lo = passes == 3
+    x = torch.randn(B, L)
+    x[1] = x[1] * 0.3 + 0.05
+    kern = torch.randn(10, 1, C) * 0.3
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    ref = O.gelu_erf(O.group_norm_per_channel(O.conv1d_valid(x[:, :, None], kern, None, stride=5), gamma, beta, 1e-5))
+    T0 = ref.shape[1]
+    xd = x.to(DEV)
+    stats = torch.empty(B, 65, dtype=torch.float64, device=DEV)
+    fs, fb = torch.empty(B, C, device=DEV), torch.empty(B, C, device=DEV)
+    ops.wave_stats(xd, stats)
+    ops.conv0_fold(kern.reshape(10, C).to(DEV), gamma.to(DEV), beta.to(DEV), stats, B, L, None, fb, scale=fs)
+    a0 = Pair(torch.empty(B, T0, 64, dtype=torch.bfloat16, device=DEV), torch.empty(B, T0, 64, dtype=torch.bfloat16, device=DEV) if lo else None)
+    ops.conv0_im2col(xd, a0)
+    wg = torch.zeros(C, 64, device=DEV)
+    wg[:, :10] = kern.reshape(10, C).t().to(DEV)
+    w = _pair(wg, lo)
+    hi = torch.empty(B, T0, C, dtype=torch.bfloat16, device=DEV)
+    lo_t = torch.empty_like(hi) if lo else None
+    ops.gemm(a0, w, K=64, N=C, rows_per_batch=T0, batch=B, a_row_len=64, a_rows=T0, a_row_stride=64, a_batch_stride=T0 * 64,
+             bias=fb, scale=fs, bias_batch_stride=C, gelu=True, out_hi=hi, out_lo=lo_t, passes=passes)
+    torch.cuda.synchronize()
+    got = (hi.float() + (lo_t.float() if lo else 0)).cpu()
+    err = (got - ref).abs().max().item()
+    print(f"conv0 tensor-core route passes={passes}: max err {err:.3e} (|ref| max {ref.abs().max():.2f})")
+    assert err < (0.08 if passes == 1 else 3e-4)
+
+
+@pytest.mark.parametrize("passes", [1, 3])
 @pytest.mark.parametrize("T", [145, 768, 49])
 def test_attention(passes, T):
     torch.manual_seed(5)
