@@ -60,6 +60,8 @@ SIGNATURES = {
     "w2v2_ctc_loss": [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "w2v2_ctc_workspace_bytes": [_I, _I, _I],
     "w2v2_frame_argmax": [_P, _L, _I, _P, _P],
+    "w2v2_lm_head_wgrad": [_P, _P, _L, _I, _I, _P, _P, _P],
+    "w2v2_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
 }
 _RESTYPES = {"w2v2_last_error_string": C.c_char_p, "w2v2_ctc_workspace_bytes": C.c_int64}
 

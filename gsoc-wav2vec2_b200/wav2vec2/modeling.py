@@ -492,13 +492,28 @@ class Wav2Vec2ForCTC(_B200Model):
         self.pad_id = config.pad_id
 
     @torch.no_grad()
-    def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
+    def forward_with_hidden(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
+        """(logits [B,T',vocab], encoder output [B*T', hidden] fp32 - an arena view valid until the next call)."""
         self._warn_mask(attention_mask)
-        _, xs, (B, T, d) = self._encode(batch, attention_mask, training)
+        hidden, xs, (B, T, d) = self._encode(batch, attention_mask, training)
         V = self.config.vocab_size
         logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device)
         ops.gemm(xs, self._packed["lm.w"], K=d, N=V, rows_per_batch=B * T, bias=self.variables["lm_head/bias"],
                  out_f32=logits, passes=_PRECISIONS[self.precision], block_n=32)
-        return logits
+        return logits, hidden
+
+    def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
+        return self.forward_with_hidden(batch, attention_mask, training)[0]
 
     call = __call__
+
+    def _repack_lm_head(self):
+        """Refresh the kernel-layout copy of lm_head after an optimizer step (cheap: hidden x vocab)."""
+        if self._packed is None:
+            return
+        w = self.variables["lm_head/kernel"].t().contiguous()
+        V = w.shape[0]
+        Vp = ((V + 31) // 32) * 32
+        if Vp != V:
+            w = torch.cat([w, torch.zeros(Vp - V, w.shape[1], device=self.device)], 0)
+        self._packed["lm.w"] = _split(w, _PRECISIONS[self.precision] == 3)

@@ -152,3 +152,17 @@ def frame_argmax(logits):
     ids = torch.empty(logits.shape[:-1], dtype=torch.int32, device=logits.device)
     _count(); _lib.check(_lib.load().w2v2_frame_argmax(_ptr(logits), rows, V, _ptr(ids), _stream()), "w2v2_frame_argmax")
     return ids
+
+
+def lm_head_wgrad(hidden, grad_logits, grad_kernel, grad_bias):
+    _need_cuda(hidden, grad_logits, grad_kernel, grad_bias)
+    rows, d = hidden.shape
+    V = grad_logits.shape[-1]
+    _count(); _lib.check(_lib.load().w2v2_lm_head_wgrad(_ptr(hidden), _ptr(grad_logits), rows, d, V, _ptr(grad_kernel),
+                                              _ptr(grad_bias), _stream()), "w2v2_lm_head_wgrad")
+
+
+def adam(w, g, m, v, lr_t, beta1, beta2, eps):
+    _need_cuda(w, g, m, v)
+    _count(); _lib.check(_lib.load().w2v2_adam(_ptr(w), _ptr(g), _ptr(m), _ptr(v), w.numel(), float(lr_t), float(beta1),
+                                     float(beta2), float(eps), _stream()), "w2v2_adam")

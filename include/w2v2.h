@@ -152,6 +152,18 @@ int w2v2_ctc_loss(const float* logits /*[batch][frames][vocab]*/, const int32_t*
  * Wav2Vec2Processor.decode (processor.py:71-89; tests/test_wav2vec2.py:159-165). */
 int w2v2_frame_argmax(const float* logits, int64_t rows, int vocab, int32_t* ids, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Stage-1 fine-tune step (src/main.py:210-223: the Wav2Vec2 body is frozen, only lm_head trains).
+ * w2v2_lm_head_wgrad: d loss / d kernel [hidden][vocab] = hidden^T . grad_logits and d loss / d bias
+ *   (backward of tf.keras.layers.Dense at modeling.py:231,254; what Keras fit computes at main.py:217-223).
+ * w2v2_adam: Keras Adam update (main.py:213, training_utils.py:24-31 supplies lr) on a flat fp32 buffer;
+ *   lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) is passed by the host.
+ * ------------------------------------------------------------------------------------------- */
+int w2v2_lm_head_wgrad(const float* hidden /*[rows][hidden_size]*/, const float* grad_logits /*[rows][vocab]*/,
+                       int64_t rows, int hidden_size, int vocab, float* grad_kernel, float* grad_bias, void* stream);
+int w2v2_adam(float* weights, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+              float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,51 @@ def test_batch_sharding_gives_identical_logits():
     full = m(x)
     parts = torch.cat([m(parallel.shard_batch(x, r, 2)) for r in range(2)])
     assert torch.equal(full, parts)
+
+
+def test_stage1_train_step_matches_torch_autograd():
+    """src/main.py:210-223 (head-only fine-tuning): CTC loss, lm_head gradients and the Keras-Adam update of the CUDA step
+    vs torch autograd + torch.optim.Adam(eps=1e-7) on the same hidden states."""
+    from wav2vec2 import CTCLoss
+    from wav2vec2.training import Stage1Trainer
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.0, apply_spec_augment=False)
+    m, params = _build(Wav2Vec2ForCTC, cfg, "bf16x3", seed=4)
+    B, L = 3, 16000
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(1))
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 12))).int()
+    labels[1, 7:] = 0
+    trainer = Stage1Trainer(m, CTCLoss(cfg, (B, L), division_factor=B), learning_rate=1e-3)
+    _, hidden = m.forward_with_hidden(x.cuda(), training=True)
+    h = hidden.clone().cpu().double()
+    W0 = params["lm_head/kernel"].double().clone().requires_grad_(True)
+    b0 = params["lm_head/bias"].double().clone().requires_grad_(True)
+    loss = trainer.step(x.cuda(), labels.cuda())
+    T = cfg.num_frames(L)
+    logits = (h @ W0 + b0).view(B, T, -1)
+    lp = torch.log_softmax(logits, -1).transpose(0, 1)
+    lens = (labels != 0).sum(-1)
+    ref_loss = torch.nn.functional.ctc_loss(lp, labels.long(), torch.full((B,), T), lens, blank=0, reduction="sum") / B
+    ref_loss.backward()
+    gW, gb = W0.grad.clone(), b0.grad.clone()
+
+    def keras_adam(w, g, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7, t=1):   # Keras (non-amsgrad) update, first step
+        m, v = (1 - b1) * g, (1 - b2) * g * g
+        lr_t = lr * (1 - b2 ** t) ** 0.5 / (1 - b1 ** t)
+        return w.detach() - lr_t * m / (v.sqrt() + eps)
+    W1, b1_ = keras_adam(W0, gW), keras_adam(b0, gb)
+    assert abs(loss.item() - ref_loss.item()) < 1e-3 * max(1.0, abs(ref_loss.item()))
+    got_gW = trainer.flat_g[: trainer.d * trainer.V].view(trainer.d, trainer.V).cpu().double()
+    assert (got_gW - gW).abs().max().item() < 1e-4 * max(1.0, gW.abs().max().item())
+    assert (trainer.flat_g[trainer.d * trainer.V:].cpu().double() - gb).abs().max().item() < 1e-4 * max(1.0, gb.abs().max().item())
+    # the first Adam step is ~ lr * sign(g): only entries whose gradient is well above fp32 noise are comparable
+    big = gW.abs() > 1e-3 * gW.abs().max()
+    dW = (m.variables["lm_head/kernel"].cpu().double() - W1).abs()
+    print(f"stage-1 step: loss {loss.item():.4f} vs {ref_loss.item():.4f}; max |dW - ref| on significant entries {dW[big].max():.2e}")
+    assert dW[big].max().item() < 2e-5 and dW.max().item() < 2.1e-3
+    assert (m.variables["lm_head/bias"].cpu().double() - b1_).abs().max().item() < 2e-5
+    # the packed copy follows the update: a second forward uses the new head
+    logits2 = m(x.cuda())
+    Wn, bn = m.variables["lm_head/kernel"].cpu().double(), m.variables["lm_head/bias"].cpu().double()
+    want = (h @ Wn + bn).view(B, T, -1).float()
+    assert (logits2.cpu() - want).abs().max().item() < 1e-3
