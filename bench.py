@@ -129,7 +129,9 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "audio-sec/s", "value": val, "unit": "audio-sec/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"wav2vec2-base inference, seq={args.seq}, CPU sample batch={CPU_SAMPLE_BATCH}"},
+        "config": {"workload": f"wav2vec2-base inference (Wav2Vec2ForCTC forward), batch={args.batch}/GPU, seq={args.seq} -> "
+                               f"{cfg.num_frames(args.seq)} frames", "global_batch": args.batch * max(world, 1),
+                   "seq_len": args.seq, "note": f"CPU arm: each step is a bounded sample of {CPU_SAMPLE_BATCH} utterances of that workload"},
         "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
