@@ -317,8 +317,28 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const int et = threadIdx.x - 128;  // 0..511
     uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * S::EPI_WARP_BYTES;
     const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
+    // bias (threads 0..255) / scale (threads 256..511) slice of a tile: fetched ONE TILE AHEAD into a register and
+    // parked in smem (double-buffered with the accumulator stage) so that its global-load latency never sits on the
+    // per-tile critical path
+    const int bcol = et & (BLOCK_N - 1);
+    auto fetch_bias = [&](int w) -> float {
+      if (w >= total_work) return 0.0f;
+      const int n0 = (w % p.n_tiles) * BLOCK_N;
+      const int m_tile = min((w / p.n_tiles) * 2 + crank, total_m_tiles - 1);
+      const size_t boff = (size_t)(m_tile / p.tiles_per_batch) * p.bias_bstride + n0 + bcol;
+      if (et < BLOCK_N) return (p.bias != nullptr && n0 + bcol < p.N) ? __ldg(p.bias + boff) : 0.0f;
+      return (f_scale && n0 + bcol < p.N) ? __ldg(p.scale + boff) : 1.0f;
+    };
+    auto park_bias = [&](int acc, float v) {
+      float* sb = s_bias + acc * BLOCK_N;
+      if (et < BLOCK_N) sb[bcol] = v;
+      else if (f_scale) sb[2 * BLOCK_N + bcol] = v;
+    };
+    const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
     int acc = 0;
     uint32_t acc_phase = 0;
+    park_bias(0, fetch_bias(pair_id));
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     for (int w = pair_id; w < total_work; w += num_pairs) {
       const int n_tile = w % p.n_tiles;
       const int m_raw = (w / p.n_tiles) * 2 + crank;
@@ -328,26 +348,20 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const int n0 = n_tile * BLOCK_N;
       const int rows_valid = (m_raw < total_m_tiles) ? min(32, p.rows_per_batch - t_warp0) : 0;
       const bool zero_row = p.row_valid != nullptr && t_warp0 + lane >= p.row_valid[b];
-      float* sb = s_bias + acc * BLOCK_N;
-      // bias (threads 0..255) and scale (threads 256..511) slices of this tile -> smem, before the accumulator is ready
-      {
-        const int col = et & (BLOCK_N - 1);
-        const size_t boff = (size_t)b * p.bias_bstride + n0 + col;
-        if (et < BLOCK_N) sb[col] = (p.bias != nullptr && n0 + col < p.N) ? __ldg(p.bias + boff) : 0.0f;
-        else if (f_scale) sb[2 * BLOCK_N + col] = (n0 + col < p.N) ? __ldg(p.scale + boff) : 1.0f;
-        const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
-        if (f_res && lane < rows_valid && n0 + 64 * cg < p.N) {
-          const float* rp = p.residual + ((size_t)b * p.rows_per_batch + t_warp0 + lane) * p.N + n0 + 64 * cg;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
+      const float* sb = s_bias + acc * BLOCK_N;
+      const float next_bias = fetch_bias(w + num_pairs);   // in flight during this tile's epilogue
+      if (f_res && lane < rows_valid && n0 + 64 * cg < p.N) {
+        const float* rp = p.residual + ((size_t)b * p.rows_per_batch + t_warp0 + lane) * p.N + n0 + 64 * cg;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
       gemm2_epilogue_warp<EPI>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage,
                                mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
+      park_bias(acc ^ 1, next_bias);
+      asm volatile("bar.sync 1, 512;" ::: "memory");   // every warp is done with this tile's slice; the next one is visible
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
