@@ -151,6 +151,8 @@ class _B200Model:
         self.trainable = {k: True for k in self.variables}
         self._packed = None
         self._arena = None
+        self._use_graph = os.environ.get("W2V2_CUDA_GRAPH", "0") == "1"
+        self._graphs = {}
 
     @staticmethod
     def _check_supported(cfg):
@@ -457,6 +459,40 @@ class _B200Model:
             xs_f32 = out_f32
         return xs_f32, xs, (B, T, d)
 
+    # ---------------------------------------------------------------- CUDA graphs
+    def enable_cuda_graph(self, on=True):
+        """Replay the whole forward (about 100 kernel launches) as ONE CUDA graph per (batch, length, mask) shape.
+        Every activation lives in the arena at a fixed address and every launch goes to the current stream, so the eager
+        path is captured as is; it matters for small batches, where launch latency dominates."""
+        self._use_graph = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
+
+    def _graphed(self, fn, batch, attention_mask):
+        """Run ``fn(static_batch, static_mask)`` through a cached CUDA graph keyed by the input shapes."""
+        key = (tuple(batch.shape), attention_mask is not None, fn.__name__)
+        entry = self._graphs.get(key)
+        if entry is None:
+            sx = torch.empty(tuple(batch.shape), dtype=torch.float32, device=self.device)
+            sm = None if attention_mask is None else torch.empty(tuple(attention_mask.shape), dtype=torch.int32, device=self.device)
+            sx.copy_(batch)
+            if sm is not None:
+                sm.copy_(attention_mask)
+            fn(sx, sm)                                   # warm-up: packs weights, allocates the arena, sets attributes
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                outs = fn(sx, sm)
+            entry = (graph, sx, sm, outs)
+            self._graphs[key] = entry
+        graph, sx, sm, outs = entry
+        sx.copy_(batch, non_blocking=True)
+        if sm is not None:
+            sm.copy_(attention_mask, non_blocking=True)
+        graph.replay()
+        return outs
+
     def _warn_mask(self, attention_mask):
         # modeling.py:183-186
         if self.config.is_robust and attention_mask is None:
@@ -472,9 +508,15 @@ class Wav2Vec2Model(_B200Model):
     def __init__(self, config: Wav2Vec2Config, input_shape=(1, 246000), name="wav2vec2", precision=None, device=None):
         self._setup(config, input_shape, name, precision, device)
 
+    def _hidden_eager(self, batch, attention_mask):
+        x_f32, _, (B, T, d) = self._encode(batch, attention_mask, False)
+        return x_f32.view(B, T, d)
+
     @torch.no_grad()
     def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
         self._warn_mask(attention_mask)
+        if self._use_graph and not training:
+            return self._graphed(self._hidden_eager, batch, attention_mask).clone()
         x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
         return x_f32.view(B, T, d).clone()
 
@@ -491,10 +533,19 @@ class Wav2Vec2ForCTC(_B200Model):
         self._setup(config, input_shape, name, precision, device)
         self.pad_id = config.pad_id
 
+    def _ctc_eager(self, batch, attention_mask):
+        return self._forward_impl(batch, attention_mask, False)
+
     @torch.no_grad()
     def forward_with_hidden(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
         """(logits [B,T',vocab], encoder output [B*T', hidden] fp32 - an arena view valid until the next call)."""
         self._warn_mask(attention_mask)
+        if self._use_graph and not training:
+            logits, hidden = self._graphed(self._ctc_eager, batch, attention_mask)
+            return logits.clone(), hidden
+        return self._forward_impl(batch, attention_mask, training)
+
+    def _forward_impl(self, batch, attention_mask, training):
         hidden, xs, (B, T, d) = self._encode(batch, attention_mask, training)
         V = self.config.vocab_size
         logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device)

@@ -148,3 +148,19 @@ def test_stage1_train_step_matches_torch_autograd():
     Wn, bn = m.variables["lm_head/kernel"].cpu().double(), m.variables["lm_head/bias"].cpu().double()
     want = (h @ Wn + bn).view(B, T, -1).float()
     assert (logits2.cpu() - want).abs().max().item() < 1e-3
+
+
+def test_cuda_graph_replay_is_bit_identical():
+    """The whole forward replayed as one CUDA graph gives the same logits as the eager launch sequence, also with a mask."""
+    cfg = RobustWav2Vec2Config(num_layers=2)
+    m, _ = _build(Wav2Vec2ForCTC, cfg, "bf16")
+    g = torch.Generator().manual_seed(7)
+    x1, x2 = torch.randn(2, 16000, generator=g).cuda(), torch.randn(2, 16000, generator=g).cuda()
+    am = torch.ones(2, 16000, dtype=torch.int32, device="cuda")
+    am[1, -3000:] = 0
+    eager1, eager2 = m(x1, attention_mask=am), m(x2, attention_mask=am)
+    m.enable_cuda_graph(True)
+    assert torch.equal(m(x1, attention_mask=am), eager1)
+    assert torch.equal(m(x2, attention_mask=am), eager2)      # replay with new data in the static input buffer
+    assert torch.equal(m(x1, attention_mask=am), eager1)
+    assert len(m._graphs) == 1
