@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--seq", type=int, default=246000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the ~100 kernels of a forward eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -179,6 +180,11 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput
+    n0 = ops.LAUNCHES
+    model(x)                                   # eager: packs weights, sizes the arena, counts the kernels of one forward
+    launches_per_forward = ops.LAUNCHES - n0
+    if not args.no_graph:
+        model.enable_cuda_graph(True)          # public API: the same launch sequence replayed as one CUDA graph per step
     for _ in range(W):
         model(x)
     barrier()
@@ -190,7 +196,7 @@ def main():
             logits = model(x)
         e1.record()
         barrier()
-    launches = ops.LAUNCHES - launches0
+    launches = (ops.LAUNCHES - launches0) if args.no_graph else launches_per_forward * K   # kernels inside the replays
     ms = e0.elapsed_time(e1)
     # ---------------- end to end through the public API: pinned host input -> logits on the host, every step.
     # The input copy of step i+1 runs on a copy stream into the other of two device buffers while step i computes;
@@ -234,6 +240,7 @@ def main():
     ms, ms_e2e = t.tolist()
 
     # ---------------- per-kernel-class device times (CUDA events on the launching stream)
+    model.enable_cuda_graph(False)             # per-kernel events need the eager launch sequence
     breakdown, gemm_ffn1 = profile_classes(model, x, cfg, steps=min(K, 5))
 
     if rank != 0:
@@ -256,7 +263,8 @@ def main():
         "config": {"workload": f"wav2vec2-base inference (Wav2Vec2ForCTC forward), batch={B}/GPU, seq={L} -> {T} frames",
                    "global_batch": B * world, "seq_len": L, "parallelism": f"dp{world} (batch sharded, no collective)",
                    "l2": "activations per step (> 3 GB) far exceed the 126 MB L2; no explicit flush needed",
-                   "weights": "random init (seeded), no checkpoint offline"},
+                   "weights": "random init (seeded), no checkpoint offline",
+                   "launch": "eager" if args.no_graph else "one CUDA graph replay per step (public enable_cuda_graph())"},
         "clocks": clk.summary(),
         "e2e": {"value": e2e, "unit": "audio-sec/s", "h2d_bytes_per_step": x_host.numel() * 4,
                 "d2h_bytes_per_step": out_host.numel() * 4},
