@@ -110,6 +110,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_s = tmem_base;
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_o = tmem_base + 128;
 
   if (warp >= 4) {
@@ -377,8 +379,7 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
     attr_set = true;
   }
   dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
-  kern<<<grid, AT_THREADS, S::TOTAL, stream>>>(tm_hi, tm_lo, p);
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(kern, grid, dim3(AT_THREADS), (size_t)S::TOTAL, stream, 0, tm_hi, tm_lo, p));
   return 0;
 }
 

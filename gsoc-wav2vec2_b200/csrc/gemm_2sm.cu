@@ -236,6 +236,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // prologue above overlapped the previous kernel; from here on its results are visible
   if (warp < 4) {
     // warpgroup 0 (TMA / MMA / TMEM-alloc warps) gives registers away ...
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM2_REGS_CONTROL));
@@ -423,8 +425,7 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
   grid -= grid % 2;
   if (grid < 2) grid = 2;
-  kern<<<grid, GEMM2_THREADS, S::TOTAL, stream>>>(tmA_hi, tmA_lo, tmB_hi, tmB_lo, om, p);
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM2_THREADS), (size_t)S::TOTAL, stream, 0, tmA_hi, tmA_lo, tmB_hi, tmB_lo, om, p));
   return 0;
 }
 

@@ -89,6 +89,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (CLUSTER > 1) cluster_sync_all(); else __syncthreads();  // peers' barriers are initialised before any multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();  // prologue above overlapped the previous kernel; from here on its results are visible
   if (warp < 4) {
   // warpgroup 0 (TMA / MMA / TMEM-alloc warps) gives registers away ...
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GEMM_REGS_CONTROL));
@@ -220,6 +222,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
 // ------------------------------------------------------------------------------------------- host
 thread_local char g_last_error[512] = "";
 
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("W2V2_PDL");
+    on = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return on != 0;
+}
+
 PFN_encodeTiled get_encode_fn() {
   static PFN_encodeTiled fn = nullptr;
   if (fn == nullptr) {
@@ -315,19 +326,8 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   if (a->max_ctas > 0 && grid > a->max_ctas) grid = a->max_ctas;
   grid -= grid % CLUSTER;
   if (grid < CLUSTER) grid = CLUSTER;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(GEMM_THREADS);
-  cfg.dynamicSmemBytes = S::TOTAL;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CLUSTER;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  W2V2_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA_hi, tmA_lo, tmB_hi, tmB_lo, p));
+  W2V2_CUDA(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), (size_t)S::TOTAL, stream, CLUSTER > 1 ? CLUSTER : 0, tmA_hi, tmA_lo,
+                       tmB_hi, tmB_lo, p));
   return 0;
 }
 

@@ -86,6 +86,8 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();
+  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -230,8 +232,7 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
   auto kern = posconv_kernel<PASSES>;
   W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
   dim3 grid((a->frames + p.mt * 128 - 1) / (p.mt * 128), a->groups, a->batch);
-  kern<<<grid, PC_THREADS, smem_bytes, stream>>>(tm_hi, tm_lo, p);
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(kern, grid, dim3(PC_THREADS), (size_t)smem_bytes, stream, 0, tm_hi, tm_lo, p));
   return 0;
 }
 

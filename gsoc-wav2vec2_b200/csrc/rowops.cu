@@ -24,6 +24,8 @@ constexpr int STATS_WIN_PER_BLOCK = 2048;
 // ------------------------------------------------------------------------------------ wave_stats
 __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wave, int L, int T0,
                                                          double* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const float* x = wave + (size_t)b * L;
   const int w_begin = blockIdx.x * STATS_WIN_PER_BLOCK;
@@ -71,6 +73,8 @@ __global__ void conv0_fold_kernel(const float* __restrict__ kernel /*[10][C]*/, 
                                   const float* __restrict__ beta, const double* __restrict__ stats, int C, int T0,
                                   float eps, float* __restrict__ folded /*[B][10][C] or null*/,
                                   float* __restrict__ fbias /*[B][C]*/, float* __restrict__ fscale /*[B][C] or null*/) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -106,6 +110,8 @@ __global__ void conv0_fold_kernel(const float* __restrict__ kernel /*[10][C]*/, 
 __global__ void __launch_bounds__(256) conv0_im2col_kernel(const float* __restrict__ wave, int L, int T0,
                                                            __nv_bfloat16* __restrict__ a_hi,
                                                            __nv_bfloat16* __restrict__ a_lo) {
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.y;
   const int t = blockIdx.x * 256 + threadIdx.x;
   if (t >= T0) return;
@@ -236,6 +242,8 @@ __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                int rows, int d, int gelu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                __nv_bfloat16* __restrict__ out_lo) {
+  pdl_trigger();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = lane_id();
@@ -311,8 +319,7 @@ extern "C" int w2v2_wave_stats(const float* wave, int batch, int num_samples, do
   const int T0 = 1 + (num_samples - C0_K) / C0_S;
   W2V2_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * C0_NSTAT * batch, s));
   dim3 grid((T0 + STATS_WIN_PER_BLOCK - 1) / STATS_WIN_PER_BLOCK, batch);
-  wave_stats_kernel<<<grid, 256, 0, s>>>(wave, num_samples, T0, stats);
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(wave_stats_kernel, grid, dim3(256), 0, s, 0, wave, num_samples, T0, stats));
   return 0;
 }
 
@@ -322,9 +329,8 @@ extern "C" int w2v2_conv0_im2col(const float* wave, int batch, int num_samples, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int T0 = 1 + (num_samples - C0_K) / C0_S;
   dim3 grid((T0 + 255) / 256, batch);
-  conv0_im2col_kernel<<<grid, 256, 0, s>>>(wave, num_samples, T0, reinterpret_cast<__nv_bfloat16*>(a_hi),
-                                          reinterpret_cast<__nv_bfloat16*>(a_lo));
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(conv0_im2col_kernel, grid, dim3(256), 0, s, 0, wave, num_samples, T0,
+                       reinterpret_cast<__nv_bfloat16*>(a_hi), reinterpret_cast<__nv_bfloat16*>(a_lo)));
   return 0;
 }
 
@@ -335,8 +341,8 @@ extern "C" int w2v2_conv0_fold(const float* kernel, const float* gamma, const fl
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int T0 = 1 + (num_samples - C0_K) / C0_S;
   dim3 grid((channels + 127) / 128, batch);
-  conv0_fold_kernel<<<grid, 128, 0, s>>>(kernel, gamma, beta, stats, channels, T0, eps, folded_w, folded_b, scale);
-  W2V2_CUDA(cudaGetLastError());
+  W2V2_CUDA(launch_pdl(conv0_fold_kernel, grid, dim3(128), 0, s, 0, kernel, gamma, beta, stats, channels, T0, eps, folded_w,
+                       folded_b, scale));
   return 0;
 }
 
@@ -383,10 +389,9 @@ extern "C" int w2v2_ln_rows(const float* x, const float* gamma, const float* bet
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   if (d <= 1024)
-    ln_rows_kernel<8><<<grid, 256, 0, s>>>(x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo);
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo));
   else
-    ln_rows_kernel<16><<<grid, 256, 0, s>>>(x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo);
-  W2V2_CUDA(cudaGetLastError());
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo));
   return 0;
 }
 

@@ -25,6 +25,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// --------------------------------------------------------------------------- programmatic dependent launch
+// Every forward-path kernel is launched with programmatic stream serialization: it may START while its predecessor
+// is still draining (prologue: barrier init, TMEM alloc, tensor-map prefetch overlap the predecessor's tail), and
+// must call pdl_wait() before touching global memory.  pdl_trigger() lets the successor start as early as possible.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // --------------------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
