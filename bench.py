@@ -270,7 +270,7 @@ def main():
                 "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches,
         "model_tflops": fl["total"] * B * world / (ms / K / 1e3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}] + bias + erf-GELU",
+        "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}] + bias + GELU",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["bf16_tflops"]) if achieved else None, "traffic": None,
                      "peak_source": peaks["source"] + " (burst cuBLAS bf16; sustained %.0f)" % peaks["bf16_tflops_sustained"]},
@@ -329,6 +329,7 @@ def profile_classes(model, x, cfg, steps):
     wrap("gemm", gemm_label)
     wrap("conv0", lambda *a, **kw: "conv0")
     wrap("conv0_im2col", lambda *a, **kw: "conv0")
+    wrap("conv0_gn_gelu", lambda *a, **kw: "conv0")
     wrap("wave_stats", lambda *a, **kw: "conv0 stats+fold")
     wrap("conv0_fold", lambda *a, **kw: "conv0 stats+fold")
     wrap("ln_rows", lambda *a, **kw: "layernorm")

@@ -60,6 +60,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
                                                     const float* sb, uint8_t* stage, uint32_t tmem_empty_cluster_addr) {
   constexpr int BLOCK_N = GEMM2_BLOCK_N;
   const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
+  const bool f_fast = (EPI >= 0) ? bool(EPI & EPI_FASTGELU) : (p.gelu == 2);  // tanh-form GELU: single-pass mode
   const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
   const bool f_f32 = (EPI >= 0) ? bool(EPI & EPI_F32) : (p.out_f32 != nullptr);
   const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
@@ -132,8 +133,13 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
       }
     }
     if (f_gelu) {
+      if (f_fast) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+        for (int j = 0; j < 16; j += 2) gelu_x2<true>(v[j], v[j + 1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) gelu_x2<false>(v[j], v[j + 1]);
+      }
     }
     if (f_res && lane < rows_valid) {
 #pragma unroll
@@ -436,13 +442,14 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
   const bool gelu = (a->flags & W2V2_GEMM_GELU) != 0, res = a->residual != nullptr, sc = a->scale != nullptr;
   const bool f32 = a->out_f32 != nullptr, hi = a->out_hi != nullptr, lo = a->out_lo != nullptr;
   constexpr int LO = (PASSES == 3) ? EPI_LO : 0;     // the model writes hi+lo planes exactly in 3-pass mode
+  constexpr int G = EPI_GELU | ((PASSES == 1) ? EPI_FASTGELU : 0);   // single-pass mode: bf16-grade tanh-form GELU
   if (sc) {
-    if (gelu && !res && !f32 && hi && lo == (PASSES == 3)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | EPI_GELU | EPI_HI | LO>(a, s);
+    if (gelu && !res && !f32 && hi && lo == (PASSES == 3)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | G | EPI_HI | LO>(a, s);
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
   }
   if (lo == (PASSES == 3) || !hi) {
-    if (gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_GELU | EPI_HI | LO>(a, s);
-    if (gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_GELU | EPI_F32>(a, s);
+    if (gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, G | EPI_HI | LO>(a, s);
+    if (gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, G | EPI_F32>(a, s);
     if (!gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_F32>(a, s);
     if (!gelu && !res && f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_F32 | EPI_HI | LO>(a, s);
     if (!gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_HI | LO>(a, s);

@@ -16,7 +16,8 @@ constexpr int GEMM_REGS_CONTROL = 56;   // setmaxnreg split: 128 x 56 + 256 x 22
 constexpr int GEMM_REGS_EPILOGUE = 224;
 
 // epilogue recipe bits (template parameter EPI of the kernels; EPI < 0 = decide from GemmParams at run time)
-constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16, EPI_SCALE = 32;
+constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16, EPI_SCALE = 32,
+              EPI_FASTGELU = 64;  // tanh-form GELU (single-pass mode only; see gelu_tanh_p2)
 constexpr int EPI_RUNTIME = -1;
 
 struct GemmParams {
@@ -27,7 +28,7 @@ struct GemmParams {
   int batch;
   int n_tiles;          // ceil(N / BLOCK_N)
   int N;                // valid output columns == leading dimension of every output / residual
-  int gelu;
+  int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form (single-pass mode)
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
   int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
   const float* bias;      // [N] (or [batch][N] with bias_bstride = N) or null
@@ -54,6 +55,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
                                                    uint32_t tmem_empty_cluster_addr) {
   // compile-time epilogue recipe (EPI >= 0) or run-time flags (EPI < 0)
   const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
+  const bool f_fast = (EPI >= 0) ? bool(EPI & EPI_FASTGELU) : (p.gelu == 2);  // tanh-form GELU: single-pass mode
   const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
   const bool f_f32 = (EPI >= 0) ? bool(EPI & EPI_F32) : (p.out_f32 != nullptr);
   const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
@@ -173,8 +175,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         }
       }
       if (f_gelu) {
+        if (f_fast) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) gelu_erf_x2(v[j], v[j + 1]);
+          for (int j = 0; j < 16; j += 2) gelu_x2<true>(v[j], v[j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) gelu_x2<false>(v[j], v[j + 1]);
+        }
       }
       if (f_res) {
 #pragma unroll

@@ -271,7 +271,7 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.batch = a->batch;
   p.n_tiles = (a->N + block_n - 1) / block_n;
   p.N = a->N;
-  p.gelu = (a->flags & W2V2_GEMM_GELU) ? 1 : 0;
+  p.gelu = (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form (single-pass mode)
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.bias = a->bias;

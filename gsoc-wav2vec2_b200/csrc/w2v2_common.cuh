@@ -353,6 +353,34 @@ __device__ __forceinline__ void gelu_erf_x2(float& x0, float& x1) {
   x1 = fmaf(-ax1, e1, fmaxf(x1, 0.0f));
 }
 
+// bf16-grade GELU for the single-pass (throughput) mode, two at once on the packed pipe: gelu(x) ~= hx + hx * tanh(x (A + B x^2)),
+// hx = x / 2, (A, B) a minimax refit of the tanh form against the erf form (formula error 2.7e-4, + MUFU.TANH's 2^-11:
+// < 5e-4 absolute for |x| < 2, i.e. below the 2^-9 relative rounding of the bf16 output; tools/fit_gelu.py --tanh).
+// 3 FMUL2 + 2 FFMA2 + 2 MUFU.TANH per pair - about half the issue slots of gelu_erf_x2.  Parity mode never uses it.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint64_t gelu_tanh_p2(uint64_t v) {
+  const uint64_t x2 = mul2(v, v);
+  const uint64_t p = fma2(x2, pack2(0.03471371f, 0.03471371f), pack2(0.80012897f, 0.80012897f));
+  const uint64_t u = mul2(v, p);
+  float u0, u1;
+  unpack2(u, u0, u1);
+  const uint64_t t = pack2(tanh_approx(u0), tanh_approx(u1));
+  const uint64_t h = mul2(v, pack2(0.5f, 0.5f));
+  return fma2(h, t, h);
+}
+template <bool FAST>
+__device__ __forceinline__ void gelu_x2(float& x0, float& x1) {
+  if (FAST) {
+    unpack2(gelu_tanh_p2(pack2(x0, x1)), x0, x1);
+  } else {
+    gelu_erf_x2(x0, x1);
+  }
+}
+
 // ---- bf16 packing and hi/lo splitting (x ~= hi + lo, both bf16: ~16 mantissa bits) ----
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -254,10 +254,6 @@ class _B200Model:
         P = {}
         # conv 0: TF [10,1,C] -> [10][C] fp32
         P["conv0.w"] = v["wav2vec2/feature_extractor/conv_layers/0/conv/kernel"].reshape(cfg.kernal_sizes[0], -1).contiguous()
-        # tensor-core route for layer 0: W[C][64], taps 0..9 used (rows of the im2col operand are 64 wide)
-        wg = torch.zeros(P["conv0.w"].shape[1], 64, device=dev)
-        wg[:, : cfg.kernal_sizes[0]] = P["conv0.w"].t()
-        P["conv0.wg"] = _split(wg, lo)
         for i in range(1, len(cfg.filter_sizes)):
             kern = v[f"wav2vec2/feature_extractor/conv_layers/{i}/conv/kernel"]      # [k, cin, cout]
             k, cin, cout = kern.shape
@@ -331,19 +327,15 @@ class _B200Model:
         T0 = frames[0]
         act = A.pair("c0", (B, T0, C0), lo)
         if not layer_norm_convs:
-            # GroupNorm statistics from the waveform alone, folded to a per-(b, c) scale / shift; the conv itself runs on
-            # the tensor cores: im2col rows (10 taps, zero-padded to 64) x raw kernel, scale/shift + GELU in the epilogue
+            # GroupNorm statistics from the waveform alone, folded to a per-(b, c) scale / shift; conv + scale/shift + GELU
+            # in one kernel (window products on the tensor cores from an smem copy of the waveform, no im2col tensor)
             stats = A.get("c0.stats", (B, 65), torch.float64)
             fs = A.get("c0.fs", (B, C0), f32)
             fb = A.get("c0.fb", (B, C0), f32)
-            a0 = A.pair("c0.a", (B, T0, 64), lo)
             ops.wave_stats(x, stats)
             ops.conv0_fold(P["conv0.w"], v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], stats, B, L, None, fb,
                            1e-5, scale=fs)
-            ops.conv0_im2col(x, a0)
-            ops.gemm(a0, P["conv0.wg"], K=64, N=C0, rows_per_batch=T0, batch=B, a_row_len=64, a_rows=T0, a_row_stride=64,
-                     a_batch_stride=T0 * 64, bias=fb, scale=fs, bias_batch_stride=C0, gelu=True, out_hi=act.hi,
-                     out_lo=act.lo, passes=passes)
+            ops.conv0_gn_gelu(x, P["conv0.w"], fs, fb, act, passes)
         else:
             raw_elems = max(B * t * c for t, c in zip(frames, cfg.filter_sizes))
             raw_flat = A.get("conv.raw", (raw_elems,), f32)   # pre-norm conv output, reused by every layer

@@ -96,6 +96,15 @@ def conv0_im2col(wave, a: Pair):
     _count(); _lib.check(_lib.load().w2v2_conv0_im2col(_ptr(wave), B, L, _ptr(a.hi), _ptr(a.lo), _stream()), "w2v2_conv0_im2col")
 
 
+def conv0_gn_gelu(wave, kernel, scale, shift, out: Pair, passes=1):
+    """Fused extractor layer 0: conv (tensor cores, no im2col) + folded GroupNorm + GELU, written once."""
+    _need_cuda(wave, kernel, scale, shift, out.hi, out.lo)
+    B, L = wave.shape
+    _count(); _lib.check(_lib.load().w2v2_conv0_gn_gelu(_ptr(wave), B, L, kernel.shape[-1], _ptr(kernel), _ptr(scale),
+                                              _ptr(shift), _ptr(out.hi), _ptr(out.lo), passes, _stream()),
+                         "w2v2_conv0_gn_gelu")
+
+
 def conv0(wave, weights, w_batch_stride, bias, b_batch_stride, gelu, out_f32=None, out_hi=None, out_lo=None,
           channels=512):
     _need_cuda(wave, weights, bias, out_f32, out_hi, out_lo)

@@ -95,6 +95,13 @@ int w2v2_conv0_fold(const float* kernel /*[10][C] (TF layout [k,1,C])*/, const f
 /* Tensor-core route for layer 0: windows of the waveform as zero-padded bf16 rows a[b][t][0:64] (taps 0..9 used), to be
  * multiplied by the raw kernel W[C][64] with w2v2_gemm_bf16 (scale / bias per batch entry, GELU). */
 int w2v2_conv0_im2col(const float* wave, int batch, int num_samples, void* a_hi, void* a_lo, void* stream);
+/* Fused layer 0 (the HBM-bound kernel of the path): out = gelu(scale[b][c] * conv(wave)[b][t][c] + shift[b][c]) as bf16
+ * hi (passes == 1; tanh-form bf16-grade GELU) or hi + lo planes (passes == 3; erf-exact GELU).  kernel = raw TF kernel
+ * [10][C], scale / shift = outputs of w2v2_conv0_fold.  The window products run on the tensor cores straight from a
+ * shared-memory copy of the waveform slice: no im2col tensor, the activation is written once. */
+int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples, int channels, const float* kernel /*[10][C]*/,
+                       const float* scale /*[batch][C]*/, const float* shift /*[batch][C]*/, void* out_hi,
+                       void* out_lo /*NULL unless passes == 3*/, int passes, void* stream);
 int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, const float* weights,
                int weights_batch_stride, const float* bias /*or NULL*/, int bias_batch_stride, int gelu,
                float* out_f32, void* out_hi, void* out_lo, void* stream);

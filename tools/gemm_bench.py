@@ -12,7 +12,11 @@ from wav2vec2.ops import Pair  # noqa: E402
 
 dev = "cuda"
 shapes = [("ffn1", 24576, 768, 3072, True), ("qkv", 24576, 768, 2304, False), ("out", 24576, 768, 768, False),
-          ("ffn2", 24576, 3072, 768, False), ("conv1-like", 24576 * 8, 1536, 512, True)]
+          ("ffn2", 24576, 3072, 768, False), ("conv1-like", 24576 * 8, 1536, 512, True),
+          ("out+res32", 24576, 768, 768, "res"), ("ffn2+res32", 24576, 3072, 768, "res"), ("out f32", 24576, 768, 768, "f32")]
+only = os.environ.get("ONLY")
+if only:
+    shapes = [s for s in shapes if s[0] in only.split(",")]
 variants = [int(v) for v in os.environ.get("VARIANTS", "0,1,3").split(",")]
 iters = int(os.environ.get("ITERS", "10"))
 debug = int(os.environ.get("DEBUG", "0"))
@@ -22,13 +26,18 @@ for name, M, K, N, gelu in shapes:
     w = Pair((torch.randn(N, K, device=dev) / math.sqrt(K)).to(torch.bfloat16))
     bias = torch.randn(N, device=dev)
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    res = torch.randn(M, N, device=dev) if gelu == "res" else None
+    o32 = torch.empty(M, N, device=dev) if gelu in ("res", "f32") else None
     for cl in variants:
         ts = []
         for i in range(iters + 2):
             flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, gelu=gelu, out_hi=out, cluster=cl, debug=debug)
+            if o32 is not None:
+                ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, residual=res, out_f32=o32, cluster=cl, debug=debug)
+            else:
+                ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, gelu=gelu, out_hi=out, cluster=cl, debug=debug)
             e.record()
             torch.cuda.synchronize()
             if i >= 2:
