@@ -19,19 +19,27 @@ constexpr int GEMM2_THREADS = 128 + GEMM2_EPI_WARPS * 32;            // + warpgr
 // setmaxnreg only redistributes what the CTA got at launch (640 threads x 96 regs): 128 x 32 + 512 x 112 = 61440
 constexpr int GEMM2_REGS_CONTROL = 32, GEMM2_REGS_EPILOGUE = 112;
 
+// The fp32 + residual recipe (out-proj / FFN2: x + Dense(.)) fetches its residual slabs with TMA into the per-warp
+// staging blocks (two per warp, double-buffered) instead of per-lane row loads; it trades one ring stage for them.
+template <int EPI>
 struct Gemm2Smem {
+  static constexpr bool TMA_RES = (EPI == (EPI_RESID | EPI_F32 | EPI_TMARES));
+  static constexpr int STAGES = TMA_RES ? 4 : GEMM2_STAGES;
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;           // 16 KB
   static constexpr int B_BYTES = (GEMM2_BLOCK_N / 2) * GEMM_BLOCK_K * 2;     // 16 KB: this CTA's half of the n-tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int RING_BYTES = GEMM2_STAGES * STAGE_BYTES;
-  static constexpr int EPI_OFF = RING_BYTES;                   // 16 epilogue warps x 2 KB TMA-store staging (1024-aligned)
-  static constexpr int EPI_WARP_BYTES = 2048;                  // 32 rows x 64 B, 64-byte swizzle
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFF = RING_BYTES;                   // 16 epilogue warps x staging blocks (1024-aligned)
+  static constexpr int EPI_BLOCK_BYTES = 2048;                 // 32 rows x 64 B, 64-byte swizzle
+  static constexpr int EPI_WARP_BYTES = (TMA_RES ? 2 : 1) * EPI_BLOCK_BYTES;
   static constexpr int EPI_BYTES = GEMM2_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
-  static constexpr int BAR_BYTES = 256;
+  static constexpr int RES_BAR_OFF = BAR_OFF + 128;            // 2 residual-slab barriers per epilogue warp
+  static constexpr int BAR_BYTES = 512;
   static constexpr int BIAS_OFF = BAR_OFF + BAR_BYTES;
   static constexpr int BIAS_BYTES = 4 * GEMM2_BLOCK_N * 4;     // per accumulator stage: bias slice, then scale slices
   static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + 1024;
+  static_assert(TOTAL <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
 // TMA bulk store of one staged [rows x 128 B] block (smem, SW128 image) to a 3-D tensor {N, rows_per_batch, batch}.
@@ -47,6 +55,7 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 
 struct Gemm2OutMaps {
   CUtensorMap f32, hi, lo;  // {N, rows_per_batch, batch}; boxes {16 fp32 | 32 bf16, 32 rows, 1} = 64-byte rows, SW64
+  CUtensorMap res;          // fp32 residual, same geometry as f32 (TMA_RES recipe)
 };
 
 // Epilogue of one warp: TMEM lane quadrant `ew` (32 rows, lane = row) x column group `cg` (64 columns = 2 chunks).
@@ -57,7 +66,8 @@ struct Gemm2OutMaps {
 template <int EPI>
 __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const Gemm2OutMaps& om, uint32_t taddr, int cg,
                                                     int n0, int t_warp0, int b, int rows_valid, bool zero_row,
-                                                    const float* sb, uint8_t* stage, uint32_t tmem_empty_cluster_addr) {
+                                                    const float* sb, uint8_t* stage, uint64_t* res_bar,
+                                                    uint32_t tmem_empty_cluster_addr) {
   constexpr int BLOCK_N = GEMM2_BLOCK_N;
   const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
   const bool f_fast = (EPI >= 0) ? bool(EPI & EPI_FASTGELU) : (p.gelu == 2);  // tanh-form GELU: single-pass mode
@@ -86,6 +96,45 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   }
   if (rows_valid <= 0 || n >= p.N) return;
   const size_t orow0 = (size_t)b * p.rows_per_batch + t_warp0;
+
+  if constexpr (Gemm2Smem<EPI>::TMA_RES) {
+    // out = acc + bias + residual, fp32.  Slab q (16 columns, 64-byte rows) of the residual was TMA-loaded into block
+    // q & 1 (slabs 0 / 1 before the accumulator was ready, see the caller); the sum is written back IN PLACE and leaves
+    // with a TMA store; as soon as that store has read the block, slab q + 2 is fetched into it.  N % 64 == 0 here.
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = q >> 1, hf = q & 1;
+      const int c0 = c_base + 16 * q;
+      uint8_t* blk = stage + (q & 1) * Gemm2Smem<EPI>::EPI_BLOCK_BYTES;
+      auto bslot = [&](int piece) { return blk + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4); };
+      mbar_wait(&res_bar[q & 1], (uint32_t)(q >> 1));   // each barrier completes exactly twice per tile
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 rr = *reinterpret_cast<const float4*>(bslot(j));
+        const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
+        float4 o;
+        o.x = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x + rr.x;
+        o.y = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y + rr.y;
+        o.z = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z + rr.z;
+        o.w = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w + rr.w;
+        if (zero_row) o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        *reinterpret_cast<float4*>(bslot(j)) = o;
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&om.f32, blk, n + 16 * q, t_warp0, b);
+        bulk_commit();
+        if (q < 2) {
+          bulk_wait_read0();
+          mbar_arrive_expect_tx(&res_bar[q & 1], Gemm2Smem<EPI>::EPI_BLOCK_BYTES);
+          tma_load_3d(blk, &om.res, &res_bar[q & 1], n + 16 * (q + 2), t_warp0, b);
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
 
   // staging block: row-major 64-byte rows, 16-byte slot s of row r lives at slot s ^ ((r >> 1) & 3)  (SWIZZLE_64B)
   auto slot = [&](int row, int piece) { return stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4); };
@@ -195,16 +244,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM2_THREADS, 1)
 gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                      const __grid_constant__ CUtensorMap tmB_hi, const __grid_constant__ CUtensorMap tmB_lo,
                      const __grid_constant__ Gemm2OutMaps om, const GemmParams p) {
-  using S = Gemm2Smem;
+  using S = Gemm2Smem<EPI>;
   constexpr int BLOCK_N = GEMM2_BLOCK_N;
   constexpr int ACC_STAGES = 2;
+  constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-  uint64_t* empty_bar = full_bar + GEMM2_STAGES;
-  uint64_t* tmem_full = empty_bar + GEMM2_STAGES;
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC_STAGES);
   float* s_bias = reinterpret_cast<float*>(smem + S::BIAS_OFF);
@@ -227,13 +277,17 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     }
   }
   if (warp == 1 && elect_one()) {
-    for (int i = 0; i < GEMM2_STAGES; ++i) {
+    for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);   // leader's arrive.expect_tx covers both CTAs' bytes (used in the leader only)
       mbar_init(&empty_bar[i], 1);  // leader's multicast commit
     }
     for (int i = 0; i < ACC_STAGES; ++i) {
       mbar_init(&tmem_full[i], 1);                       // leader's multicast commit
       mbar_init(&tmem_empty[i], 2 * GEMM2_EPI_WARPS);    // every epilogue warp of both CTAs (used in the leader only)
+    }
+    if (S::TMA_RES) {
+      uint64_t* rb = reinterpret_cast<uint64_t*>(smem + S::RES_BAR_OFF);
+      for (int i = 0; i < 2 * GEMM2_EPI_WARPS; ++i) mbar_init(&rb[i], 1);
     }
     fence_barrier_init();
   }
@@ -275,7 +329,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);  // both CTAs' TMA bytes land here
             tma_load_3d_2sm(sa, ma, lead_full, kc, trow, b);
             tma_load_2d_2sm(sb, mb, lead_full, kb * GEMM_BLOCK_K, n0);
-            if (++stage == GEMM2_STAGES) {
+            if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
@@ -303,7 +357,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 #pragma unroll
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
             umma_commit_2sm_mcast(&empty_bar[stage], 3);  // slot free in both CTAs once these MMAs retire
-            if (++stage == GEMM2_STAGES) {
+            if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
             }
@@ -324,6 +378,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     const int lane = lane_id();
     const int et = threadIdx.x - 128;  // 0..511
     uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * S::EPI_WARP_BYTES;
+    uint64_t* res_bar = reinterpret_cast<uint64_t*>(smem + S::RES_BAR_OFF) + 2 * (warp - 4);
     const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
     // bias (threads 0..255) / scale (threads 256..511) slice of a tile: fetched ONE TILE AHEAD into a register and
     // parked in smem (double-buffered with the accumulator stage) so that its global-load latency never sits on the
@@ -358,7 +413,17 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       const bool zero_row = p.row_valid != nullptr && t_warp0 + lane >= p.row_valid[b];
       const float* sb = s_bias + acc * BLOCK_N;
       const float next_bias = fetch_bias(w + num_pairs);   // in flight during this tile's epilogue
-      if (f_res && lane < rows_valid && n0 + 64 * cg < p.N) {
+      if (S::TMA_RES) {
+        // residual slabs 0 and 1 of this warp's 32 x 64 slice: in flight while the MMAs of this tile run
+        if (lane == 0 && rows_valid > 0 && n0 + 64 * cg < p.N) {
+          bulk_wait_read0();   // the previous tile's stores have finished reading both staging blocks
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            mbar_arrive_expect_tx(&res_bar[q], S::EPI_BLOCK_BYTES);
+            tma_load_3d(stage + q * S::EPI_BLOCK_BYTES, &om.res, &res_bar[q], n0 + 64 * cg + 16 * q, t_warp0, b);
+          }
+        }
+      } else if (f_res && lane < rows_valid && n0 + 64 * cg < p.N) {
         const float* rp = p.residual + ((size_t)b * p.rows_per_batch + t_warp0 + lane) * p.N + n0 + 64 * cg;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
@@ -366,7 +431,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      gemm2_epilogue_warp<EPI>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage,
+      gemm2_epilogue_warp<EPI>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage, res_bar,
                                mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
       park_bias(acc ^ 1, next_bias);
       asm volatile("bar.sync 1, 512;" ::: "memory");   // every warp is done with this tile's slice; the next one is visible
@@ -386,7 +451,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
 
 template <int PASSES, int EPI>
 static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
-  using S = Gemm2Smem;
+  using S = Gemm2Smem<EPI>;
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   const uint64_t a_dims[3] = {(uint64_t)a->a_row_len, (uint64_t)a->a_rows, (uint64_t)a->batch};
   const uint64_t a_strides[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)a->a_batch_stride * 2};
@@ -412,6 +477,8 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
     const uint64_t s32[2] = {(uint64_t)a->N * 4, (uint64_t)a->rows_per_batch * a->N * 4};
     const uint32_t box16[3] = {32, 32, 1}, box32[3] = {16, 32, 1};   // 64-byte rows
     if (a->out_f32 && (rc = make_tmap(&om.f32, a->out_f32, 3, c_dims, s32, box32, CU_TENSOR_MAP_SWIZZLE_64B,
+                                      CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
+    if (S::TMA_RES && (rc = make_tmap(&om.res, a->residual, 3, c_dims, s32, box32, CU_TENSOR_MAP_SWIZZLE_64B,
                                       CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
     if (a->out_hi && (rc = make_tmap(&om.hi, a->out_hi, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if (a->out_lo && (rc = make_tmap(&om.lo, a->out_lo, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
@@ -453,6 +520,10 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
     if (!gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_F32>(a, s);
     if (!gelu && !res && f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_F32 | EPI_HI | LO>(a, s);
     if (!gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_HI | LO>(a, s);
+    // short-K tiles (out-proj) cannot hide per-lane residual loads behind the MMAs: TMA-fetched slabs (4-stage ring);
+    // long-K tiles (FFN2) keep the 5-stage ring and the L2-prefetched per-lane loads
+    if (!gelu && res && f32 && !hi && a->N % 64 == 0 && a->K * PASSES <= 1536)
+      return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32 | EPI_TMARES>(a, s);
     if (!gelu && res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32>(a, s);
   }
   return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);

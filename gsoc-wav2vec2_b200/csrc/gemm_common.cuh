@@ -17,7 +17,8 @@ constexpr int GEMM_REGS_EPILOGUE = 224;
 
 // epilogue recipe bits (template parameter EPI of the kernels; EPI < 0 = decide from GemmParams at run time)
 constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16, EPI_SCALE = 32,
-              EPI_FASTGELU = 64;  // tanh-form GELU (single-pass mode only; see gelu_tanh_p2)
+              EPI_FASTGELU = 64,     // tanh-form GELU (single-pass mode only; see gelu_tanh_p2)
+              EPI_TMARES = 128;    // 2-SM kernel: residual slabs fetched by TMA into the staging blocks
 constexpr int EPI_RUNTIME = -1;
 
 struct GemmParams {
