@@ -1,0 +1,364 @@
+// Backward of the attention core (reference forward: TransformerAttention.get_context, encoder.py:34-54; Keras `fit`
+// differentiates it in the stage-2 fine-tune, main.py:234-250).  Inputs are the tensors the forward already keeps:
+// the packed projection qkv[b][t][0:3d] = [q | k | v] (q pre-scaled by dh^-1/2), the context O = softmax(q k^T) v and its
+// gradient dO, both [b][t][d] bf16.  Output dqkv[b][t][0:3d] in the same packed layout (the q part multiplied by `q_scale`,
+// so that every downstream product uses the UNSCALED projection kernels).
+//
+//     P = softmax(S), S = Q K^T;  D_i = sum_c dO_ic O_ic;  dV = P^T dO;  dP = dO V^T;  dS = P o (dP - D);
+//     dQ = dS K;  dK = dS^T Q
+//
+// Two kernels, no atomics, deterministic:
+//   attn_bwd_dq   : CTA = 64 queries of one (b, h).  Sweep 1 over the key blocks rebuilds the softmax statistics
+//                   (running max / sum), sweep 2 forms P, dP, dS and accumulates dQ; it also stores lse2 (log2-domain
+//                   log-sum-exp) and D for the second kernel.
+//   attn_bwd_dkv  : CTA = 64 keys of one (b, h); loops over the query blocks with the TRANSPOSED products
+//                   (S^T = K Q^T, dP^T = V dO^T) so that P^T / dS^T come out of the MMA already in the layout the next
+//                   MMA needs as its A operand.
+// Tensor cores through warp-level mma.sync m16n8k16 (bf16 in, fp32 accumulate): this kernel is ~2 % of a train step's
+// FLOPs budget at 768 frames; a tcgen05 version only matters once the GEMMs around it are at peak.
+#include "host_util.h"
+#include "w2v2_common.cuh"
+#include "../../include/w2v2.h"
+
+namespace w2v2 {
+
+constexpr int AB_BLK = 64;      // queries / keys per tile
+constexpr int AB_DH = 64;
+constexpr int AB_LD = 72;       // padded row stride (bf16 elements): 144 B, keeps ldmatrix / LDS.32 conflict free
+constexpr float AB_LOG2E = 1.4426950408889634f;
+
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A fragment (16 x 16, row-major tile[m][k])
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const __nv_bfloat16* tile, int m0, int k0, int g, int q) {
+  a[0] = *reinterpret_cast<const uint32_t*>(tile + (m0 + g) * AB_LD + k0 + 2 * q);
+  a[1] = *reinterpret_cast<const uint32_t*>(tile + (m0 + g + 8) * AB_LD + k0 + 2 * q);
+  a[2] = *reinterpret_cast<const uint32_t*>(tile + (m0 + g) * AB_LD + k0 + 2 * q + 8);
+  a[3] = *reinterpret_cast<const uint32_t*>(tile + (m0 + g + 8) * AB_LD + k0 + 2 * q + 8);
+}
+// B fragment (k16 x n8) with B[k][n] = tile[n0 + n][k0 + k]   ("tile rows are the n index": Q K^T style products)
+__device__ __forceinline__ void load_b_nk(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* tile, int n0, int k0, int g, int q) {
+  b0 = *reinterpret_cast<const uint32_t*>(tile + (n0 + g) * AB_LD + k0 + 2 * q);
+  b1 = *reinterpret_cast<const uint32_t*>(tile + (n0 + g) * AB_LD + k0 + 2 * q + 8);
+}
+// B fragment (k16 x n8) with B[k][n] = tile[k0 + k][n0 + n]   ("tile rows are the k index": P V style products)
+__device__ __forceinline__ void load_b_kn(uint32_t& b0, uint32_t& b1, const __nv_bfloat16* tile, int k0, int n0, int lane) {
+  const uint32_t addr = smem_u32(tile + (k0 + (lane & 15)) * AB_LD + n0);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
+}
+// copy a [64 x 64] bf16 tile (rows t0.., row stride ld_g elements) into padded smem, zero beyond `t_end`
+__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int t0, int t_end, size_t ld_g,
+                                          int tid, int nthreads) {
+  for (int i = tid; i < AB_BLK * 8; i += nthreads) {   // 8 x 16-byte pieces per row
+    const int r = i >> 3, p = i & 7;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (t0 + r < t_end) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t)(t0 + r) * ld_g) + p);
+    *reinterpret_cast<uint4*>(dst + r * AB_LD + 8 * p) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ dQ (+ lse2, D)
+__global__ void __launch_bounds__(128)
+attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+                   const __nv_bfloat16* __restrict__ d_o, const int* __restrict__ kv_len, int T, int H, float q_scale,
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ lse2_out, float* __restrict__ dsum_out) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[AB_BLK * AB_LD], sdO[AB_BLK * AB_LD], sK[AB_BLK * AB_LD], sV[AB_BLK * AB_LD];
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int d = H * AB_DH;
+  const int t0 = blockIdx.x * AB_BLK;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int klen = kv_len ? min(kv_len[b], T) : T;
+  const size_t ld3 = 3 * (size_t)d;
+  const __nv_bfloat16* qp = qkv + (size_t)b * T * ld3 + h * AB_DH;
+  const __nv_bfloat16* kp = qp + d;
+  const __nv_bfloat16* vp = qp + 2 * d;
+  const __nv_bfloat16* op = o + (size_t)b * T * d + h * AB_DH;
+  const __nv_bfloat16* dop = d_o + (size_t)b * T * d + h * AB_DH;
+
+  load_tile(sQ, qp, t0, T, ld3, tid, 128);
+  load_tile(sdO, dop, t0, T, d, tid, 128);
+  __syncthreads();
+  const int m0 = warp * 16;
+  uint32_t aq[4][4], ado[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    load_a(aq[ks], sQ, m0, 16 * ks, g, q);
+    load_a(ado[ks], sdO, m0, 16 * ks, g, q);
+  }
+  // D_i = sum_c dO_ic O_ic for rows m0 + g and m0 + g + 8
+  float dsum[2] = {0.0f, 0.0f};
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 + m0 + g + 8 * r;
+    if (t < T) {
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {   // this lane's 16 columns: [16 q, 16 q + 16) as two 16-byte pieces
+        const uint4 ov = __ldg(reinterpret_cast<const uint4*>(op + (size_t)t * d + 16 * q + 8 * c));
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dop + (size_t)t * d + 16 * q + 8 * c));
+        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          dsum[r] += bf16_lo_to_f32(ow[e]) * bf16_lo_to_f32(gw[e]) + bf16_hi_to_f32(ow[e]) * bf16_hi_to_f32(gw[e]);
+      }
+    }
+    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
+    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
+  }
+
+  const int nkb = (klen + AB_BLK - 1) / AB_BLK;
+  float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.0f, 0.0f};
+  // ---- sweep 1: softmax statistics (log2 domain)
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile(sK, kp, kb * AB_BLK, klen, ld3, tid, 128);
+    __syncthreads();
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1;
+        load_b_nk(b0, b1, sK, 8 * j, 16 * ks, g, q);
+        mma16816(s[j], aq[ks], b0, b1);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float bm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = kb * AB_BLK + 8 * j + 2 * q + e;
+          float v = s[j][2 * r + e] * AB_LOG2E;
+          if (key >= klen) v = -INFINITY;
+          s[j][2 * r + e] = v;
+          bm = fmaxf(bm, v);
+        }
+      }
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
+      bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
+      const float nm = fmaxf(mx[r], bm);
+      float ps = 0.0f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ps += exp2f(s[j][2 * r] - nm) + exp2f(s[j][2 * r + 1] - nm);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+      ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+      sum[r] = sum[r] * exp2f(mx[r] - nm) + ps;
+      mx[r] = nm;
+    }
+  }
+  float lse2[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    lse2[r] = mx[r] + log2f(sum[r]);
+    const int t = t0 + m0 + g + 8 * r;
+    if (q == 0 && t < T) {
+      lse2_out[(size_t)bh * T + t] = lse2[r];
+      dsum_out[(size_t)bh * T + t] = dsum[r];
+    }
+  }
+
+  // ---- sweep 2: dQ += (P o (dO V^T - D)) K
+  float dq[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
+  for (int kb = 0; kb < nkb; ++kb) {
+    __syncthreads();
+    load_tile(sK, kp, kb * AB_BLK, klen, ld3, tid, 128);
+    load_tile(sV, vp, kb * AB_BLK, klen, ld3, tid, 128);
+    __syncthreads();
+    float s[8][4], dp[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1;
+        load_b_nk(b0, b1, sK, 8 * j, 16 * ks, g, q);
+        mma16816(s[j], aq[ks], b0, b1);
+        load_b_nk(b0, b1, sV, 8 * j, 16 * ks, g, q);
+        mma16816(dp[j], ado[ks], b0, b1);
+      }
+    }
+    // dS (bf16) as A fragments: key pairs (2 jj, 2 jj + 1) of n-tiles form one 16-wide k step
+    uint32_t ads[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float ds[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int key = kb * AB_BLK + 8 * j + 2 * q + e;
+          const float p = (key < klen) ? exp2f(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
+          ds[2 * r + e] = p * (dp[j][2 * r + e] - dsum[r]);
+        }
+      }
+      ads[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(ds[0], ds[1]);   // row g
+      ads[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);   // row g + 8
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {      // k = 16 keys
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {       // n = 8 head channels
+        uint32_t b0, b1;
+        load_b_kn(b0, b1, sK, 16 * ks, 8 * j, lane);
+        mma16816(dq[j], ads[ks], b0, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 + m0 + g + 8 * r;
+    if (t < T) {
+      __nv_bfloat16* dst = dqkv + ((size_t)b * T + t) * ld3 + h * AB_DH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint32_t*>(dst + 8 * j + 2 * q) = pack_bf16x2(dq[j][2 * r] * q_scale, dq[j][2 * r + 1] * q_scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------ dK, dV
+__global__ void __launch_bounds__(128)
+attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
+                    const int* __restrict__ kv_len, int T, int H, const float* __restrict__ lse2_in,
+                    const float* __restrict__ dsum_in, __nv_bfloat16* __restrict__ dqkv) {
+  __shared__ __align__(16) __nv_bfloat16 sQ[AB_BLK * AB_LD], sdO[AB_BLK * AB_LD], sK[AB_BLK * AB_LD], sV[AB_BLK * AB_LD];
+  __shared__ float s_lse[AB_BLK], s_ds[AB_BLK];
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int d = H * AB_DH;
+  const int k0 = blockIdx.x * AB_BLK;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+  const int klen = kv_len ? min(kv_len[b], T) : T;
+  const size_t ld3 = 3 * (size_t)d;
+  const __nv_bfloat16* qp = qkv + (size_t)b * T * ld3 + h * AB_DH;
+  const __nv_bfloat16* kp = qp + d;
+  const __nv_bfloat16* vp = qp + 2 * d;
+  const __nv_bfloat16* dop = d_o + (size_t)b * T * d + h * AB_DH;
+
+  load_tile(sK, kp, k0, klen, ld3, tid, 128);
+  load_tile(sV, vp, k0, klen, ld3, tid, 128);
+  __syncthreads();
+  const int m0 = warp * 16;   // this warp's 16 keys
+  uint32_t ak[4][4], av[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    load_a(ak[ks], sK, m0, 16 * ks, g, q);
+    load_a(av[ks], sV, m0, 16 * ks, g, q);
+  }
+  float dk[8][4], dv[8][4];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = 0.0f;
+    dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.0f;
+  }
+  const bool key_ok[2] = {k0 + m0 + g < klen, k0 + m0 + g + 8 < klen};
+  const int nqb = (T + AB_BLK - 1) / AB_BLK;
+  for (int qb = 0; qb < nqb; ++qb) {
+    __syncthreads();
+    load_tile(sQ, qp, qb * AB_BLK, T, ld3, tid, 128);
+    load_tile(sdO, dop, qb * AB_BLK, T, d, tid, 128);
+    if (tid < AB_BLK) {
+      const int t = qb * AB_BLK + tid;
+      s_lse[tid] = (t < T) ? lse2_in[(size_t)bh * T + t] : 0.0f;
+      s_ds[tid] = (t < T) ? dsum_in[(size_t)bh * T + t] : 0.0f;
+    }
+    __syncthreads();
+    // S^T = K Q^T and dP^T = V dO^T : [16 keys] x [64 queries]
+    float st[8][4], dpt[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.0f;
+      dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.0f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t b0, b1;
+        load_b_nk(b0, b1, sQ, 8 * j, 16 * ks, g, q);
+        mma16816(st[j], ak[ks], b0, b1);
+        load_b_nk(b0, b1, sdO, 8 * j, 16 * ks, g, q);
+        mma16816(dpt[j], av[ks], b0, b1);
+      }
+    }
+    uint32_t ap[4][4], ads[4][4];   // P^T and dS^T as A fragments (k = query index)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float p[4], ds[4];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int qi = 8 * j + 2 * q + e;
+          const bool ok = key_ok[r] && (qb * AB_BLK + qi < T);
+          const float pv = ok ? exp2f(st[j][2 * r + e] * AB_LOG2E - s_lse[qi]) : 0.0f;
+          p[2 * r + e] = pv;
+          ds[2 * r + e] = pv * (dpt[j][2 * r + e] - s_ds[qi]);
+        }
+      }
+      ap[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p[0], p[1]);
+      ap[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(p[2], p[3]);
+      ads[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(ds[0], ds[1]);
+      ads[j >> 1][(j & 1) * 2 + 1] = pack_bf16x2(ds[2], ds[3]);
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {      // k = 16 queries
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {       // n = 8 head channels
+        uint32_t b0, b1;
+        load_b_kn(b0, b1, sdO, 16 * ks, 8 * j, lane);
+        mma16816(dv[j], ap[ks], b0, b1);
+        load_b_kn(b0, b1, sQ, 16 * ks, 8 * j, lane);
+        mma16816(dk[j], ads[ks], b0, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int t = k0 + m0 + g + 8 * r;
+    if (t < T) {
+      __nv_bfloat16* dst = dqkv + ((size_t)b * T + t) * ld3 + h * AB_DH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t*>(dst + d + 8 * j + 2 * q) = pack_bf16x2(dk[j][2 * r], dk[j][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(dst + 2 * d + 8 * j + 2 * q) = pack_bf16x2(dv[j][2 * r], dv[j][2 * r + 1]);
+      }
+    }
+  }
+}
+
+}  // namespace w2v2
+
+using namespace w2v2;
+
+extern "C" int64_t w2v2_attn_bwd_workspace_bytes(int batch, int frames, int num_heads) {
+  return (int64_t)2 * batch * num_heads * frames * (int64_t)sizeof(float);
+}
+
+extern "C" int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void* dctx_hi, int batch, int frames,
+                             int num_heads, int head_size, const int32_t* kv_len, float q_scale, void* workspace,
+                             void* dqkv_hi, void* stream) {
+  W2V2_CHECK_ARG(qkv_hi && ctx_hi && dctx_hi && workspace && dqkv_hi, "null pointer");
+  W2V2_CHECK_ARG(head_size == AB_DH, "built for head_size 64");
+  W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  float* lse2 = reinterpret_cast<float*>(workspace);
+  float* dsum = lse2 + (size_t)batch * num_heads * frames;
+  dim3 grid((frames + AB_BLK - 1) / AB_BLK, batch * num_heads);
+  attn_bwd_dq_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
+                                          reinterpret_cast<const __nv_bfloat16*>(ctx_hi),
+                                          reinterpret_cast<const __nv_bfloat16*>(dctx_hi), kv_len, frames, num_heads, q_scale,
+                                          reinterpret_cast<__nv_bfloat16*>(dqkv_hi), lse2, dsum);
+  W2V2_CUDA(cudaGetLastError());
+  attn_bwd_dkv_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
+                                           reinterpret_cast<const __nv_bfloat16*>(dctx_hi), kv_len, frames, num_heads, lse2,
+                                           dsum, reinterpret_cast<__nv_bfloat16*>(dqkv_hi));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -25,6 +25,9 @@ constexpr int PC_WIN_ROWS = 2 * PC_HALF_ROWS;  // 384 >= 2*128 + 127
 struct PosconvParams {
   int T, d, cpg, groups, ktaps, mt;  // mt = m-tiles (128 frames each) per CTA
   int stages;
+  int shift;              // window starts at frame tf0 - ktaps/2 + shift (0 = forward; +1 = transposed conv of the backward)
+  int linear;             // 1: out = resid + acc (no bias, no GELU): the dgrad of the conv
+  float* pre_out;         // optional fp32 [B, T, d]: bias + conv (pre-activation kept for the backward)
   const float* bias;      // [d]
   const float* resid;     // fp32 [B, T, d]
   float* out_f32;         // fp32 [B, T, d]
@@ -98,7 +101,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
         for (int c = 0; c < cpc; ++c)
           for (int q = 0; q < 2; ++q)
             tma_load_4d(a_smem + pl * a_plane + c * a_lbo + q * PC_HALF_ROWS * 16, tm, a_full, 0,
-                        tf0 - p.ktaps / 2 + q * PC_HALF_ROWS, g * cpc + c, b);
+                        tf0 - p.ktaps / 2 + p.shift + q * PC_HALF_ROWS, g * cpc + c, b);
       }
       int stage = 0;
       uint32_t phase = 0;
@@ -167,16 +170,26 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           const int n = g * p.cpg + c0;
           const size_t o = ((size_t)b * p.T + t) * p.d + n;
           float v[16];
+          if (p.linear) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
-            v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
+              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+            }
+            if (p.pre_out != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                reinterpret_cast<float4*>(p.pre_out + o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) gelu_erf_x2(v[i], v[i + 1]);
           }
-#pragma unroll
-          for (int i = 0; i < 16; i += 2) gelu_erf_x2(v[i], v[i + 1]);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 rr = __ldg(reinterpret_cast<const float4*>(p.resid + o) + i);
@@ -217,6 +230,9 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
   p.groups = a->groups;
   p.ktaps = a->ktaps;
   p.mt = (a->frames > 128) ? 2 : 1;
+  p.shift = a->shift;
+  p.linear = a->linear;
+  p.pre_out = a->pre_out;
   p.bias = a->bias;
   p.resid = a->resid;
   p.out_f32 = a->out_f32;
@@ -241,7 +257,7 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
 extern "C" int w2v2_posconv(const w2v2_posconv_args* a, void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(a != nullptr, "args is null");
-  W2V2_CHECK_ARG(a->x_hi && a->w_hi && a->bias && a->resid && a->out_f32, "null pointer");
+  W2V2_CHECK_ARG(a->x_hi && a->w_hi && (a->bias || a->linear) && a->resid && a->out_f32, "null pointer");
   W2V2_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3");
   W2V2_CHECK_ARG(a->passes == 1 || (a->x_lo && a->w_lo), "3-pass mode needs the lo planes");
   W2V2_CHECK_ARG(a->groups > 0 && a->hidden % a->groups == 0, "hidden must be divisible by groups");

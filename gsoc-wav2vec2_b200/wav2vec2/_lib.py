@@ -38,6 +38,7 @@ class PosconvArgs(C.Structure):
         ("bias", C.c_void_p), ("resid", C.c_void_p), ("out_f32", C.c_void_p),
         ("batch", C.c_int32), ("frames", C.c_int32), ("hidden", C.c_int32), ("groups", C.c_int32),
         ("ktaps", C.c_int32), ("passes", C.c_int32),
+        ("pre_out", C.c_void_p), ("shift", C.c_int32), ("linear", C.c_int32),
     ]
 
 
@@ -63,8 +64,17 @@ SIGNATURES = {
     "w2v2_frame_argmax": [_P, _L, _I, _P, _P],
     "w2v2_lm_head_wgrad": [_P, _P, _L, _I, _I, _P, _P, _P],
     "w2v2_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
+    "w2v2_ln_bwd": [_P, _P, _P, _F, _L, _I, _P, _P, _P, _P, _P, _P],
+    "w2v2_gelu_rows": [_P, _L, _I, _P, _P, _P],
+    "w2v2_dact_colsum": [_P, _P, _L, _I, _P, _P, _P],
+    "w2v2_transpose_bf16": [_P, _L, _I, _P, _L, _P],
+    "w2v2_lm_head_dgrad": [_P, _P, _L, _I, _I, _P, _P],
+    "w2v2_attn_bwd_workspace_bytes": [_I, _I, _I],
+    "w2v2_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P],
+    "w2v2_posconv_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
 }
-_RESTYPES = {"w2v2_last_error_string": C.c_char_p, "w2v2_ctc_workspace_bytes": C.c_int64}
+_RESTYPES = {"w2v2_last_error_string": C.c_char_p, "w2v2_ctc_workspace_bytes": C.c_int64,
+             "w2v2_attn_bwd_workspace_bytes": C.c_int64}
 
 _lib = None
 

@@ -124,6 +124,12 @@ def _split(t: torch.Tensor, lo: bool) -> Pair:
     return Pair(hi, (t - hi.float()).to(torch.bfloat16) if lo else None)
 
 
+def pack_posconv_kernel(kern: torch.Tensor, groups: int) -> torch.Tensor:
+    """TF grouped-conv kernel [k, cin/groups, cout] -> the posconv kernel's layout [groups][k][cin/8][cout/groups][8]."""
+    k, cpg, d = kern.shape
+    return kern.reshape(k, cpg // 8, 8, groups, cpg).permute(3, 0, 1, 4, 2).contiguous()
+
+
 # ------------------------------------------------------------------------------------------ base class
 class _B200Model:
     with_head = False
@@ -266,8 +272,7 @@ class _B200Model:
         kern = wv * torch.rsqrt(torch.clamp(ss, min=1e-12)) * wg                     # [k, cpg, d]
         k, cpg, d = kern.shape
         G = d // cpg
-        packed = kern.reshape(k, cpg // 8, 8, G, cpg).permute(3, 0, 1, 4, 2).contiguous()
-        P["pos.w"] = _split(packed, lo)
+        P["pos.w"] = _split(pack_posconv_kernel(kern, G), lo)
         dh = cfg.head_size
         scale = dh ** (-0.5)                                                         # encoder.py:28, folded
         for i in range(cfg.num_layers):
@@ -298,12 +303,11 @@ class _B200Model:
             n = 1 + torch.div(n - k, s, rounding_mode="floor")
         return torch.clamp(n, min=0, max=T).to(torch.int32).contiguous()
 
-    def _encode(self, batch, attention_mask, training):
+    def _features(self, batch):
+        """Conv feature extractor (feature_extractor.py:27-59): waveform [B, L] -> fp32 [B*T', C_last] (arena view)."""
         cfg, v = self.config, self.variables
         if not torch.cuda.is_available() or self.device.type != "cuda":
             raise RuntimeError("Wav2Vec2 forward needs a CUDA device: the sm_100a kernels have no CPU fallback")
-        if training and cfg.dropout:
-            raise NotImplementedError("training-mode forward (dropout RNG) is not built yet; use dropout=0")
         P = self._packed or self._pack()
         if self._arena is None:
             self._arena = _Arena(self.device)
@@ -318,7 +322,6 @@ class _B200Model:
         if frames[-1] < 1:
             raise ValueError(f"input of {L} samples is shorter than the extractor's receptive field")
         f32, C0 = torch.float32, cfg.filter_sizes[0]
-        eps = cfg.layer_norm_eps
         fe = "wav2vec2/feature_extractor/conv_layers/"
         layer_norm_convs = cfg.feature_extractor_norm_type == "layer"
         nconv = len(cfg.filter_sizes)
@@ -370,7 +373,18 @@ class _B200Model:
                 nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
                 ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, out_hi=nxt.hi, out_lo=nxt.lo, **geo)
                 act = nxt
-        T, Cl, d = frames[-1], cfg.filter_sizes[-1], cfg.hidden_size
+        return last_f32, B, frames[-1]
+
+    def _encode(self, batch, attention_mask, training):
+        cfg, v = self.config, self.variables
+        if training and cfg.dropout:
+            raise NotImplementedError("training-mode forward (dropout RNG) is not built yet; use dropout=0")
+        last_f32, B, T = self._features(batch)
+        P, A = self._packed, self._arena
+        passes = _PRECISIONS[self.precision]
+        lo = passes == 3
+        f32, eps = torch.float32, cfg.layer_norm_eps
+        Cl, d = cfg.filter_sizes[-1], cfg.hidden_size
         M = B * T
 
         # ---- feature projection (feature_extractor.py:92-95) + frame mask (modeling.py:201-206, encoder.py:253)

@@ -175,3 +175,65 @@ def adam(w, g, m, v, lr_t, beta1, beta2, eps):
     _need_cuda(w, g, m, v)
     _count(); _lib.check(_lib.load().w2v2_adam(_ptr(w), _ptr(g), _ptr(m), _ptr(v), w.numel(), float(lr_t), float(beta1),
                                      float(beta2), float(eps), _stream()), "w2v2_adam")
+
+
+# ------------------------------------------------------------------------------------------ stage-2 backward kernels
+def ln_bwd(x, gamma, dy, eps, rows, d, dx_f32=None, dx_hi=None, dgamma=None, dbeta=None, colsum=None):
+    """LayerNorm backward; dgamma / dbeta / colsum are accumulated into (caller zeroes them once per step)."""
+    _need_cuda(x, gamma, dy, dx_f32, dx_hi, dgamma, dbeta, colsum)
+    _count(); _lib.check(_lib.load().w2v2_ln_bwd(_ptr(x), _ptr(gamma), _ptr(dy), float(eps), rows, d, _ptr(dx_f32), _ptr(dx_hi),
+                                       _ptr(dgamma), _ptr(dbeta), _ptr(colsum), _stream()), "w2v2_ln_bwd")
+
+
+def gelu_rows(pre, out_hi, fast, out_lo=None):
+    _need_cuda(pre, out_hi, out_lo)
+    _count(); _lib.check(_lib.load().w2v2_gelu_rows(_ptr(pre), pre.numel(), 1 if fast else 0, _ptr(out_hi), _ptr(out_lo),
+                                          _stream()), "w2v2_gelu_rows")
+
+
+def dact_colsum(dy_hi, pre, rows, cols, out_hi=None, colsum=None):
+    _need_cuda(dy_hi, pre, out_hi, colsum)
+    _count(); _lib.check(_lib.load().w2v2_dact_colsum(_ptr(dy_hi), _ptr(pre), rows, cols, _ptr(out_hi), _ptr(colsum), _stream()),
+                         "w2v2_dact_colsum")
+
+
+def transpose_bf16(x, rows, cols, out, out_ld):
+    _need_cuda(x, out)
+    _count(); _lib.check(_lib.load().w2v2_transpose_bf16(_ptr(x), rows, cols, _ptr(out), out_ld, _stream()), "w2v2_transpose_bf16")
+
+
+def lm_head_dgrad(grad_logits, kernel, out):
+    _need_cuda(grad_logits, kernel, out)
+    d, V = kernel.shape
+    rows = grad_logits.numel() // V
+    _count(); _lib.check(_lib.load().w2v2_lm_head_dgrad(_ptr(grad_logits), _ptr(kernel), rows, d, V, _ptr(out), _stream()),
+                         "w2v2_lm_head_dgrad")
+
+
+def attn_bwd(qkv_hi, ctx_hi, dctx_hi, B, T, H, dh, kv_len, q_scale, dqkv_hi, workspace=None):
+    _need_cuda(qkv_hi, ctx_hi, dctx_hi, dqkv_hi, kv_len)
+    lib = _lib.load()
+    need = lib.w2v2_attn_bwd_workspace_bytes(B, T, H)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need // 4, dtype=torch.float32, device=qkv_hi.device)
+    _count(2); _lib.check(lib.w2v2_attn_bwd(_ptr(qkv_hi), _ptr(ctx_hi), _ptr(dctx_hi), B, T, H, dh, _ptr(kv_len), float(q_scale),
+                                  _ptr(workspace), _ptr(dqkv_hi), _stream()), "w2v2_attn_bwd")
+    return workspace
+
+
+def posconv_train(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps, passes=1, pre_out=None, shift=0, linear=False):
+    """w2v2_posconv with the training options: pre-activation output / transposed-conv (input gradient) mode."""
+    _need_cuda(x.hi, w.hi, bias, resid, out_f32, pre_out)
+    args = _lib.PosconvArgs()
+    args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if passes == 3 else None
+    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
+    args.bias, args.resid, args.out_f32 = _ptr(bias), _ptr(resid), _ptr(out_f32)
+    args.batch, args.frames, args.hidden, args.groups, args.ktaps, args.passes = B, T, d, groups, ktaps, passes
+    args.pre_out, args.shift, args.linear = _ptr(pre_out), shift, 1 if linear else 0
+    _count(); _lib.check(_lib.load().w2v2_posconv(C.byref(args), _stream()), "w2v2_posconv")
+
+
+def posconv_wgrad(x_hi, dpre_hi, B, T, d, groups, ktaps, grad_kernel):
+    _need_cuda(x_hi, dpre_hi, grad_kernel)
+    _count(); _lib.check(_lib.load().w2v2_posconv_wgrad(_ptr(x_hi), _ptr(dpre_hi), B, T, d, groups, ktaps, _ptr(grad_kernel),
+                                              _stream()), "w2v2_posconv_wgrad")

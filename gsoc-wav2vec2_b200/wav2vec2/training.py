@@ -54,3 +54,287 @@ class Stage1Trainer:
         ops.adam(self.flat_w, self.flat_g, self.m, self.v, lr_t, self.b1, self.b2, self.eps)
         model._repack_lm_head()
         return loss
+
+
+# ============================================================================================ stage 2
+from .modeling import _PRECISIONS, pack_posconv_kernel  # noqa: E402
+from .ops import Pair  # noqa: E402
+
+
+def pack_posconv(kern: torch.Tensor, groups: int) -> torch.Tensor:
+    """bf16 posconv-kernel layout of a TF grouped-conv kernel [k, cin/groups, cout]."""
+    return pack_posconv_kernel(kern, groups).to(torch.bfloat16)
+
+
+def pack_posconv_transposed(kern: torch.Tensor, groups: int) -> torch.Tensor:
+    """Taps flipped and in/out channels swapped inside each group: fed to the forward posconv kernel (linear=1, shift=1)
+    this computes the INPUT gradient of the convolution, dx[u] = sum_j W_j^T dpre[u - j + k/2]."""
+    k, cpg, d = kern.shape
+    kt = kern.reshape(k, cpg, groups, cpg).flip(0).permute(0, 3, 2, 1).reshape(k, cpg, d)
+    return pack_posconv(kt, groups)
+
+
+class Stage2Trainer:
+    """Stage-2 fine-tune step of the reference recipe (src/main.py:234-250): ``model.freeze_feature_extractor()``, then
+    Keras ``fit`` differentiates everything else - feature projection, positional conv (through its weight norm),
+    encoder LayerNorms, all transformer layers, ``masked_spec_embed`` and ``lm_head`` (90 195 872 parameters for base) -
+    sums the gradients over replicas and applies Adam.
+
+    Every arithmetic step of forward and backward is a kernel behind the C ABI: the inference kernels (forward, with the
+    activations the backward needs kept in the arena), ``w2v2_ctc_loss`` (loss + dlogits), the tcgen05 GEMM for every
+    dgrad / wgrad product (operands transposed by ``w2v2_transpose_bf16``), ``w2v2_ln_bwd``, ``w2v2_dact_colsum``,
+    ``w2v2_attn_bwd``, ``w2v2_posconv`` (transposed-conv mode) + ``w2v2_posconv_wgrad``, then ONE ``all_reduce(SUM)``
+    over the flat fp32 gradient buffer and ONE ``w2v2_adam`` launch.  Parameter-sized algebra (weight-norm chain rule,
+    bf16 casts of the updated kernels) is host-side torch on the parameter tensors.
+
+    Limits: post-norm encoder with the group-norm extractor (the base architecture of BASELINE config 3), no attention
+    mask, ``dropout == 0`` (no dropout RNG yet); SpecAugment masks (host RNG like the reference) are supported.
+    Backward products run single-pass bf16 with fp32 accumulation; LayerNorm / softmax / GELU derivatives in fp32.
+    """
+
+    def __init__(self, model: Wav2Vec2ForCTC, loss_fn: CTCLoss, learning_rate=5e-5, beta_1=0.9, beta_2=0.999,
+                 epsilon=1e-7):
+        cfg = model.config
+        if cfg.attention_norm_type != "postnorm" or cfg.feature_extractor_norm_type != "group":
+            raise NotImplementedError("Stage2Trainer covers the base architecture (group-norm extractor, post-norm encoder)")
+        if cfg.dropout:
+            raise NotImplementedError("dropout RNG is not built yet; use dropout=0")
+        self.model, self.loss_fn = model, loss_fn
+        self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
+        self.t = 0
+        model.freeze_feature_extractor()                               # main.py:236-237
+        self.names = [n for n in model.variables if model.trainable[n]]
+        sizes = [model.variables[n].numel() for n in self.names]
+        # all trainable variables in ONE flat fp32 buffer: a single all-reduce message, a single Adam launch
+        self.flat_w = torch.cat([model.variables[n].reshape(-1) for n in self.names]).contiguous()
+        self.flat_g = torch.zeros_like(self.flat_w)
+        self.m = torch.zeros_like(self.flat_w)
+        self.v = torch.zeros_like(self.flat_w)
+        self.G = {}
+        off = 0
+        for n, sz in zip(self.names, sizes):
+            shape = model.variables[n].shape
+            model.variables[n] = self.flat_w[off: off + sz].view(shape)
+            self.G[n] = self.flat_g[off: off + sz].view(shape)
+            off += sz
+        model._packed = None
+        self._wt = None
+        self.saved = None
+
+    # ------------------------------------------------------------------ operand packs of the backward GEMMs
+    def _pack_backward(self):
+        """dgrad weight operands: the TF kernels themselves ([in, out] row-major == W^T, K-major) as bf16."""
+        m, v, cfg = self.model, self.model.variables, self.model.config
+        bf = torch.bfloat16
+        W = {"proj": Pair(v["wav2vec2/feature_projection/projection/kernel"].to(bf))}
+        pc = "wav2vec2/encoder/pos_conv_embed/conv/"
+        wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
+        nrm = torch.sqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12))
+        W["pos.T"] = Pair(pack_posconv_transposed(wv / nrm * wg, cfg.num_conv_pos_embedding_groups))
+        for i in range(cfg.num_layers):
+            a = f"wav2vec2/encoder/layers/{i}/attention/"
+            f = f"wav2vec2/encoder/layers/{i}/feed_forward/"
+            W[f"l{i}.qkv"] = Pair(torch.cat([v[a + "q_proj/kernel"], v[a + "k_proj/kernel"], v[a + "v_proj/kernel"]], 1).to(bf))
+            W[f"l{i}.out"] = Pair(v[a + "out_proj/kernel"].to(bf))
+            W[f"l{i}.ff1"] = Pair(v[f + "intermediate_dense/kernel"].to(bf))
+            W[f"l{i}.ff2"] = Pair(v[f + "output_dense/kernel"].to(bf))
+        self._wt = W
+        return W
+
+    # ------------------------------------------------------------------ forward keeping what the backward needs
+    def _forward(self, speech, spec_mask=None):
+        model = self.model
+        cfg, v = model.config, model.variables
+        last_f32, B, T = model._features(speech)          # frozen extractor: the inference kernels, nothing kept
+        P, A = model._packed, model._arena
+        passes = _PRECISIONS[model.precision]
+        lo = passes == 3
+        f32, eps = torch.float32, cfg.layer_norm_eps
+        Cl, d, ffn = cfg.filter_sizes[-1], cfg.hidden_size, cfg.intermediate_size
+        H, dh = cfg.num_heads, cfg.head_size
+        M = B * T
+        S = {"B": B, "T": T, "last_f32": last_f32}
+        fp = "wav2vec2/feature_projection/"
+        pn = A.pair("proj.in", (M, Cl), lo)
+        ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo)
+        h_f32 = A.get("h.f32", (M, d), f32)
+        h = A.pair("h", (M, d), lo)
+        ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"], out_f32=h_f32,
+                 out_hi=h.hi, out_lo=h.lo, passes=passes)
+        S["spec_mask"] = None
+        if cfg.apply_spec_augment:                         # modeling.py:193-199 (host RNG like the reference's numpy RNG)
+            if spec_mask is None:
+                from .spec_augment import _compute_mask_indices
+                spec_mask = _compute_mask_indices((B, T), cfg.mask_time_prob, cfg.mask_time_length, min_masks=2)
+            mask = torch.as_tensor(spec_mask).to(model.device).bool()
+            hv = torch.where(mask[:, :, None], v["wav2vec2/masked_spec_embed"], h_f32.view(B, T, d))
+            h_f32.copy_(hv.reshape(M, d))
+            sp = ops.split_bf16(h_f32, lo)
+            h.hi.copy_(sp.hi)
+            if lo:
+                h.lo.copy_(sp.lo)
+            S["spec_mask"] = mask.reshape(M)
+        S["pn"], S["h"] = pn, h
+        enc = "wav2vec2/encoder/"
+        y0 = A.get("t.y0", (M, d), f32)
+        pos_pre = A.get("t.pos.pre", (M, d), f32)
+        ops.posconv_train(h, P["pos.w"], v[enc + "pos_conv_embed/conv/bias"], h_f32, y0, B, T, d,
+                          cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes, pre_out=pos_pre)
+        S["y0"], S["pos_pre"] = y0, pos_pre
+        xs_f32 = A.get("x.f32", (M, d), f32)
+        x1_f32 = A.get("x1.f32", (M, d), f32)
+        xs = A.pair("t.xs.0", (M, d), lo)
+        ops.ln_rows(y0, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=xs_f32, out_hi=xs.hi,
+                    out_lo=xs.lo)
+        L = []
+        for i in range(cfg.num_layers):
+            lb = f"{enc}layers/{i}/"
+            qkv = A.pair(f"t.qkv.{i}", (M, 3 * d), lo)
+            ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi, out_lo=qkv.lo,
+                     passes=passes)
+            ctx = A.pair(f"t.ctx.{i}", (M, d), lo)
+            ops.attn_fwd(qkv, B, T, H, dh, None, ctx, passes)
+            y1 = A.get(f"t.y1.{i}", (M, d), f32)
+            ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
+                     residual=xs_f32, out_f32=y1, passes=passes)
+            x1 = A.pair(f"t.x1.{i}", (M, d), lo)
+            ops.ln_rows(y1, v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"], eps, M, d, out_f32=x1_f32, out_hi=x1.hi,
+                        out_lo=x1.lo)
+            pre = A.get(f"t.pre.{i}", (M, ffn), f32)
+            ops.gemm(x1, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
+                     out_f32=pre, passes=passes)
+            mid = A.pair(f"t.mid.{i}", (M, ffn), lo)
+            ops.gelu_rows(pre, mid.hi, fast=(passes == 1), out_lo=mid.lo)
+            y2 = A.get(f"t.y2.{i}", (M, d), f32)
+            ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=v[lb + "feed_forward/output_dense/bias"],
+                     residual=x1_f32, out_f32=y2, passes=passes)
+            nxt = A.pair(f"t.xs.{i + 1}", (M, d), lo)
+            ops.ln_rows(y2, v[lb + "final_layer_norm/gamma"], v[lb + "final_layer_norm/beta"], eps, M, d, out_f32=xs_f32,
+                        out_hi=nxt.hi, out_lo=nxt.lo)
+            L.append(dict(xs=xs, qkv=qkv, ctx=ctx, y1=y1, x1=x1, pre=pre, mid=mid, y2=y2))
+            xs = nxt
+        V = cfg.vocab_size
+        logits = A.get("t.logits", (B, T, V), f32)
+        ops.gemm(xs, P["lm.w"], K=d, N=V, rows_per_batch=M, bias=v["lm_head/bias"], out_f32=logits, passes=passes, block_n=32)
+        S["layers"], S["hidden_f32"] = L, xs_f32
+        self.saved = S
+        return logits
+
+    # ------------------------------------------------------------------ backward
+    def _wgrad(self, x_hi, dy_t, M, Mp, n_in, out):
+        """out[n_in][n_out] = x^T dy: A = x^T [n_in][Mp] (made here), weight operand = dy^T rows [n_out][Mp]."""
+        A = self.model._arena
+        xt = A.get(f"b.T.{n_in}", (n_in, Mp), torch.bfloat16)
+        ops.transpose_bf16(x_hi, M, n_in, xt, Mp)
+        ops.gemm(Pair(xt), Pair(dy_t), K=Mp, N=dy_t.shape[0], rows_per_batch=n_in, out_f32=out)
+
+    def _backward(self, dlogits):
+        model, G, S = self.model, self.G, self.saved
+        cfg, v, A = model.config, model.variables, model._arena
+        W = self._wt or self._pack_backward()
+        B, T = S["B"], S["T"]
+        M = B * T
+        Mp = ((M + 63) // 64) * 64
+        f32, bf, eps = torch.float32, torch.bfloat16, cfg.layer_norm_eps
+        Cl, d, ffn = cfg.filter_sizes[-1], cfg.hidden_size, cfg.intermediate_size
+        H, dh, V = cfg.num_heads, cfg.head_size, cfg.vocab_size
+        self.flat_g.zero_()
+        ops.lm_head_wgrad(S["hidden_f32"], dlogits.view(M, V), G["lm_head/kernel"], G["lm_head/bias"])
+        g = A.get("b.g", (M, d), f32)
+        ops.lm_head_dgrad(dlogits, v["lm_head/kernel"], g)
+        dy, dyh = A.get("b.dy", (M, d), f32), A.get("b.dyh", (M, d), bf)
+        g1 = A.get("b.g1", (M, d), f32)
+        dmid, dpre = A.get("b.dmid", (M, ffn), bf), A.get("b.dpre", (M, ffn), bf)
+        dctx, dqkv = A.get("b.dctx", (M, d), bf), A.get("b.dqkv", (M, 3 * d), bf)
+        dyT, dffT = A.get("b.dyT", (d, Mp), bf), A.get("b.dffT", (ffn, Mp), bf)
+        dqkvT = A.get("b.dqkvT", (3 * d, Mp), bf)
+        qkv_bias = A.get("b.qkvb", (3 * d,), f32)
+        ws = A.get("b.attn.ws", (2 * B * H * T,), f32)
+        enc = "wav2vec2/encoder/"
+        for i in reversed(range(cfg.num_layers)):
+            Li = S["layers"][i]
+            lb = f"{enc}layers/{i}/"
+            ff, at = lb + "feed_forward/", lb + "attention/"
+            # x_{i+1} = LN2(y2),  y2 = x1 + mid W2 + b2
+            ops.ln_bwd(Li["y2"], v[lb + "final_layer_norm/gamma"], g, eps, M, d, dx_f32=dy, dx_hi=dyh,
+                       dgamma=G[lb + "final_layer_norm/gamma"], dbeta=G[lb + "final_layer_norm/beta"],
+                       colsum=G[ff + "output_dense/bias"])
+            ops.gemm(Pair(dyh), W[f"l{i}.ff2"], K=d, N=ffn, rows_per_batch=M, out_hi=dmid)
+            ops.transpose_bf16(dyh, M, d, dyT, Mp)
+            self._wgrad(Li["mid"].hi, dyT, M, Mp, ffn, G[ff + "output_dense/kernel"])
+            # mid = gelu(pre),  pre = x1 W1 + b1
+            ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"])
+            ops.gemm(Pair(dpre), W[f"l{i}.ff1"], K=ffn, N=d, rows_per_batch=M, residual=dy, out_f32=g1)
+            ops.transpose_bf16(dpre, M, ffn, dffT, Mp)
+            self._wgrad(Li["x1"].hi, dffT, M, Mp, d, G[ff + "intermediate_dense/kernel"])
+            # x1 = LN1(y1),  y1 = x + ctx Wo + bo
+            ops.ln_bwd(Li["y1"], v[lb + "layer_norm/gamma"], g1, eps, M, d, dx_f32=dy, dx_hi=dyh,
+                       dgamma=G[lb + "layer_norm/gamma"], dbeta=G[lb + "layer_norm/beta"], colsum=G[at + "out_proj/bias"])
+            ops.gemm(Pair(dyh), W[f"l{i}.out"], K=d, N=d, rows_per_batch=M, out_hi=dctx)
+            ops.transpose_bf16(dyh, M, d, dyT, Mp)
+            self._wgrad(Li["ctx"].hi, dyT, M, Mp, d, G[at + "out_proj/kernel"])
+            # ctx = softmax(q k^T) v  (q carries dh^-1/2: encoder.py:28 folded into the packed q projection)
+            ops.attn_bwd(Li["qkv"].hi, Li["ctx"].hi, dctx, B, T, H, dh, None, dh ** -0.5, dqkv, workspace=ws)
+            qkv_bias.zero_()
+            ops.dact_colsum(dqkv, None, M, 3 * d, colsum=qkv_bias)
+            for j, n in enumerate(("q", "k", "v")):
+                G[at + f"{n}_proj/bias"].copy_(qkv_bias[j * d:(j + 1) * d])
+            ops.gemm(Pair(dqkv), W[f"l{i}.qkv"], K=3 * d, N=d, rows_per_batch=M, residual=dy, out_f32=g)
+            ops.transpose_bf16(dqkv, M, 3 * d, dqkvT, Mp)
+            xt = A.get(f"b.T.{d}", (d, Mp), bf)
+            ops.transpose_bf16(Li["xs"].hi, M, d, xt, Mp)
+            for j, n in enumerate(("q", "k", "v")):
+                ops.gemm(Pair(xt), Pair(dqkvT[j * d:(j + 1) * d]), K=Mp, N=d, rows_per_batch=d, out_f32=G[at + f"{n}_proj/kernel"])
+        # x_0 = LN_enc(y0),  y0 = h + gelu(pos_pre),  pos_pre = conv(h) + b
+        ops.ln_bwd(S["y0"], v[enc + "layer_norm/gamma"], g, eps, M, d, dx_f32=dy, dx_hi=dyh,
+                   dgamma=G[enc + "layer_norm/gamma"], dbeta=G[enc + "layer_norm/beta"])
+        pc = enc + "pos_conv_embed/conv/"
+        dpc = dctx
+        ops.dact_colsum(dyh, S["pos_pre"], M, d, out_hi=dpc, colsum=G[pc + "bias"])
+        groups, ktaps = cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings
+        dh_f32 = g1
+        ops.posconv_train(Pair(dpc), W["pos.T"], None, dy, dh_f32, B, T, d, groups, ktaps, 1, shift=1, linear=True)
+        dwn = A.get("b.dwn", (ktaps, d // groups, d), f32)
+        ops.posconv_wgrad(S["h"].hi, dpc, B, T, d, groups, ktaps, dwn)
+        # weight-norm chain rule (tensorflow_addons.py:16-21: W = g * v / ||v||, norm over axes (1, 2) of every tap)
+        wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
+        nrm = torch.sqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12))
+        dot = (dwn * wv).sum(dim=(1, 2), keepdim=True)
+        G[pc + "weight_g"].copy_(dot / nrm)
+        G[pc + "weight_v"].copy_(wg / nrm * (dwn - wv * dot / (nrm * nrm)))
+        if S["spec_mask"] is not None:                      # masked frames were replaced by masked_spec_embed (modeling.py:193-199)
+            msk = S["spec_mask"]
+            G["wav2vec2/masked_spec_embed"].copy_((dh_f32 * msk[:, None]).sum(0))
+            dh_f32.mul_((~msk)[:, None])
+        # h = pn Wp + bp,  pn = LN_fp(extractor output)
+        fp = "wav2vec2/feature_projection/"
+        dhh = ops.split_bf16(dh_f32, False).hi
+        ops.dact_colsum(dhh, None, M, d, colsum=G[fp + "projection/bias"])
+        ops.transpose_bf16(dhh, M, d, dyT, Mp)
+        self._wgrad(S["pn"].hi, dyT, M, Mp, Cl, G[fp + "projection/kernel"])
+        dpn = A.get("b.dpn", (M, Cl), f32)
+        ops.gemm(Pair(dhh), W["proj"], K=d, N=Cl, rows_per_batch=M, out_f32=dpn)
+        ops.ln_bwd(S["last_f32"], v[fp + "layer_norm/gamma"], dpn, eps, M, Cl, dgamma=G[fp + "layer_norm/gamma"],
+                   dbeta=G[fp + "layer_norm/beta"])
+
+    # ------------------------------------------------------------------ one optimisation step
+    @torch.no_grad()
+    def loss_and_gradients(self, speech, labels, spec_mask=None):
+        """Forward + CTC loss + backward on this rank's shard; gradients land in ``self.G`` (views of ``flat_g``).
+        ``spec_mask`` [B, T'] overrides the sampled SpecAugment mask (tests)."""
+        logits = self._forward(speech.to(self.model.device), spec_mask)
+        loss, dlogits = self.loss_fn(labels, logits, return_grad=True)
+        self._backward(dlogits)
+        return loss
+
+    @torch.no_grad()
+    def step(self, speech, labels, spec_mask=None):
+        loss = self.loss_and_gradients(speech, labels, spec_mask)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)          # the step's single collective
+        self.t += 1
+        lr_t = self.lr * (1.0 - self.b2 ** self.t) ** 0.5 / (1.0 - self.b1 ** self.t)
+        ops.adam(self.flat_w, self.flat_g, self.m, self.v, lr_t, self.b1, self.b2, self.eps)
+        self.model._packed = None          # kernel-layout copies follow the update at the next forward
+        self._wt = None
+        return loss

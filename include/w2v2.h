@@ -139,6 +139,11 @@ typedef struct w2v2_posconv_args {
   const float* resid;    /* fp32 [batch][frames][hidden] */
   float* out_f32;        /* fp32 [batch][frames][hidden] */
   int32_t batch, frames, hidden, groups, ktaps, passes;
+  /* training (zero for inference): */
+  float* pre_out;        /* optional fp32 [batch][frames][hidden]: bias + conv, the pre-activation kept for the backward */
+  int32_t shift;         /* the tap window starts at frame t - ktaps/2 + shift */
+  int32_t linear;        /* 1: out = resid + conv(x) (no bias, no GELU) - with flipped / transposed taps and shift = 1
+                            this is the input gradient of the convolution */
 } w2v2_posconv_args;
 
 int w2v2_posconv(const w2v2_posconv_args* args, void* stream);
@@ -170,6 +175,42 @@ int w2v2_lm_head_wgrad(const float* hidden /*[rows][hidden_size]*/, const float*
                        int64_t rows, int hidden_size, int vocab, float* grad_kernel, float* grad_bias, void* stream);
 int w2v2_adam(float* weights, const float* grads, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
               float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage-2 fine-tune step (src/main.py:234-250: Keras `fit` differentiates the whole encoder; the conv extractor
+ * stays frozen, main.py:236-237).  The matrix products of the backward pass reuse w2v2_gemm_bf16:
+ *   dgrad  dX = dY . W^T    A = dY [rows][out], weight operand = the TF Dense kernel itself ([in][out] is W^T, K-major)
+ *   wgrad  dW = X^T . dY    A = X^T [in][rows], weight operand = dY^T [out][rows]  (w2v2_transpose_bf16 makes both),
+ *                           out_f32 = the gradient in the TF layout [in][out]
+ * and these kernels supply everything else.
+ * ------------------------------------------------------------------------------------------- */
+/* Backward of LayerNormalization (encoder.py:96-108,232-234, feature_extractor.py:86-88): x = the LN input kept by the
+ * forward, dy = gradient of its output.  dx -> fp32 and/or bf16; dgamma / dbeta / colsum (= sum over rows of dx, the
+ * bias gradient of the Dense that produced x) are ACCUMULATED (atomicAdd): the caller zeroes them once per step. */
+int w2v2_ln_bwd(const float* x, const float* gamma, const float* dy, float eps, int64_t rows, int d, float* dx_f32,
+                void* dx_hi, float* dgamma, float* dbeta, float* colsum /*or NULL*/, void* stream);
+/* GELU of a saved fp32 pre-activation -> bf16 (training forward keeps the pre-activation for the backward).
+ * fast != 0: the tanh-form of the single-pass mode (same values as the GEMM epilogue of inference). */
+int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_hi, void* out_lo /*or NULL*/, void* stream);
+/* out = dy * gelu'(pre) (exact erf form, config.py:14) as bf16, colsum += column sums of the ROUNDED result (bias
+ * gradient).  pre == NULL: no activation (plain column sums of dy, out may be NULL). */
+int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t rows, int cols, void* out_hi, float* colsum, void* stream);
+/* out[n][m] = in[m][n] (bf16), rows m in [rows, out_ld) are written as zeros (K padding of the wgrad GEMMs). */
+int w2v2_transpose_bf16(const void* in, int64_t rows, int cols, void* out, int64_t out_ld, void* stream);
+/* dHidden[rows][hidden] = dLogits[rows][vocab] . kernel[hidden][vocab]^T (backward of the Dense at modeling.py:231,254), fp32. */
+int w2v2_lm_head_dgrad(const float* grad_logits, const float* kernel, int64_t rows, int hidden_size, int vocab, float* out,
+                       void* stream);
+/* Backward of the attention core (forward: w2v2_attn_fwd; reference encoder.py:34-54): from the packed projection qkv,
+ * the context ctx = softmax(q k^T) v and its gradient dctx (all bf16) to dqkv in the packed layout; the q part is
+ * multiplied by q_scale (= head_size^-1/2: the forward folds that factor into the q projection, encoder.py:28).
+ * workspace: w2v2_attn_bwd_workspace_bytes(batch, frames, num_heads). */
+int64_t w2v2_attn_bwd_workspace_bytes(int batch, int frames, int num_heads);
+int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void* dctx_hi, int batch, int frames, int num_heads,
+                  int head_size, const int32_t* kv_len, float q_scale, void* workspace, void* dqkv_hi, void* stream);
+/* Weight gradient of the positional convolution in the TF kernel layout [ktaps][hidden/groups][hidden]
+ * (w.r.t. the weight-NORMALISED kernel; the weight-norm chain rule is parameter-sized host algebra). */
+int w2v2_posconv_wgrad(const void* x_hi, const void* dpre_hi, int batch, int frames, int hidden, int groups, int ktaps,
+                       float* grad_kernel, void* stream);
 
 #ifdef __cplusplus
 }
