@@ -137,13 +137,96 @@ def run_reference(args, rank, world):
     }))
 
 
+def run_train(args, rank, world, local_rank):
+    """--mode train: BASELINE.json configs[2] - the stage-2 CTC fine-tune step (src/main.py:234-250) of wav2vec2-base,
+    `--batch` utterances of `--seq` samples per GPU, data parallel over the ranks with ONE NCCL all-reduce of the flat
+    fp32 gradient buffer per step.  Forward in the model's precision, backward products single-pass bf16."""
+    import numpy as np
+    import torch.distributed as dist
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC, ops
+    from wav2vec2.training import Stage2Trainer
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, K = max(args.warmup, 3), args.steps
+    B, L = args.batch, args.seq
+    cfg = Wav2Vec2Config(dropout=0.0)                       # reference defaults otherwise (SpecAugment on); no dropout RNG yet
+    model = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision=args.precision, device=dev).init_random(seed=0)
+    trainer = Stage2Trainer(model, CTCLoss(cfg, (B, L), division_factor=B * world), learning_rate=5e-5)
+    x_host = torch.randn(B, L, generator=torch.Generator().manual_seed(rank)).pin_memory()
+    np.random.seed(rank)
+    lab = np.zeros((B, 256), dtype=np.int32)                # main.py:51: labels padded to 256
+    lab[:, :24] = np.random.randint(1, 30, size=(B, 24))    # tests/test_wav2vec2.py:41-42
+    lab_host = torch.from_numpy(lab).pin_memory()
+    x, labels = x_host.to(dev), lab_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n0 = ops.LAUNCHES
+    losses = [trainer.step(x, labels).item()]
+    launches_per_step = ops.LAUNCHES - n0
+    for _ in range(W - 1):
+        losses.append(trainer.step(x, labels).item())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        e0.record()
+        for _ in range(K):
+            loss = trainer.step(x, labels)
+        e1.record()
+        barrier()
+    losses.append(loss.item())
+    ms = e0.elapsed_time(e1)
+    # end to end: pinned host speech + labels -> device, step, loss back on the host, every step
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(K):
+        x.copy_(x_host, non_blocking=True)
+        labels.copy_(lab_host, non_blocking=True)
+        loss_host = trainer.step(x, labels).item()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    audio_s = world * B * L / SAMPLE_RATE
+    fl = flops_forward(cfg, L)
+    enc_fl = fl["total"] - sum(fl["convs"])                 # the extractor is frozen: forward only
+    step_flops = B * (sum(fl["convs"]) + 3.0 * enc_fl)      # backward ~ 2x forward for the trained part
+    print(json.dumps({
+        "metric": "audio-sec/s", "value": audio_s / (ms / K / 1e3), "unit": "audio-sec/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "bf16x3 forward / bf16 backward", "data": "synthetic",
+        "config": {"workload": f"wav2vec2-base stage-2 CTC fine-tune step (forward + CTC + backward + all-reduce + Adam), "
+                               f"batch={B}/GPU, seq={L}", "global_batch": B * world, "seq_len": L,
+                   "parallelism": f"dp{world} (batch sharded; one NCCL all-reduce of {trainer.flat_g.numel()} fp32 gradients per step)",
+                   "trainable_params": int(trainer.flat_w.numel()), "dropout": 0.0, "spec_augment": bool(cfg.apply_spec_augment)},
+        "clocks": clk.summary(),
+        "e2e": {"value": audio_s / (ms_e2e / K / 1e3), "unit": "audio-sec/s",
+                "h2d_bytes_per_step": int(x_host.numel() * 4 + lab_host.numel() * 4), "d2h_bytes_per_step": 4},
+        "gpu_launches": launches_per_step * K, "model_tflops": step_flops / (ms / K / 1e3) / 1e12,
+        "loss_first_last": [losses[0], losses[-1]],
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="utterances per GPU")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="infer: BASELINE configs[1] (default, the headline); train: configs[2], the stage-2 fine-tune step")
+    ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default 32 for infer, 8 for train)")
     ap.add_argument("--seq", type=int, default=246000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -153,8 +236,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.batch is None:
+        args.batch = 8 if args.mode == "train" else 32
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.mode == "train":
+        run_train(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist

@@ -50,6 +50,19 @@ __device__ __forceinline__ void load_b_kn(uint32_t& b0, uint32_t& b1, const __nv
   const uint32_t addr = smem_u32(tile + (k0 + (lane & 15)) * AB_LD + n0);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(addr));
 }
+// the same two fragment kinds for TWO adjacent n-tiles with one ldmatrix.x4: b[0], b[1] = n-tile n0, b[2], b[3] = n-tile n0 + 8
+__device__ __forceinline__ void load_b_nk_x4(uint32_t (&b)[4], const __nv_bfloat16* tile, int n0, int k0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  const uint32_t addr = smem_u32(tile + (n0 + 8 * (mat >> 1) + r) * AB_LD + k0 + 8 * (mat & 1));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+}
+__device__ __forceinline__ void load_b_kn_x4(uint32_t (&b)[4], const __nv_bfloat16* tile, int k0, int n0, int lane) {
+  const int mat = lane >> 3, r = lane & 7;
+  const uint32_t addr = smem_u32(tile + (k0 + 8 * (mat & 1) + r) * AB_LD + n0 + 8 * (mat >> 1));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]) : "r"(addr));
+}
 // copy a [64 x 64] bf16 tile (rows t0.., row stride ld_g elements) into padded smem, zero beyond `t_end`
 __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, int t0, int t_end, size_t ld_g,
                                           int tid, int nthreads) {
@@ -60,6 +73,24 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
     *reinterpret_cast<uint4*>(dst + r * AB_LD + 8 * p) = v;
   }
 }
+
+// asynchronous (cp.async, 16 B per request) version: rows >= t_end are zero-filled through src-size 0
+__device__ __forceinline__ void load_tile_async(__nv_bfloat16* dst, const __nv_bfloat16* src, int t0, int t_end, size_t ld_g,
+                                                int tid, int nthreads) {
+  for (int i = tid; i < AB_BLK * 8; i += nthreads) {
+    const int r = i >> 3, p = i & 7;
+    const bool ok = t0 + r < t_end;
+    const __nv_bfloat16* g = src + (ok ? (size_t)(t0 + r) * ld_g + 8 * p : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + r * AB_LD + 8 * p)), "l"(g),
+                 "r"(ok ? 16 : 0) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_f32(float* dst, const float* src, bool ok) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(ok ? 4 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ------------------------------------------------------------------------------------ dQ (+ lse2, D)
 __global__ void __launch_bounds__(128)
@@ -110,21 +141,36 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   }
 
   const int nkb = (klen + AB_BLK - 1) / AB_BLK;
+  // K / V tiles stream through a 2-deep cp.async pipeline over the 2 * nkb stages of both sweeps (sweep 1 needs K only);
+  // the Q / dO tiles are dead once their fragments sit in registers, so they serve as the second pair of buffers
+  __syncthreads();
+  __nv_bfloat16* const bufK[2] = {sK, sQ};
+  __nv_bfloat16* const bufV[2] = {sV, sdO};
+  auto issue = [&](int stage) {
+    const int kb2 = (stage >= nkb) ? stage - nkb : stage;
+    load_tile_async(bufK[stage & 1], kp, kb2 * AB_BLK, klen, ld3, tid, 128);
+    if (stage >= nkb) load_tile_async(bufV[stage & 1], vp, kb2 * AB_BLK, klen, ld3, tid, 128);
+    cp_async_commit();
+  };
+  issue(0);
   float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.0f, 0.0f};
   // ---- sweep 1: softmax statistics (log2 domain)
   for (int kb = 0; kb < nkb; ++kb) {
+    issue(kb + 1);                 // stage nkb (first of sweep 2) always exists
+    cp_async_wait<1>();
     __syncthreads();
-    load_tile(sK, kp, kb * AB_BLK, klen, ld3, tid, 128);
-    __syncthreads();
+    const __nv_bfloat16* sK = bufK[kb & 1];
     float s[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < 8; j += 2) {
       s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
+      s[j + 1][0] = s[j + 1][1] = s[j + 1][2] = s[j + 1][3] = 0.0f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1;
-        load_b_nk(b0, b1, sK, 8 * j, 16 * ks, g, q);
-        mma16816(s[j], aq[ks], b0, b1);
+        uint32_t bb[4];
+        load_b_nk_x4(bb, sK, 8 * j, 16 * ks, lane);
+        mma16816(s[j], aq[ks], bb[0], bb[1]);
+        mma16816(s[j + 1], aq[ks], bb[2], bb[3]);
       }
     }
 #pragma unroll
@@ -146,12 +192,13 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       const float nm = fmaxf(mx[r], bm);
       float ps = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ps += exp2f(s[j][2 * r] - nm) + exp2f(s[j][2 * r + 1] - nm);
+      for (int j = 0; j < 8; ++j) ps += ex2_approx(s[j][2 * r] - nm) + ex2_approx(s[j][2 * r + 1] - nm);
       ps += __shfl_xor_sync(0xffffffffu, ps, 1);
       ps += __shfl_xor_sync(0xffffffffu, ps, 2);
       sum[r] = sum[r] * exp2f(mx[r] - nm) + ps;
       mx[r] = nm;
     }
+    __syncthreads();               // every warp is done with this buffer before the stage after next refills it
   }
   float lse2[2];
 #pragma unroll
@@ -169,22 +216,30 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
   for (int kb = 0; kb < nkb; ++kb) {
+    const int stage = nkb + kb;
+    if (kb + 1 < nkb) {
+      issue(stage + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    load_tile(sK, kp, kb * AB_BLK, klen, ld3, tid, 128);
-    load_tile(sV, vp, kb * AB_BLK, klen, ld3, tid, 128);
-    __syncthreads();
+    const __nv_bfloat16* sK = bufK[stage & 1];
+    const __nv_bfloat16* sV = bufV[stage & 1];
     float s[8][4], dp[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
-      dp[j][0] = dp[j][1] = dp[j][2] = dp[j][3] = 0.0f;
+    for (int j = 0; j < 8; j += 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = s[j + 1][e] = dp[j][e] = dp[j + 1][e] = 0.0f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1;
-        load_b_nk(b0, b1, sK, 8 * j, 16 * ks, g, q);
-        mma16816(s[j], aq[ks], b0, b1);
-        load_b_nk(b0, b1, sV, 8 * j, 16 * ks, g, q);
-        mma16816(dp[j], ado[ks], b0, b1);
+        uint32_t bb[4];
+        load_b_nk_x4(bb, sK, 8 * j, 16 * ks, lane);
+        mma16816(s[j], aq[ks], bb[0], bb[1]);
+        mma16816(s[j + 1], aq[ks], bb[2], bb[3]);
+        load_b_nk_x4(bb, sV, 8 * j, 16 * ks, lane);
+        mma16816(dp[j], ado[ks], bb[0], bb[1]);
+        mma16816(dp[j + 1], ado[ks], bb[2], bb[3]);
       }
     }
     // dS (bf16) as A fragments: key pairs (2 jj, 2 jj + 1) of n-tiles form one 16-wide k step
@@ -197,7 +252,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const int key = kb * AB_BLK + 8 * j + 2 * q + e;
-          const float p = (key < klen) ? exp2f(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
+          const float p = (key < klen) ? ex2_approx(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
           ds[2 * r + e] = p * (dp[j][2 * r + e] - dsum[r]);
         }
       }
@@ -207,12 +262,14 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {      // k = 16 keys
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {       // n = 8 head channels
-        uint32_t b0, b1;
-        load_b_kn(b0, b1, sK, 16 * ks, 8 * j, lane);
-        mma16816(dq[j], ads[ks], b0, b1);
+      for (int j = 0; j < 8; j += 2) {    // n = 2 x 8 head channels
+        uint32_t bb[4];
+        load_b_kn_x4(bb, sK, 16 * ks, 8 * j, lane);
+        mma16816(dq[j], ads[ks], bb[0], bb[1]);
+        mma16816(dq[j + 1], ads[ks], bb[2], bb[3]);
       }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -232,7 +289,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
                     const int* __restrict__ kv_len, int T, int H, const float* __restrict__ lse2_in,
                     const float* __restrict__ dsum_in, __nv_bfloat16* __restrict__ dqkv) {
   __shared__ __align__(16) __nv_bfloat16 sQ[AB_BLK * AB_LD], sdO[AB_BLK * AB_LD], sK[AB_BLK * AB_LD], sV[AB_BLK * AB_LD];
-  __shared__ float s_lse[AB_BLK], s_ds[AB_BLK];
+  __shared__ float s_lse2[2][AB_BLK], s_ds2[2][AB_BLK];
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int d = H * AB_DH;
   const int k0 = blockIdx.x * AB_BLK;
@@ -262,29 +319,47 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   }
   const bool key_ok[2] = {k0 + m0 + g < klen, k0 + m0 + g + 8 < klen};
   const int nqb = (T + AB_BLK - 1) / AB_BLK;
+  // Q / dO tiles (+ lse2, D) stream through a 2-deep cp.async pipeline; the K / V tiles are dead once their fragments sit
+  // in registers, so they serve as the second pair of buffers
+  __syncthreads();
+  __nv_bfloat16* const bufQ[2] = {sQ, sK};
+  __nv_bfloat16* const bufdO[2] = {sdO, sV};
+  auto issue = [&](int qb2) {
+    load_tile_async(bufQ[qb2 & 1], qp, qb2 * AB_BLK, T, ld3, tid, 128);
+    load_tile_async(bufdO[qb2 & 1], dop, qb2 * AB_BLK, T, d, tid, 128);
+    const int t = qb2 * AB_BLK + (tid & 63);
+    const float* src = (tid < 64 ? lse2_in : dsum_in) + (size_t)bh * T + (t < T ? t : 0);
+    cp_async_f32(tid < 64 ? &s_lse2[qb2 & 1][tid] : &s_ds2[qb2 & 1][tid - 64], src, t < T);
+    cp_async_commit();
+  };
+  issue(0);
   for (int qb = 0; qb < nqb; ++qb) {
-    __syncthreads();
-    load_tile(sQ, qp, qb * AB_BLK, T, ld3, tid, 128);
-    load_tile(sdO, dop, qb * AB_BLK, T, d, tid, 128);
-    if (tid < AB_BLK) {
-      const int t = qb * AB_BLK + tid;
-      s_lse[tid] = (t < T) ? lse2_in[(size_t)bh * T + t] : 0.0f;
-      s_ds[tid] = (t < T) ? dsum_in[(size_t)bh * T + t] : 0.0f;
+    if (qb + 1 < nqb) {
+      issue(qb + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const __nv_bfloat16* sQ = bufQ[qb & 1];
+    const __nv_bfloat16* sdO = bufdO[qb & 1];
+    const float* s_lse = s_lse2[qb & 1];
+    const float* s_ds = s_ds2[qb & 1];
     // S^T = K Q^T and dP^T = V dO^T : [16 keys] x [64 queries]
     float st[8][4], dpt[8][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      st[j][0] = st[j][1] = st[j][2] = st[j][3] = 0.0f;
-      dpt[j][0] = dpt[j][1] = dpt[j][2] = dpt[j][3] = 0.0f;
+    for (int j = 0; j < 8; j += 2) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) st[j][e] = st[j + 1][e] = dpt[j][e] = dpt[j + 1][e] = 0.0f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
-        uint32_t b0, b1;
-        load_b_nk(b0, b1, sQ, 8 * j, 16 * ks, g, q);
-        mma16816(st[j], ak[ks], b0, b1);
-        load_b_nk(b0, b1, sdO, 8 * j, 16 * ks, g, q);
-        mma16816(dpt[j], av[ks], b0, b1);
+        uint32_t bb[4];
+        load_b_nk_x4(bb, sQ, 8 * j, 16 * ks, lane);
+        mma16816(st[j], ak[ks], bb[0], bb[1]);
+        mma16816(st[j + 1], ak[ks], bb[2], bb[3]);
+        load_b_nk_x4(bb, sdO, 8 * j, 16 * ks, lane);
+        mma16816(dpt[j], av[ks], bb[0], bb[1]);
+        mma16816(dpt[j + 1], av[ks], bb[2], bb[3]);
       }
     }
     uint32_t ap[4][4], ads[4][4];   // P^T and dS^T as A fragments (k = query index)
@@ -297,7 +372,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
         for (int e = 0; e < 2; ++e) {
           const int qi = 8 * j + 2 * q + e;
           const bool ok = key_ok[r] && (qb * AB_BLK + qi < T);
-          const float pv = ok ? exp2f(st[j][2 * r + e] * AB_LOG2E - s_lse[qi]) : 0.0f;
+          const float pv = ok ? ex2_approx(st[j][2 * r + e] * AB_LOG2E - s_lse[qi]) : 0.0f;
           p[2 * r + e] = pv;
           ds[2 * r + e] = pv * (dpt[j][2 * r + e] - s_ds[qi]);
         }
@@ -310,14 +385,17 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {      // k = 16 queries
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {       // n = 8 head channels
-        uint32_t b0, b1;
-        load_b_kn(b0, b1, sdO, 16 * ks, 8 * j, lane);
-        mma16816(dv[j], ap[ks], b0, b1);
-        load_b_kn(b0, b1, sQ, 16 * ks, 8 * j, lane);
-        mma16816(dk[j], ads[ks], b0, b1);
+      for (int j = 0; j < 8; j += 2) {    // n = 2 x 8 head channels
+        uint32_t bb[4];
+        load_b_kn_x4(bb, sdO, 16 * ks, 8 * j, lane);
+        mma16816(dv[j], ap[ks], bb[0], bb[1]);
+        mma16816(dv[j + 1], ap[ks], bb[2], bb[3]);
+        load_b_kn_x4(bb, sQ, 16 * ks, 8 * j, lane);
+        mma16816(dk[j], ads[ks], bb[0], bb[1]);
+        mma16816(dk[j + 1], ads[ks], bb[2], bb[3]);
       }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {

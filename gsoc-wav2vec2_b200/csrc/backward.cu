@@ -269,8 +269,8 @@ extern "C" int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t row
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int gx = (cols / 4 + 255) / 256;
-  int gy = (int)((rows + 63) / 64);
-  if (gy > 296) gy = 296;
+  int gy = (int)((rows + 15) / 16);   // short dependent-load chains: many row chunks, 4 atomics per thread at the end
+  if (gy > 1024) gy = 1024;
   dact_colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy_hi), pre, (int)rows, cols,
                                                   reinterpret_cast<__nv_bfloat16*>(out_hi), colsum);
   W2V2_CUDA(cudaGetLastError());
