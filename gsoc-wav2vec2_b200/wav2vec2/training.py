@@ -11,6 +11,8 @@ forward (all the inference kernels), ``w2v2_ctc_loss`` (loss + d loss / d logits
 Not covered yet (stage 2, main.py:234-250): gradients through the encoder.  Dropout RNG is not implemented, so the step
 requires ``config.dropout == 0`` (SpecAugment, main.py/modeling.py:193-199, is applied when enabled).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -120,6 +122,9 @@ class Stage2Trainer:
         model._packed = None
         self._wt = None
         self.saved = None
+        # weight-gradient GEMMs have few output tiles and a long K (= all frames): 1-SM 128 x 128 tiles spread them over
+        # 4x as many SMs as the 256 x 256 CTA-pair tiles of the forward
+        self.wgrad_tiles = dict(cluster=int(os.environ.get("W2V2_WGRAD_CLUSTER", "1")), block_n=int(os.environ.get("W2V2_WGRAD_BN", "128")))
 
     # ------------------------------------------------------------------ operand packs of the backward GEMMs
     def _pack_backward(self):
@@ -226,7 +231,7 @@ class Stage2Trainer:
         A = self.model._arena
         xt = A.get(f"b.T.{n_in}", (n_in, Mp), torch.bfloat16)
         ops.transpose_bf16(x_hi, M, n_in, xt, Mp)
-        ops.gemm(Pair(xt), Pair(dy_t), K=Mp, N=dy_t.shape[0], rows_per_batch=n_in, out_f32=out)
+        ops.gemm(Pair(xt), Pair(dy_t), K=Mp, N=dy_t.shape[0], rows_per_batch=n_in, out_f32=out, **self.wgrad_tiles)
 
     def _backward(self, dlogits):
         model, G, S = self.model, self.G, self.saved
@@ -284,7 +289,8 @@ class Stage2Trainer:
             xt = A.get(f"b.T.{d}", (d, Mp), bf)
             ops.transpose_bf16(Li["xs"].hi, M, d, xt, Mp)
             for j, n in enumerate(("q", "k", "v")):
-                ops.gemm(Pair(xt), Pair(dqkvT[j * d:(j + 1) * d]), K=Mp, N=d, rows_per_batch=d, out_f32=G[at + f"{n}_proj/kernel"])
+                ops.gemm(Pair(xt), Pair(dqkvT[j * d:(j + 1) * d]), K=Mp, N=d, rows_per_batch=d, out_f32=G[at + f"{n}_proj/kernel"],
+                         **self.wgrad_tiles)
         # x_0 = LN_enc(y0),  y0 = h + gelu(pos_pre),  pos_pre = conv(h) + b
         ops.ln_bwd(S["y0"], v[enc + "layer_norm/gamma"], g, eps, M, d, dx_f32=dy, dx_hi=dyh,
                    dgamma=G[enc + "layer_norm/gamma"], dbeta=G[enc + "layer_norm/beta"])
