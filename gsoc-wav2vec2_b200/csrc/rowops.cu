@@ -297,6 +297,51 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
+// ------------------------------------------------------------------------------------ utterance normalisation
+// Wav2Vec2Processor._normalize (processor.py:101-106): (x - mean) / sqrt(var + 1e-5), biased variance, per utterance over
+// its `len` real samples ("before padding", data_utils.py:233); samples past `len` are written as the padding value 0.
+__global__ void __launch_bounds__(1024)
+normalize_utterance_kernel(const float* __restrict__ x, const int* __restrict__ lengths, int L, float eps,
+                           float* __restrict__ out) {
+  __shared__ double red[2][32];
+  __shared__ float s_mean, s_rstd;
+  const int b = blockIdx.x;
+  const int n = lengths ? min(max(lengths[b], 0), L) : L;
+  const float* xp = x + (size_t)b * L;
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const double v = (double)__ldg(xp + i);
+    s += v;
+    q += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if (lane_id() == 0) {
+    red[0][threadIdx.x >> 5] = s;
+    red[1][threadIdx.x >> 5] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 32; ++w) {
+      ts += red[0][w];
+      tq += red[1][w];
+    }
+    const double mean = n > 0 ? ts / n : 0.0;
+    double var = n > 0 ? tq / n - mean * mean : 0.0;
+    if (var < 0.0) var = 0.0;
+    s_mean = (float)mean;
+    s_rstd = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  float* op = out + (size_t)b * L;
+  for (int i = threadIdx.x; i < L; i += 1024) op[i] = (i < n) ? (__ldg(xp + i) - mean) * rstd : 0.0f;
+}
+
 // fp32 -> bf16 hi(/lo) planes (weight packing, staging test inputs)
 __global__ void split_bf16_kernel(const float* __restrict__ x, size_t n, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo) {
@@ -403,6 +448,16 @@ extern "C" int w2v2_split_bf16(const float* x, int64_t n, void* hi, void* lo, vo
   if (grid > 148 * 16) grid = 148 * 16;
   split_bf16_kernel<<<grid, 256, 0, s>>>(x, (size_t)n, reinterpret_cast<__nv_bfloat16*>(hi),
                                          reinterpret_cast<__nv_bfloat16*>(lo));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int w2v2_normalize_utterances(const float* wave, const int32_t* lengths, int batch, int num_samples, float eps,
+                                         float* out, void* stream) {
+  W2V2_CHECK_ARG(wave && out, "null pointer");
+  W2V2_CHECK_ARG(batch > 0 && num_samples > 0, "batch and num_samples must be positive");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  normalize_utterance_kernel<<<batch, 1024, 0, s>>>(wave, lengths, num_samples, eps, out);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }

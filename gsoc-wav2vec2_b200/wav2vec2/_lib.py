@@ -56,6 +56,7 @@ SIGNATURES = {
     "w2v2_conv0_gn_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
+    "w2v2_normalize_utterances": [_P, _P, _I, _I, _F, _P, _P],
     "w2v2_split_bf16": [_P, _L, _P, _P, _P],
     "w2v2_attn_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
     "w2v2_posconv": [C.POINTER(PosconvArgs), _P],

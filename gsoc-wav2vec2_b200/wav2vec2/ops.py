@@ -114,6 +114,17 @@ def conv0(wave, weights, w_batch_stride, bias, b_batch_stride, gelu, out_f32=Non
                                       _stream()), "w2v2_conv0")
 
 
+def normalize_utterances(wave, lengths=None, eps=1e-5, out=None):
+    """Device version of Wav2Vec2Processor._normalize: wave [B, L] fp32 (CUDA), lengths [B] int32 or None."""
+    _need_cuda(wave, lengths, out)
+    wave = wave.contiguous().float()
+    B, L = wave.shape
+    out = torch.empty_like(wave) if out is None else out
+    _count(); _lib.check(_lib.load().w2v2_normalize_utterances(_ptr(wave), _ptr(lengths), B, L, float(eps), _ptr(out), _stream()),
+                         "w2v2_normalize_utterances")
+    return out
+
+
 def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None):
     _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo)
     _count(); _lib.check(_lib.load().w2v2_ln_rows(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,

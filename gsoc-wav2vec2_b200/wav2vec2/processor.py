@@ -1,6 +1,7 @@
 """``Wav2Vec2Processor`` with the reference's surface (src/wav2vec2/processor.py:10-106): either a
 feature extractor (per-utterance normalisation) or a character tokenizer with greedy-CTC decode.
-Host-side pre/post-processing; no network access (a missing vocab raises instead of downloading)."""
+Host-side pre/post-processing (CUDA tensors are normalised by the ``w2v2_normalize_utterances`` kernel); no network
+access (a missing vocab raises instead of downloading)."""
 import json
 import os
 import re
@@ -55,6 +56,10 @@ class Wav2Vec2Processor:
     def _normalize(self, x):
         """(x - mean) / sqrt(var + 1e-5), biased variance, per utterance, before padding
         (processor.py:101-106)."""
+        if torch.is_tensor(x) and x.is_cuda:
+            # device path (w2v2_normalize_utterances): one utterance [L] or a batch [B, L] of full-length utterances
+            from . import ops
+            return torch.squeeze(ops.normalize_utterances(x.reshape(-1, x.shape[-1])).reshape(x.shape))
         x = torch.as_tensor(x, dtype=torch.float32)
         mean = x.mean(dim=-1, keepdim=True)
         var = x.var(dim=-1, unbiased=False, keepdim=True)

@@ -112,6 +112,12 @@ int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, cons
 int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
                  float* out_f32, void* out_hi, void* out_lo, void* stream);
 
+/* Wav2Vec2Processor._normalize (processor.py:101-106) on the device: per utterance (x - mean) / sqrt(var + eps) with the
+ * biased variance over its lengths[b] real samples (NULL: all num_samples); the padded tail is written as 0
+ * (normalise BEFORE padding, data_utils.py:233,63).  In place (out == wave) is allowed. */
+int w2v2_normalize_utterances(const float* wave, const int32_t* lengths, int batch, int num_samples, float eps, float* out,
+                              void* stream);
+
 /* fp32 -> bf16 hi(/lo) planes (weight packing). */
 int w2v2_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
 

@@ -304,3 +304,30 @@ def test_frame_argmax():
     torch.manual_seed(8)
     x = torch.randn(4, 77, 32, device=DEV)
     assert torch.equal(ops.frame_argmax(x).long(), x.argmax(-1))
+
+
+def test_processor_normalize_on_device_matches_golden():
+    """Wav2Vec2Processor._normalize on the GPU: the reference's known answer (tests/test_dataloader.py:56-63 via
+    tests/golden/processor.npz), padded batches normalised over their real samples only."""
+    import os
+    import numpy as np
+    from wav2vec2 import Wav2Vec2Processor
+    G = os.path.join(os.path.dirname(__file__), "golden")
+    wav = torch.from_numpy(O.read_wav_s16(os.path.join(G, "sample.wav")).astype(np.float32))
+    want = torch.from_numpy(O.normalize_utterance(wav.numpy()))
+    got = Wav2Vec2Processor(is_tokenizer=False)(wav.to(DEV)).cpu()
+    assert got.shape == want.shape and (got - want).abs().max().item() < 2e-6
+    z = np.load(os.path.join(G, "processor.npz"))
+    assert np.allclose(got[32:40].numpy(), z["reference_vector"], atol=1e-6)     # the reference's own golden vector
+    L = 50000
+    batch = torch.zeros(3, L)
+    lens = torch.tensor([L, 46797, 1234], dtype=torch.int32)
+    batch[0] = torch.randn(L) * 3 + 1
+    batch[1, :46797] = wav
+    batch[2, :1234] = torch.randn(1234) * 0.01
+    out = ops.normalize_utterances(batch.to(DEV), lens.to(DEV)).cpu()
+    for b in range(3):
+        n = int(lens[b])
+        ref = torch.from_numpy(O.normalize_utterance(batch[b, :n].numpy()))
+        assert (out[b, :n] - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+        assert torch.all(out[b, n:] == 0)

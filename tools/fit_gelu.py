@@ -51,3 +51,25 @@ for c in [5.0, 5.5, 6.0]:
 np.set_printoptions(precision=10)
 m = fit(5.5, 8); print(repr(m)); print(evalerr(m,5.5))
 m = fit(5.5, 6); print(repr(m)); print(evalerr(m,5.5))
+
+
+def fit_tanh_form():
+    """--tanh: minimax refit of gelu(x) ~= x/2 (1 + tanh(x (A + B x^2))) against the erf form (single-pass mode epilogues)."""
+    import numpy as np
+    from scipy.optimize import minimize
+    from scipy.special import erf
+    x = np.linspace(-8, 8, 160001)
+    g = 0.5 * x * (1 + erf(x / np.sqrt(2)))
+
+    def f(c):
+        return 0.5 * x * (1 + np.tanh(x * (c[0] + c[1] * x * x)))
+    best = np.array([np.sqrt(2 / np.pi), 0.044715 * np.sqrt(2 / np.pi)])
+    print("textbook constants", best, "max |err|", np.abs(f(best) - g).max())
+    for p in (4, 8, 16, 32):
+        best = minimize(lambda c: (np.abs(f(c) - g) ** p).sum() ** (1 / p), best, method="Nelder-Mead",
+                        options=dict(xatol=1e-10, fatol=1e-14, maxiter=20000)).x
+    print("refit", best, "max |err|", np.abs(f(best) - g).max())
+
+
+if __name__ == "__main__" and "--tanh" in __import__("sys").argv:
+    fit_tanh_form()
