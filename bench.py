@@ -26,6 +26,15 @@ SAMPLE_RATE = 16000
 CPU_SAMPLE_BATCH = 2
 
 
+def _ncu_traffic():
+    """dram bytes per launch of the two roofline kernels from the committed ncu --set full capture (B=32 x 246000 only)."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    if os.path.isfile(path):
+        with open(path) as fh:
+            return json.load(fh)
+    return {}
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -340,6 +349,7 @@ def main():
     value = audio_s / (ms / K / 1e3)
     e2e = audio_s / (ms_e2e / K / 1e3)
     peaks = _peaks()
+    traffic = _ncu_traffic()
     fl = flops_forward(cfg, L)
     ffn1_flops = 2.0 * B * T * cfg.hidden_size * cfg.intermediate_size
     achieved = ffn1_flops / (gemm_ffn1 * 1e-3) / 1e12 if gemm_ffn1 else None
@@ -360,7 +370,9 @@ def main():
         "model_tflops": fl["total"] * B * world / (ms / K / 1e3) / 1e12,
         "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}] + bias + GELU",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                     "frac": (achieved / peaks["bf16_tflops"]) if achieved else None, "traffic": None,
+                     "frac": (achieved / peaks["bf16_tflops"]) if achieved else None,
+                     "traffic": traffic.get("ffn1_gemm_bytes_per_launch") if (B, L) == (32, 246000) else None,
+                     "algorithmic_flops_per_launch": ffn1_flops,
                      "peak_source": peaks["source"] + " (burst cuBLAS bf16; sustained %.0f)" % peaks["bf16_tflops_sustained"]},
         "breakdown_ms": breakdown,
     }
@@ -369,7 +381,8 @@ def main():
         by = B * (4.0 * L + 2.0 * 512 * fl["frames"][0])
         gbs = by / (breakdown["conv0"] * 1e-3) / 1e9
         result["roofline_conv0"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                    "frac": gbs / peaks["hbm_gbs"], "traffic": None}
+                                    "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": by,
+                                    "traffic": traffic.get("conv0_bytes_per_launch") if (B, L) == (32, 246000) else None}
     if not args.no_cpu_baseline:
         result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args))
     print(json.dumps(result))
