@@ -160,7 +160,7 @@ def run_train(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     W, K = max(args.warmup, 3), args.steps
     B, L = args.batch, args.seq
-    cfg = Wav2Vec2Config(dropout=0.0)                       # reference defaults otherwise (SpecAugment on); no dropout RNG yet
+    cfg = Wav2Vec2Config()                                  # the reference's training defaults: dropout 0.1, SpecAugment on
     model = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision=args.precision, device=dev).init_random(seed=0)
     trainer = Stage2Trainer(model, CTCLoss(cfg, (B, L), division_factor=B * world), learning_rate=5e-5)
     x_host = torch.randn(B, L, generator=torch.Generator().manual_seed(rank)).pin_memory()
@@ -219,7 +219,8 @@ def run_train(args, rank, world, local_rank):
         "config": {"workload": f"wav2vec2-base stage-2 CTC fine-tune step (forward + CTC + backward + all-reduce + Adam), "
                                f"batch={B}/GPU, seq={L}", "global_batch": B * world, "seq_len": L,
                    "parallelism": f"dp{world} (batch sharded; one NCCL all-reduce of {trainer.flat_g.numel()} fp32 gradients per step)",
-                   "trainable_params": int(trainer.flat_w.numel()), "dropout": 0.0, "spec_augment": bool(cfg.apply_spec_augment)},
+                   "trainable_params": int(trainer.flat_w.numel()), "dropout": float(cfg.dropout),
+                   "spec_augment": bool(cfg.apply_spec_augment)},
         "clocks": clk.summary(),
         "e2e": {"value": audio_s / (ms_e2e / K / 1e3), "unit": "audio-sec/s",
                 "h2d_bytes_per_step": int(x_host.numel() * 4 + lab_host.numel() * 4), "d2h_bytes_per_step": 4},

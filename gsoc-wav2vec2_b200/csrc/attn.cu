@@ -54,6 +54,8 @@ struct AttnParams {
   const int* kv_len;   // [B] or null
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
+  DropSpec drop;       // attention-probability dropout of the training forward (encoder.py:42); thr16 == 0: off
+  int H;
 };
 
 template <int PASSES>
@@ -295,6 +297,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         unpack2(sum2[3], s6, s7);
         l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
       }
+      if (p.drop.thr16) {
+        // training: dropout on the probabilities AFTER the softmax (the row sum above is the undropped one)
+        const uint64_t rg = attn_row_group(b * p.H + h, q0 + r, p.T) + (uint64_t)(key0 >> 2);
+#pragma unroll
+        for (int pc = 0; pc < 4; ++pc) {
+#pragma unroll
+          for (int i4 = 0; i4 < 8; ++i4) {
+            const uint64_t bits = drop_bits4(p.drop.seed, p.drop.site, rg + pc * 8 + i4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float v = __uint_as_float(sr[pc][4 * i4 + e]);
+              sr[pc][4 * i4 + e] = drop_keep(bits, e, p.drop.thr16) ? __float_as_uint(v * p.drop.scale) : 0u;
+            }
+          }
+        }
+      }
       // ---- P -> smem (bf16, SW128 K-major image) once the previous PV has consumed the buffer
       mbar_wait(p_empty, par ^ 1);
 #pragma unroll
@@ -352,7 +370,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
 
 template <int PASSES>
 static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int H, const int* kv_len, void* out_hi,
-                       void* out_lo, cudaStream_t stream) {
+                       void* out_lo, DropSpec drop, cudaStream_t stream) {
   using S = AttnSmem<PASSES>;
   const int d = H * AT_DH;
   CUtensorMap tm_hi, tm_lo;
@@ -372,6 +390,8 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
   p.kv_len = kv_len;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  p.drop = drop;
+  p.H = H;
   auto kern = attn_fwd_kernel<PASSES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -385,9 +405,8 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
 
 }  // namespace w2v2
 
-extern "C" int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
-                             int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes,
-                             void* stream) {
+static int attn_fwd_impl(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
+                         const int32_t* kv_len, void* out_hi, void* out_lo, int passes, w2v2::DropSpec drop, void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(qkv_hi && out_hi, "null pointer");
   W2V2_CHECK_ARG(head_size == AT_DH, "only head_size == 64 is implemented (base: 768/12, large: 1024/16)");
@@ -395,6 +414,21 @@ extern "C" int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, 
   W2V2_CHECK_ARG(passes == 1 || (qkv_lo && out_lo), "3-pass mode needs the lo planes");
   W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (passes == 1) return launch_attn<1>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, s);
-  return launch_attn<3>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, s);
+  if (passes == 1) return launch_attn<1>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, drop, s);
+  return launch_attn<3>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, drop, s);
+}
+
+extern "C" int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
+                             int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes,
+                             void* stream) {
+  return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes,
+                       w2v2::make_drop(0.0f, 0, 0), stream);
+}
+
+extern "C" int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
+                                   int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes,
+                                   float drop_p, uint64_t seed, uint32_t site, void* stream) {
+  if (!(drop_p >= 0.0f && drop_p < 1.0f)) return w2v2::fail(-1, "%s: drop_p must be in [0, 1)", __func__);
+  return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes,
+                       w2v2::make_drop(drop_p, seed, site), stream);
 }

@@ -96,7 +96,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                    const __nv_bfloat16* __restrict__ d_o, const int* __restrict__ kv_len, int T, int H, float q_scale,
-                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ lse2_out, float* __restrict__ dsum_out) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ lse2_out, float* __restrict__ dsum_out, DropSpec dr) {
   __shared__ __align__(16) __nv_bfloat16 sQ[AB_BLK * AB_LD], sdO[AB_BLK * AB_LD], sK[AB_BLK * AB_LD], sV[AB_BLK * AB_LD];
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
   const int d = H * AB_DH;
@@ -253,7 +253,12 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         for (int e = 0; e < 2; ++e) {
           const int key = kb * AB_BLK + 8 * j + 2 * q + e;
           const float p = (key < klen) ? ex2_approx(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
-          ds[2 * r + e] = p * (dp[j][2 * r + e] - dsum[r]);
+          float dpv = dp[j][2 * r + e];
+          if (dr.thr16) {   // dP = dP_dropped o mask / (1 - p_drop)
+            const uint64_t bits = drop_bits4(dr.seed, dr.site, attn_row_group(bh, t0 + m0 + g + 8 * r, T) + (key >> 2));
+            dpv = drop_keep(bits, key & 3, dr.thr16) ? dpv * dr.scale : 0.0f;
+          }
+          ds[2 * r + e] = p * (dpv - dsum[r]);
         }
       }
       ads[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(ds[0], ds[1]);   // row g
@@ -287,7 +292,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 __global__ void __launch_bounds__(128)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o,
                     const int* __restrict__ kv_len, int T, int H, const float* __restrict__ lse2_in,
-                    const float* __restrict__ dsum_in, __nv_bfloat16* __restrict__ dqkv) {
+                    const float* __restrict__ dsum_in, __nv_bfloat16* __restrict__ dqkv, DropSpec dr) {
   __shared__ __align__(16) __nv_bfloat16 sQ[AB_BLK * AB_LD], sdO[AB_BLK * AB_LD], sK[AB_BLK * AB_LD], sV[AB_BLK * AB_LD];
   __shared__ float s_lse2[2][AB_BLK], s_ds2[2][AB_BLK];
   const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
@@ -373,8 +378,14 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           const int qi = 8 * j + 2 * q + e;
           const bool ok = key_ok[r] && (qb * AB_BLK + qi < T);
           const float pv = ok ? ex2_approx(st[j][2 * r + e] * AB_LOG2E - s_lse[qi]) : 0.0f;
-          p[2 * r + e] = pv;
-          ds[2 * r + e] = pv * (dpt[j][2 * r + e] - s_ds[qi]);
+          float keep = 1.0f;
+          if (dr.thr16) {
+            const int key = k0 + m0 + g + 8 * r;
+            const uint64_t bits = drop_bits4(dr.seed, dr.site, attn_row_group(bh, qb * AB_BLK + qi, T) + (key >> 2));
+            keep = drop_keep(bits, key & 3, dr.thr16) ? dr.scale : 0.0f;
+          }
+          p[2 * r + e] = pv * keep;                                   // dV uses the dropped probabilities
+          ds[2 * r + e] = pv * (dpt[j][2 * r + e] * keep - s_ds[qi]);
         }
       }
       ap[j >> 1][(j & 1) * 2 + 0] = pack_bf16x2(p[0], p[1]);
@@ -421,22 +432,24 @@ extern "C" int64_t w2v2_attn_bwd_workspace_bytes(int batch, int frames, int num_
 
 extern "C" int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void* dctx_hi, int batch, int frames,
                              int num_heads, int head_size, const int32_t* kv_len, float q_scale, void* workspace,
-                             void* dqkv_hi, void* stream) {
+                             void* dqkv_hi, float drop_p, uint64_t seed, uint32_t site, void* stream) {
   W2V2_CHECK_ARG(qkv_hi && ctx_hi && dctx_hi && workspace && dqkv_hi, "null pointer");
   W2V2_CHECK_ARG(head_size == AB_DH, "built for head_size 64");
   W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   float* lse2 = reinterpret_cast<float*>(workspace);
   float* dsum = lse2 + (size_t)batch * num_heads * frames;
+  W2V2_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "drop_p must be in [0, 1)");
+  const DropSpec dr = make_drop(drop_p, seed, site);
   dim3 grid((frames + AB_BLK - 1) / AB_BLK, batch * num_heads);
   attn_bwd_dq_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
                                           reinterpret_cast<const __nv_bfloat16*>(ctx_hi),
                                           reinterpret_cast<const __nv_bfloat16*>(dctx_hi), kv_len, frames, num_heads, q_scale,
-                                          reinterpret_cast<__nv_bfloat16*>(dqkv_hi), lse2, dsum);
+                                          reinterpret_cast<__nv_bfloat16*>(dqkv_hi), lse2, dsum, dr);
   W2V2_CUDA(cudaGetLastError());
   attn_bwd_dkv_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
                                            reinterpret_cast<const __nv_bfloat16*>(dctx_hi), kv_len, frames, num_heads, lse2,
-                                           dsum, reinterpret_cast<__nv_bfloat16*>(dqkv_hi));
+                                           dsum, reinterpret_cast<__nv_bfloat16*>(dqkv_hi), dr);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }

@@ -122,11 +122,18 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 template <bool FAST>
 __global__ void __launch_bounds__(256)
 gelu_rows_kernel(const float* __restrict__ pre, size_t n4, __nv_bfloat16* __restrict__ out_hi,
-                 __nv_bfloat16* __restrict__ out_lo) {
+                 __nv_bfloat16* __restrict__ out_lo, DropSpec dr) {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 v = __ldg(reinterpret_cast<const float4*>(pre) + i);
     gelu_x2<FAST>(v.x, v.y);
     gelu_x2<FAST>(v.z, v.w);
+    if (dr.thr16) {   // encoder.py:128: dropout on the activated intermediate
+      const uint64_t bits = drop_bits4(dr.seed, dr.site, i);
+      v.x = drop_keep(bits, 0, dr.thr16) ? v.x * dr.scale : 0.0f;
+      v.y = drop_keep(bits, 1, dr.thr16) ? v.y * dr.scale : 0.0f;
+      v.z = drop_keep(bits, 2, dr.thr16) ? v.z * dr.scale : 0.0f;
+      v.w = drop_keep(bits, 3, dr.thr16) ? v.w * dr.scale : 0.0f;
+    }
     uint32_t l0, l1;
     const uint32_t h0 = split_bf16x2(v.x, v.y, l0), h1 = split_bf16x2(v.z, v.w, l1);
     reinterpret_cast<uint2*>(out_hi)[i] = make_uint2(h0, h1);
@@ -144,7 +151,7 @@ __device__ __forceinline__ float gelu_grad(float x) {
 // thread = 4 consecutive columns, walks the rows of its chunk (blockIdx.y); dy bf16, pre fp32 (or null), out bf16 (or null)
 __global__ void __launch_bounds__(256)
 dact_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ pre, int rows, int cols,
-                   __nv_bfloat16* __restrict__ out_hi, float* __restrict__ colsum) {
+                   __nv_bfloat16* __restrict__ out_hi, float* __restrict__ colsum, DropSpec dr) {
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
   if (c >= cols) return;
   const int per = (rows + gridDim.y - 1) / gridDim.y;
@@ -154,6 +161,13 @@ dact_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     const size_t off = (size_t)r * cols + c;
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dy + off));
     float4 g = make_float4(bf16_lo_to_f32(raw.x), bf16_hi_to_f32(raw.x), bf16_lo_to_f32(raw.y), bf16_hi_to_f32(raw.y));
+    if (dr.thr16) {   // gradient of a dropout that sat AFTER the activation (or after a Dense when pre == null)
+      const uint64_t bits = drop_bits4(dr.seed, dr.site, off >> 2);
+      g.x = drop_keep(bits, 0, dr.thr16) ? g.x * dr.scale : 0.0f;
+      g.y = drop_keep(bits, 1, dr.thr16) ? g.y * dr.scale : 0.0f;
+      g.z = drop_keep(bits, 2, dr.thr16) ? g.z * dr.scale : 0.0f;
+      g.w = drop_keep(bits, 3, dr.thr16) ? g.w * dr.scale : 0.0f;
+    }
     if (pre != nullptr) {
       const float4 p = __ldg(reinterpret_cast<const float4*>(pre + off));
       g.x *= gelu_grad(p.x); g.y *= gelu_grad(p.y); g.z *= gelu_grad(p.z); g.w *= gelu_grad(p.w);
@@ -169,6 +183,44 @@ dact_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
   if (colsum != nullptr) {
     atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
     atomicAdd(colsum + c + 2, acc.z); atomicAdd(colsum + c + 3, acc.w);
+  }
+}
+
+// ------------------------------------------------------------------------------------ dropout (forward and backward)
+// out = (resid ? resid : 0) + keep(x) * x / (1 - p)  on fp32, optional bf16 hi copy; in place (out == x) is allowed.
+// Used for tf.keras.layers.Dropout at feature_extractor.py:95, encoder.py:118,270, modeling.py:253 and for their gradients.
+__global__ void __launch_bounds__(256)
+dropout_rows_kernel(const float* __restrict__ x, const float* __restrict__ resid, size_t n4, float* __restrict__ out_f32,
+                    __nv_bfloat16* __restrict__ out_hi, DropSpec dr) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    const uint64_t bits = drop_bits4(dr.seed, dr.site, i);
+    v.x = drop_keep(bits, 0, dr.thr16) ? v.x * dr.scale : 0.0f;
+    v.y = drop_keep(bits, 1, dr.thr16) ? v.y * dr.scale : 0.0f;
+    v.z = drop_keep(bits, 2, dr.thr16) ? v.z * dr.scale : 0.0f;
+    v.w = drop_keep(bits, 3, dr.thr16) ? v.w * dr.scale : 0.0f;
+    if (resid != nullptr) {
+      const float4 r = reinterpret_cast<const float4*>(resid)[i];
+      v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+    }
+    if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32)[i] = v;
+    if (out_hi != nullptr) reinterpret_cast<uint2*>(out_hi)[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+// the keep mask itself (1 = kept), for tests: elementwise sites use index = flat element index
+__global__ void dropout_mask_kernel(size_t n, uint8_t* __restrict__ out, DropSpec dr) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = drop_keep(drop_bits4(dr.seed, dr.site, i >> 2), (int)(i & 3), dr.thr16) ? 1 : 0;
+}
+
+// keep mask of the attention-probability dropout, out[bh][q][k]
+__global__ void attn_dropout_mask_kernel(int BH, int T, uint8_t* __restrict__ out, DropSpec dr) {
+  const size_t n = (size_t)BH * T * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % T);
+    const size_t row = i / T;
+    const int q = (int)(row % T), bh = (int)(row / T);
+    out[i] = drop_keep(drop_bits4(dr.seed, dr.site, attn_row_group(bh, q, T) + (k >> 2)), k & 3, dr.thr16) ? 1 : 0;
   }
 }
 
@@ -246,7 +298,8 @@ extern "C" int w2v2_ln_bwd(const float* x, const float* gamma, const float* dy, 
   return 0;
 }
 
-extern "C" int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_hi, void* out_lo, void* stream) {
+extern "C" int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_hi, void* out_lo, float drop_p,
+                              uint64_t seed, uint32_t site, void* stream) {
   W2V2_CHECK_ARG(pre && out_hi, "null pointer");
   W2V2_CHECK_ARG(n % 4 == 0, "element count must be a multiple of 4");
   if (n <= 0) return 0;
@@ -256,14 +309,15 @@ extern "C" int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_h
   if (grid > 148 * 16) grid = 148 * 16;
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  if (fast) gelu_rows_kernel<true><<<grid, 256, 0, s>>>(pre, n4, hi, lo);
-  else gelu_rows_kernel<false><<<grid, 256, 0, s>>>(pre, n4, hi, lo);
+  const DropSpec dr = make_drop(drop_p, seed, site);
+  if (fast) gelu_rows_kernel<true><<<grid, 256, 0, s>>>(pre, n4, hi, lo, dr);
+  else gelu_rows_kernel<false><<<grid, 256, 0, s>>>(pre, n4, hi, lo, dr);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t rows, int cols, void* out_hi, float* colsum,
-                                void* stream) {
+                                float drop_p, uint64_t seed, uint32_t site, void* stream) {
   W2V2_CHECK_ARG(dy_hi && (out_hi || colsum), "null pointer");
   W2V2_CHECK_ARG(cols > 0 && cols % 4 == 0, "cols must be a multiple of 4");
   if (rows <= 0) return 0;
@@ -272,7 +326,7 @@ extern "C" int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t row
   int gy = (int)((rows + 15) / 16);   // short dependent-load chains: many row chunks, 4 atomics per thread at the end
   if (gy > 1024) gy = 1024;
   dact_colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy_hi), pre, (int)rows, cols,
-                                                  reinterpret_cast<__nv_bfloat16*>(out_hi), colsum);
+                                                  reinterpret_cast<__nv_bfloat16*>(out_hi), colsum, make_drop(drop_p, seed, site));
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }
@@ -296,6 +350,42 @@ extern "C" int w2v2_lm_head_dgrad(const float* grad_logits, const float* kernel,
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   lm_head_dgrad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(grad_logits, kernel, (int)rows, hidden_size, vocab, out);
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int w2v2_dropout_rows(const float* x, const float* resid, int64_t n, float drop_p, uint64_t seed, uint32_t site,
+                                 float* out_f32, void* out_hi, void* stream) {
+  W2V2_CHECK_ARG(x && (out_f32 || out_hi), "null pointer");
+  W2V2_CHECK_ARG(n % 4 == 0, "element count must be a multiple of 4");
+  W2V2_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "drop_p must be in [0, 1)");
+  if (n <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const size_t n4 = (size_t)n / 4;
+  int grid = (int)((n4 + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  dropout_rows_kernel<<<grid, 256, 0, s>>>(x, resid, n4, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                           make_drop(drop_p, seed, site));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int w2v2_attn_dropout_mask(int batch_heads, int frames, float drop_p, uint64_t seed, uint32_t site, uint8_t* out,
+                                      void* stream) {
+  W2V2_CHECK_ARG(out != nullptr && batch_heads > 0 && frames > 0, "bad arguments");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  attn_dropout_mask_kernel<<<148 * 8, 256, 0, s>>>(batch_heads, frames, out, make_drop(drop_p, seed, site));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int w2v2_dropout_mask(int64_t n, float drop_p, uint64_t seed, uint32_t site, uint8_t* out, void* stream) {
+  W2V2_CHECK_ARG(out != nullptr, "null pointer");
+  if (n <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  dropout_mask_kernel<<<grid, 256, 0, s>>>((size_t)n, out, make_drop(drop_p, seed, site));
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }

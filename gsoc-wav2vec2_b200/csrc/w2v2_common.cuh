@@ -381,6 +381,40 @@ __device__ __forceinline__ void gelu_x2(float& x0, float& x1) {
   }
 }
 
+// --------------------------------------------------------------------------- dropout RNG
+// Counter-based: 64 random bits per group of FOUR consecutive elements = splitmix64(seed, site, element_index / 4); element e
+// of the group is KEPT when its 16-bit lane >= thr16 (thr16 = round(p * 65536)).  Stateless, so the backward pass (and the
+// test oracle, through w2v2_dropout_mask) regenerates exactly the mask of the forward pass.
+__device__ __forceinline__ uint64_t drop_bits4(uint64_t seed, uint32_t site, uint64_t group) {
+  uint64_t z = seed + (group + ((uint64_t)site << 48)) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ bool drop_keep(uint64_t bits, int e, uint32_t thr16) {
+  return ((uint32_t)(bits >> (16 * e)) & 0xFFFFu) >= thr16;
+}
+struct DropSpec {       // thr16 == 0: dropout off
+  uint64_t seed;
+  uint32_t site;
+  uint32_t thr16;
+  float scale;          // 1 / (1 - p)
+};
+inline DropSpec make_drop(float p, uint64_t seed, uint32_t site) {
+  DropSpec d;
+  d.seed = seed;
+  d.site = site;
+  d.thr16 = (p > 0.0f) ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
+  if (d.thr16 > 65535u) d.thr16 = 65535u;
+  d.scale = (d.thr16 > 0u) ? 65536.0f / (65536.0f - (float)d.thr16) : 1.0f;
+  return d;
+}
+// attention-probability dropout (encoder.py:42): the group index of key k of query row (bh, q) is row_group + (k >> 2),
+// row_group = (bh * T + q) * ceil(T / 4); the lane is k & 3.
+__device__ __forceinline__ uint64_t attn_row_group(int bh, int q, int T) {
+  return ((uint64_t)bh * T + q) * (uint64_t)((T + 3) >> 2);
+}
+
 // ---- bf16 packing and hi/lo splitting (x ~= hi + lo, both bf16: ~16 mantissa bits) ----
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -43,6 +43,7 @@ class PosconvArgs(C.Structure):
 
 
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_U64, _U32 = C.c_uint64, C.c_uint32
 
 # name -> argtypes (restype is int unless listed in _RESTYPES).  Kept in one table so the
 # "library exports every declared symbol" test can walk it.
@@ -66,12 +67,16 @@ SIGNATURES = {
     "w2v2_lm_head_wgrad": [_P, _P, _L, _I, _I, _P, _P, _P],
     "w2v2_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
     "w2v2_ln_bwd": [_P, _P, _P, _F, _L, _I, _P, _P, _P, _P, _P, _P],
-    "w2v2_gelu_rows": [_P, _L, _I, _P, _P, _P],
-    "w2v2_dact_colsum": [_P, _P, _L, _I, _P, _P, _P],
+    "w2v2_gelu_rows": [_P, _L, _I, _P, _P, _F, _U64, _U32, _P],
+    "w2v2_dact_colsum": [_P, _P, _L, _I, _P, _P, _F, _U64, _U32, _P],
     "w2v2_transpose_bf16": [_P, _L, _I, _P, _L, _P],
     "w2v2_lm_head_dgrad": [_P, _P, _L, _I, _I, _P, _P],
     "w2v2_attn_bwd_workspace_bytes": [_I, _I, _I],
-    "w2v2_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _P],
+    "w2v2_attn_bwd": [_P, _P, _P, _I, _I, _I, _I, _P, _F, _P, _P, _F, _U64, _U32, _P],
+    "w2v2_dropout_rows": [_P, _P, _L, _F, _U64, _U32, _P, _P, _P],
+    "w2v2_dropout_mask": [_L, _F, _U64, _U32, _P, _P],
+    "w2v2_attn_dropout_mask": [_I, _I, _F, _U64, _U32, _P, _P],
+    "w2v2_attn_fwd_train": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _F, _U64, _U32, _P],
     "w2v2_posconv_wgrad": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
 }
 _RESTYPES = {"w2v2_last_error_string": C.c_char_p, "w2v2_ctc_workspace_bytes": C.c_int64,

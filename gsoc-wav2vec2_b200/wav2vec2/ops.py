@@ -196,16 +196,46 @@ def ln_bwd(x, gamma, dy, eps, rows, d, dx_f32=None, dx_hi=None, dgamma=None, dbe
                                        _ptr(dgamma), _ptr(dbeta), _ptr(colsum), _stream()), "w2v2_ln_bwd")
 
 
-def gelu_rows(pre, out_hi, fast, out_lo=None):
+NO_DROP = (0.0, 0, 0)   # (rate, seed, site): dropout off
+
+
+def gelu_rows(pre, out_hi, fast, out_lo=None, drop=NO_DROP):
     _need_cuda(pre, out_hi, out_lo)
     _count(); _lib.check(_lib.load().w2v2_gelu_rows(_ptr(pre), pre.numel(), 1 if fast else 0, _ptr(out_hi), _ptr(out_lo),
-                                          _stream()), "w2v2_gelu_rows")
+                                          float(drop[0]), int(drop[1]), int(drop[2]), _stream()), "w2v2_gelu_rows")
 
 
-def dact_colsum(dy_hi, pre, rows, cols, out_hi=None, colsum=None):
+def dact_colsum(dy_hi, pre, rows, cols, out_hi=None, colsum=None, drop=NO_DROP):
     _need_cuda(dy_hi, pre, out_hi, colsum)
-    _count(); _lib.check(_lib.load().w2v2_dact_colsum(_ptr(dy_hi), _ptr(pre), rows, cols, _ptr(out_hi), _ptr(colsum), _stream()),
-                         "w2v2_dact_colsum")
+    _count(); _lib.check(_lib.load().w2v2_dact_colsum(_ptr(dy_hi), _ptr(pre), rows, cols, _ptr(out_hi), _ptr(colsum),
+                                            float(drop[0]), int(drop[1]), int(drop[2]), _stream()), "w2v2_dact_colsum")
+
+
+def dropout_rows(x, drop, resid=None, out_f32=None, out_hi=None):
+    """out = (resid or 0) + dropout(x); fp32 (in place allowed) and / or a bf16 copy."""
+    _need_cuda(x, resid, out_f32, out_hi)
+    _count(); _lib.check(_lib.load().w2v2_dropout_rows(_ptr(x), _ptr(resid), x.numel(), float(drop[0]), int(drop[1]), int(drop[2]),
+                                             _ptr(out_f32), _ptr(out_hi), _stream()), "w2v2_dropout_rows")
+
+
+def dropout_mask(n, drop, device):
+    out = torch.empty(n, dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().w2v2_dropout_mask(n, float(drop[0]), int(drop[1]), int(drop[2]), _ptr(out), _stream()), "w2v2_dropout_mask")
+    return out
+
+
+def attn_dropout_mask(BH, T, drop, device):
+    out = torch.empty((BH, T, T), dtype=torch.uint8, device=device)
+    _lib.check(_lib.load().w2v2_attn_dropout_mask(BH, T, float(drop[0]), int(drop[1]), int(drop[2]), _ptr(out), _stream()),
+               "w2v2_attn_dropout_mask")
+    return out
+
+
+def attn_fwd_train(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes, drop):
+    _need_cuda(qkv.hi, out.hi, kv_len)
+    _count(); _lib.check(_lib.load().w2v2_attn_fwd_train(_ptr(qkv.hi), _ptr(qkv.lo) if passes == 3 else None, B, T, H, dh,
+                                               _ptr(kv_len), _ptr(out.hi), _ptr(out.lo) if passes == 3 else None, passes,
+                                               float(drop[0]), int(drop[1]), int(drop[2]), _stream()), "w2v2_attn_fwd_train")
 
 
 def transpose_bf16(x, rows, cols, out, out_ld):
@@ -221,14 +251,15 @@ def lm_head_dgrad(grad_logits, kernel, out):
                          "w2v2_lm_head_dgrad")
 
 
-def attn_bwd(qkv_hi, ctx_hi, dctx_hi, B, T, H, dh, kv_len, q_scale, dqkv_hi, workspace=None):
+def attn_bwd(qkv_hi, ctx_hi, dctx_hi, B, T, H, dh, kv_len, q_scale, dqkv_hi, workspace=None, drop=NO_DROP):
     _need_cuda(qkv_hi, ctx_hi, dctx_hi, dqkv_hi, kv_len)
     lib = _lib.load()
     need = lib.w2v2_attn_bwd_workspace_bytes(B, T, H)
     if workspace is None or workspace.numel() * workspace.element_size() < need:
         workspace = torch.empty(need // 4, dtype=torch.float32, device=qkv_hi.device)
     _count(2); _lib.check(lib.w2v2_attn_bwd(_ptr(qkv_hi), _ptr(ctx_hi), _ptr(dctx_hi), B, T, H, dh, _ptr(kv_len), float(q_scale),
-                                  _ptr(workspace), _ptr(dqkv_hi), _stream()), "w2v2_attn_bwd")
+                                  _ptr(workspace), _ptr(dqkv_hi), float(drop[0]), int(drop[1]), int(drop[2]), _stream()),
+                          "w2v2_attn_bwd")
     return workspace
 
 

@@ -89,19 +89,41 @@ class Stage2Trainer:
     over the flat fp32 gradient buffer and ONE ``w2v2_adam`` launch.  Parameter-sized algebra (weight-norm chain rule,
     bf16 casts of the updated kernels) is host-side torch on the parameter tensors.
 
+    Dropout (config.py:9, rate 0.1 by default) is applied at the reference's six sites - after the feature projection, on
+    the attention probabilities (inside the attention kernel), after the attention output projection, on the GELU
+    intermediate, after the encoder LayerNorm and before ``lm_head`` - with masks from a stateless counter-based generator
+    (``include/w2v2.h``), so the backward pass regenerates them instead of storing them.
     Limits: post-norm encoder with the group-norm extractor (the base architecture of BASELINE config 3), no attention
-    mask, ``dropout == 0`` (no dropout RNG yet); SpecAugment masks (host RNG like the reference) are supported.
+    mask, ``survival_prob == 1``; SpecAugment masks (host RNG like the reference) are supported.
     Backward products run single-pass bf16 with fp32 accumulation; LayerNorm / softmax / GELU derivatives in fp32.
     """
 
+    # dropout sites (tf.keras.layers.Dropout in the reference): id of the counter-based mask stream
+    SITE_PROJ, SITE_ENC, SITE_HEAD = 1, 2, 3                    # feature_extractor.py:95, encoder.py:270, modeling.py:253
+
+    @staticmethod
+    def site_attn_probs(i):                                      # encoder.py:41-43
+        return 16 + 4 * i
+
+    @staticmethod
+    def site_attn_out(i):                                        # encoder.py:118
+        return 17 + 4 * i
+
+    @staticmethod
+    def site_ffn_mid(i):                                         # encoder.py:128
+        return 18 + 4 * i
+
+    def _drop(self, site):
+        """(rate, seed, site) of this step's mask stream; rate 0 = off."""
+        return (float(self.model.config.dropout), self.seed + 0x9E3779B1 * (self.t + 1), site)
+
     def __init__(self, model: Wav2Vec2ForCTC, loss_fn: CTCLoss, learning_rate=5e-5, beta_1=0.9, beta_2=0.999,
-                 epsilon=1e-7):
+                 epsilon=1e-7, seed=0):
         cfg = model.config
         if cfg.attention_norm_type != "postnorm" or cfg.feature_extractor_norm_type != "group":
             raise NotImplementedError("Stage2Trainer covers the base architecture (group-norm extractor, post-norm encoder)")
-        if cfg.dropout:
-            raise NotImplementedError("dropout RNG is not built yet; use dropout=0")
         self.model, self.loss_fn = model, loss_fn
+        self.seed = int(seed)
         self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
         self.t = 0
         model.freeze_feature_extractor()                               # main.py:236-237
@@ -166,6 +188,17 @@ class Stage2Trainer:
         h = A.pair("h", (M, d), lo)
         ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"], out_f32=h_f32,
                  out_hi=h.hi, out_lo=h.lo, passes=passes)
+        p_drop = float(cfg.dropout)
+        S["dropout"] = p_drop
+
+        def resplit(t_f32, pair):
+            sp = ops.split_bf16(t_f32, lo)
+            pair.hi.copy_(sp.hi)
+            if lo:
+                pair.lo.copy_(sp.lo)
+        if p_drop:                                          # feature_extractor.py:95
+            ops.dropout_rows(h_f32, self._drop(self.SITE_PROJ), out_f32=h_f32)
+            resplit(h_f32, h)
         S["spec_mask"] = None
         if cfg.apply_spec_augment:                         # modeling.py:193-199 (host RNG like the reference's numpy RNG)
             if spec_mask is None:
@@ -174,10 +207,7 @@ class Stage2Trainer:
             mask = torch.as_tensor(spec_mask).to(model.device).bool()
             hv = torch.where(mask[:, :, None], v["wav2vec2/masked_spec_embed"], h_f32.view(B, T, d))
             h_f32.copy_(hv.reshape(M, d))
-            sp = ops.split_bf16(h_f32, lo)
-            h.hi.copy_(sp.hi)
-            if lo:
-                h.lo.copy_(sp.lo)
+            resplit(h_f32, h)
             S["spec_mask"] = mask.reshape(M)
         S["pn"], S["h"] = pn, h
         enc = "wav2vec2/encoder/"
@@ -191,6 +221,10 @@ class Stage2Trainer:
         xs = A.pair("t.xs.0", (M, d), lo)
         ops.ln_rows(y0, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=xs_f32, out_hi=xs.hi,
                     out_lo=xs.lo)
+        if p_drop:                                          # encoder.py:270
+            ops.dropout_rows(xs_f32, self._drop(self.SITE_ENC), out_f32=xs_f32)
+            resplit(xs_f32, xs)
+        tmp = A.get("t.tmp", (M, d), f32) if p_drop else None
         L = []
         for i in range(cfg.num_layers):
             lb = f"{enc}layers/{i}/"
@@ -198,10 +232,16 @@ class Stage2Trainer:
             ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi, out_lo=qkv.lo,
                      passes=passes)
             ctx = A.pair(f"t.ctx.{i}", (M, d), lo)
-            ops.attn_fwd(qkv, B, T, H, dh, None, ctx, passes)
             y1 = A.get(f"t.y1.{i}", (M, d), f32)
-            ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
-                     residual=xs_f32, out_f32=y1, passes=passes)
+            if p_drop:
+                ops.attn_fwd_train(qkv, B, T, H, dh, None, ctx, passes, self._drop(self.site_attn_probs(i)))
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
+                         out_f32=tmp, passes=passes)
+                ops.dropout_rows(tmp, self._drop(self.site_attn_out(i)), resid=xs_f32, out_f32=y1)     # encoder.py:118-119
+            else:
+                ops.attn_fwd(qkv, B, T, H, dh, None, ctx, passes)
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
+                         residual=xs_f32, out_f32=y1, passes=passes)
             x1 = A.pair(f"t.x1.{i}", (M, d), lo)
             ops.ln_rows(y1, v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"], eps, M, d, out_f32=x1_f32, out_hi=x1.hi,
                         out_lo=x1.lo)
@@ -209,7 +249,8 @@ class Stage2Trainer:
             ops.gemm(x1, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
                      out_f32=pre, passes=passes)
             mid = A.pair(f"t.mid.{i}", (M, ffn), lo)
-            ops.gelu_rows(pre, mid.hi, fast=(passes == 1), out_lo=mid.lo)
+            ops.gelu_rows(pre, mid.hi, fast=(passes == 1), out_lo=mid.lo,
+                          drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
             y2 = A.get(f"t.y2.{i}", (M, d), f32)
             ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=v[lb + "feed_forward/output_dense/bias"],
                      residual=x1_f32, out_f32=y2, passes=passes)
@@ -220,8 +261,14 @@ class Stage2Trainer:
             xs = nxt
         V = cfg.vocab_size
         logits = A.get("t.logits", (B, T, V), f32)
+        hidden_f32 = xs_f32
+        if p_drop:                                          # modeling.py:253
+            hidden_f32 = A.get("t.hidden.drop", (M, d), f32)
+            ops.dropout_rows(xs_f32, self._drop(self.SITE_HEAD), out_f32=hidden_f32)
+            xs = A.pair("t.hidden.drop.op", (M, d), lo)
+            resplit(hidden_f32, xs)
         ops.gemm(xs, P["lm.w"], K=d, N=V, rows_per_batch=M, bias=v["lm_head/bias"], out_f32=logits, passes=passes, block_n=32)
-        S["layers"], S["hidden_f32"] = L, xs_f32
+        S["layers"], S["hidden_f32"] = L, hidden_f32
         self.saved = S
         return logits
 
@@ -247,6 +294,9 @@ class Stage2Trainer:
         ops.lm_head_wgrad(S["hidden_f32"], dlogits.view(M, V), G["lm_head/kernel"], G["lm_head/bias"])
         g = A.get("b.g", (M, d), f32)
         ops.lm_head_dgrad(dlogits, v["lm_head/kernel"], g)
+        p_drop = S["dropout"]
+        if p_drop:
+            ops.dropout_rows(g, self._drop(self.SITE_HEAD), out_f32=g)
         dy, dyh = A.get("b.dy", (M, d), f32), A.get("b.dyh", (M, d), bf)
         g1 = A.get("b.g1", (M, d), f32)
         dmid, dpre = A.get("b.dmid", (M, ffn), bf), A.get("b.dpre", (M, ffn), bf)
@@ -268,18 +318,26 @@ class Stage2Trainer:
             ops.transpose_bf16(dyh, M, d, dyT, Mp)
             self._wgrad(Li["mid"].hi, dyT, M, Mp, ffn, G[ff + "output_dense/kernel"])
             # mid = gelu(pre),  pre = x1 W1 + b1
-            ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"])
+            ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"],
+                            drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
             ops.gemm(Pair(dpre), W[f"l{i}.ff1"], K=ffn, N=d, rows_per_batch=M, residual=dy, out_f32=g1)
             ops.transpose_bf16(dpre, M, ffn, dffT, Mp)
             self._wgrad(Li["x1"].hi, dffT, M, Mp, d, G[ff + "intermediate_dense/kernel"])
             # x1 = LN1(y1),  y1 = x + ctx Wo + bo
-            ops.ln_bwd(Li["y1"], v[lb + "layer_norm/gamma"], g1, eps, M, d, dx_f32=dy, dx_hi=dyh,
-                       dgamma=G[lb + "layer_norm/gamma"], dbeta=G[lb + "layer_norm/beta"], colsum=G[at + "out_proj/bias"])
+            if p_drop:
+                # the attention branch sees the gradient through its dropout mask, the residual branch sees all of it
+                ops.ln_bwd(Li["y1"], v[lb + "layer_norm/gamma"], g1, eps, M, d, dx_f32=dy, dx_hi=dyh,
+                           dgamma=G[lb + "layer_norm/gamma"], dbeta=G[lb + "layer_norm/beta"])
+                ops.dact_colsum(dyh, None, M, d, out_hi=dyh, colsum=G[at + "out_proj/bias"], drop=self._drop(self.site_attn_out(i)))
+            else:
+                ops.ln_bwd(Li["y1"], v[lb + "layer_norm/gamma"], g1, eps, M, d, dx_f32=dy, dx_hi=dyh,
+                           dgamma=G[lb + "layer_norm/gamma"], dbeta=G[lb + "layer_norm/beta"], colsum=G[at + "out_proj/bias"])
             ops.gemm(Pair(dyh), W[f"l{i}.out"], K=d, N=d, rows_per_batch=M, out_hi=dctx)
             ops.transpose_bf16(dyh, M, d, dyT, Mp)
             self._wgrad(Li["ctx"].hi, dyT, M, Mp, d, G[at + "out_proj/kernel"])
             # ctx = softmax(q k^T) v  (q carries dh^-1/2: encoder.py:28 folded into the packed q projection)
-            ops.attn_bwd(Li["qkv"].hi, Li["ctx"].hi, dctx, B, T, H, dh, None, dh ** -0.5, dqkv, workspace=ws)
+            ops.attn_bwd(Li["qkv"].hi, Li["ctx"].hi, dctx, B, T, H, dh, None, dh ** -0.5, dqkv, workspace=ws,
+                         drop=self._drop(self.site_attn_probs(i)) if p_drop else ops.NO_DROP)
             qkv_bias.zero_()
             ops.dact_colsum(dqkv, None, M, 3 * d, colsum=qkv_bias)
             for j, n in enumerate(("q", "k", "v")):
@@ -291,7 +349,9 @@ class Stage2Trainer:
             for j, n in enumerate(("q", "k", "v")):
                 ops.gemm(Pair(xt), Pair(dqkvT[j * d:(j + 1) * d]), K=Mp, N=d, rows_per_batch=d, out_f32=G[at + f"{n}_proj/kernel"],
                          **self.wgrad_tiles)
-        # x_0 = LN_enc(y0),  y0 = h + gelu(pos_pre),  pos_pre = conv(h) + b
+        # x_0 = dropout(LN_enc(y0)),  y0 = h + gelu(pos_pre),  pos_pre = conv(h) + b
+        if p_drop:
+            ops.dropout_rows(g, self._drop(self.SITE_ENC), out_f32=g)
         ops.ln_bwd(S["y0"], v[enc + "layer_norm/gamma"], g, eps, M, d, dx_f32=dy, dx_hi=dyh,
                    dgamma=G[enc + "layer_norm/gamma"], dbeta=G[enc + "layer_norm/beta"])
         pc = enc + "pos_conv_embed/conv/"
@@ -312,8 +372,10 @@ class Stage2Trainer:
             msk = S["spec_mask"]
             G["wav2vec2/masked_spec_embed"].copy_((dh_f32 * msk[:, None]).sum(0))
             dh_f32.mul_((~msk)[:, None])
-        # h = pn Wp + bp,  pn = LN_fp(extractor output)
+        # h = dropout(pn Wp + bp),  pn = LN_fp(extractor output)
         fp = "wav2vec2/feature_projection/"
+        if p_drop:
+            ops.dropout_rows(dh_f32, self._drop(self.SITE_PROJ), out_f32=dh_f32)
         dhh = ops.split_bf16(dh_f32, False).hi
         ops.dact_colsum(dhh, None, M, d, colsum=G[fp + "projection/bias"])
         ops.transpose_bf16(dhh, M, d, dyT, Mp)

@@ -197,10 +197,13 @@ int w2v2_ln_bwd(const float* x, const float* gamma, const float* dy, float eps, 
                 void* dx_hi, float* dgamma, float* dbeta, float* colsum /*or NULL*/, void* stream);
 /* GELU of a saved fp32 pre-activation -> bf16 (training forward keeps the pre-activation for the backward).
  * fast != 0: the tanh-form of the single-pass mode (same values as the GEMM epilogue of inference). */
-int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_hi, void* out_lo /*or NULL*/, void* stream);
+int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_hi, void* out_lo /*or NULL*/, float drop_p, uint64_t seed,
+                   uint32_t site, void* stream);   /* drop_p > 0: dropout on the activated values (encoder.py:128) */
 /* out = dy * gelu'(pre) (exact erf form, config.py:14) as bf16, colsum += column sums of the ROUNDED result (bias
  * gradient).  pre == NULL: no activation (plain column sums of dy, out may be NULL). */
-int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t rows, int cols, void* out_hi, float* colsum, void* stream);
+int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t rows, int cols, void* out_hi, float* colsum, float drop_p,
+                     uint64_t seed, uint32_t site, void* stream);   /* drop_p > 0: dy is first masked / rescaled (gradient of a dropout
+                                                                       that followed the activation, or a Dense when pre == NULL) */
 /* out[n][m] = in[m][n] (bf16), rows m in [rows, out_ld) are written as zeros (K padding of the wgrad GEMMs). */
 int w2v2_transpose_bf16(const void* in, int64_t rows, int cols, void* out, int64_t out_ld, void* stream);
 /* dHidden[rows][hidden] = dLogits[rows][vocab] . kernel[hidden][vocab]^T (backward of the Dense at modeling.py:231,254), fp32. */
@@ -212,7 +215,23 @@ int w2v2_lm_head_dgrad(const float* grad_logits, const float* kernel, int64_t ro
  * workspace: w2v2_attn_bwd_workspace_bytes(batch, frames, num_heads). */
 int64_t w2v2_attn_bwd_workspace_bytes(int batch, int frames, int num_heads);
 int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void* dctx_hi, int batch, int frames, int num_heads,
-                  int head_size, const int32_t* kv_len, float q_scale, void* workspace, void* dqkv_hi, void* stream);
+                  int head_size, const int32_t* kv_len, float q_scale, void* workspace, void* dqkv_hi, float drop_p,
+                  uint64_t seed, uint32_t site, void* stream);   /* drop_p, seed, site: those of w2v2_attn_fwd_train */
+/* Dropout (tf.keras.layers.Dropout at feature_extractor.py:95, encoder.py:42,118,128,270, modeling.py:253; rate config.py:9).
+ * Masks come from a stateless counter-based generator: 64 bits per group of 4 consecutive elements =
+ * splitmix64(seed, site, index / 4), element kept when its 16-bit lane >= round(p * 65536), kept values scaled by 1 / (1 - p).
+ * The backward pass regenerates the mask from (seed, site); w2v2_dropout_mask / w2v2_attn_dropout_mask export it (tests).
+ *   w2v2_dropout_rows : out = (resid ? resid : 0) + dropout(x)  (fp32, optional bf16 copy; in place allowed)
+ *   w2v2_attn_fwd_train : w2v2_attn_fwd with dropout on the attention probabilities (after the softmax, encoder.py:41-43) */
+int w2v2_dropout_rows(const float* x, const float* resid /*or NULL*/, int64_t n, float drop_p, uint64_t seed, uint32_t site,
+                      float* out_f32, void* out_hi, void* stream);
+int w2v2_dropout_mask(int64_t n, float drop_p, uint64_t seed, uint32_t site, uint8_t* out, void* stream);
+int w2v2_attn_dropout_mask(int batch_heads, int frames, float drop_p, uint64_t seed, uint32_t site, uint8_t* out /*[bh][q][k]*/,
+                           void* stream);
+int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
+                        const int32_t* kv_len, void* out_hi, void* out_lo, int passes, float drop_p, uint64_t seed,
+                        uint32_t site, void* stream);
+
 /* Weight gradient of the positional convolution in the TF kernel layout [ktaps][hidden/groups][hidden]
  * (w.r.t. the weight-NORMALISED kernel; the weight-norm chain rule is parameter-sized host algebra). */
 int w2v2_posconv_wgrad(const void* x_hi, const void* dpre_hi, int batch, int frames, int hidden, int groups, int ktaps,

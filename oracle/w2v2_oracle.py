@@ -98,11 +98,19 @@ def feature_extractor_layer(x, p: Params, cfg, i: int, prefix="wav2vec2/"):
     return gelu_erf(y)
 
 
-def feature_projection(x, p: Params, cfg, prefix="wav2vec2/"):
-    """LN(512) -> Dense (feature_extractor.py:92-95); dropout is identity at eval."""
+def _drop(x, drop, key):
+    """tf.keras.layers.Dropout in training mode with an EXPLICIT mask: ``drop[key]`` holds keep / (1 - rate) per element
+    (0 where dropped).  ``drop is None`` (or a missing key) = eval mode / rate 0: identity."""
+    if drop is None or key not in drop:
+        return x
+    return x * drop[key].to(x.dtype)
+
+
+def feature_projection(x, p: Params, cfg, prefix="wav2vec2/", drop=None):
+    """LN(512) -> Dense -> dropout (feature_extractor.py:92-95)."""
     base = f"{prefix}feature_projection/"
     y = layer_norm(x, p[base + "layer_norm/gamma"], p[base + "layer_norm/beta"], cfg.layer_norm_eps)
-    return dense(y, p[base + "projection/kernel"], p[base + "projection/bias"])
+    return _drop(dense(y, p[base + "projection/kernel"], p[base + "projection/bias"]), drop, "proj")
 
 
 def positional_conv_embedding(x, p: Params, cfg, prefix="wav2vec2/"):
@@ -118,7 +126,7 @@ def positional_conv_embedding(x, p: Params, cfg, prefix="wav2vec2/"):
     return gelu_erf(y)
 
 
-def attention(x, p: Params, cfg, base: str, additive_mask=None):
+def attention(x, p: Params, cfg, base: str, additive_mask=None, drop=None, layer=0):
     """encoder.py:22-54: q/k/v Dense, q scaled AFTER bias, softmax(QK^T + mask) V, out_proj."""
     B, T, D = x.shape
     H = cfg.num_heads
@@ -133,12 +141,12 @@ def attention(x, p: Params, cfg, base: str, additive_mask=None):
     scores = q @ k.transpose(-1, -2)
     if additive_mask is not None:
         scores = scores + additive_mask
-    ctx = torch.softmax(scores, dim=-1) @ v
+    ctx = _drop(torch.softmax(scores, dim=-1), drop, f"attn_probs.{layer}") @ v          # encoder.py:41-43
     ctx = ctx.permute(0, 2, 1, 3).reshape(B, T, D)
     return dense(ctx, p[base + "out_proj/kernel"], p[base + "out_proj/bias"])
 
 
-def transformer_layer(x, p: Params, cfg, i: int, additive_mask=None, prefix="wav2vec2/"):
+def transformer_layer(x, p: Params, cfg, i: int, additive_mask=None, prefix="wav2vec2/", drop=None):
     """encoder.py:111-134 (eval: dropout = id, StochasticDepth = add, addons :386-390)."""
     base = f"{prefix}encoder/layers/{i}/"
     eps = cfg.layer_norm_eps
@@ -146,14 +154,14 @@ def transformer_layer(x, p: Params, cfg, i: int, additive_mask=None, prefix="wav
     res = x
     if pre:
         x = layer_norm(x, p[base + "layer_norm/gamma"], p[base + "layer_norm/beta"], eps)
-    x = attention(x, p, cfg, base + "attention/", additive_mask) + res
+    x = _drop(attention(x, p, cfg, base + "attention/", additive_mask, drop, i), drop, f"attn_out.{i}") + res   # :117-119
     if not pre:
         x = layer_norm(x, p[base + "layer_norm/gamma"], p[base + "layer_norm/beta"], eps)
     res = x
     if pre:
         x = layer_norm(x, p[base + "final_layer_norm/gamma"], p[base + "final_layer_norm/beta"], eps)
-    h = gelu_erf(dense(x, p[base + "feed_forward/intermediate_dense/kernel"],
-                       p[base + "feed_forward/intermediate_dense/bias"]))
+    h = _drop(gelu_erf(dense(x, p[base + "feed_forward/intermediate_dense/kernel"],
+                             p[base + "feed_forward/intermediate_dense/bias"])), drop, f"ffn_mid.{i}")             # :127-128
     x = res + dense(h, p[base + "feed_forward/output_dense/kernel"],
                     p[base + "feed_forward/output_dense/bias"])
     if not pre:
@@ -170,7 +178,7 @@ def frame_lengths(cfg, sample_lengths: torch.Tensor) -> torch.Tensor:
 
 
 def encoder(x, p: Params, cfg, frame_mask: Optional[torch.Tensor] = None, prefix="wav2vec2/",
-            num_layers: Optional[int] = None):
+            num_layers: Optional[int] = None, drop=None):
     """encoder.py:251-276.  frame_mask: bool [B,T] (True = real frame) or None."""
     additive = None
     if frame_mask is not None:
@@ -181,8 +189,9 @@ def encoder(x, p: Params, cfg, frame_mask: Optional[torch.Tensor] = None, prefix
     base = f"{prefix}encoder/layer_norm/"
     if cfg.attention_norm_type == "postnorm":
         x = layer_norm(x, p[base + "gamma"], p[base + "beta"], cfg.layer_norm_eps)
+    x = _drop(x, drop, "enc")                                                              # encoder.py:270
     for i in range(cfg.num_layers if num_layers is None else num_layers):
-        x = transformer_layer(x, p, cfg, i, additive, prefix)
+        x = transformer_layer(x, p, cfg, i, additive, prefix, drop)
     if cfg.attention_norm_type == "prenorm":
         x = layer_norm(x, p[base + "gamma"], p[base + "beta"], cfg.layer_norm_eps)
     return x
@@ -194,14 +203,14 @@ def apply_time_mask(features, masked_spec_embed, mask_indices):
 
 
 def wav2vec2_model(speech, p: Params, cfg, attention_mask=None, spec_mask=None, prefix="wav2vec2/",
-                   return_intermediates=False):
+                   return_intermediates=False, drop=None):
     """Wav2Vec2Model.call (modeling.py:169-209).  speech [B,L] fp32 -> [B,T',hidden]."""
     inter = {}
     x = speech[:, :, None]                                   # :188
     for i in range(len(cfg.filter_sizes)):                   # :189-190
         x = feature_extractor_layer(x, p, cfg, i, prefix)
         inter[f"conv{i}"] = x
-    x = feature_projection(x, p, cfg, prefix)                # :191
+    x = feature_projection(x, p, cfg, prefix, drop)          # :191
     inter["proj"] = x
     if spec_mask is not None:                                # :193-199 (training only)
         x = apply_time_mask(x, p[f"{prefix}masked_spec_embed"], spec_mask)
@@ -209,17 +218,17 @@ def wav2vec2_model(speech, p: Params, cfg, attention_mask=None, spec_mask=None, 
     if attention_mask is not None:                           # :201-206
         n = frame_lengths(cfg, attention_mask.to(torch.int64).sum(-1))
         frame_mask = torch.arange(x.shape[1])[None, :] < n[:, None]
-    x = encoder(x, p, cfg, frame_mask, prefix)               # :208
+    x = encoder(x, p, cfg, frame_mask, prefix, drop=drop)    # :208
     if return_intermediates:
         return x, inter
     return x
 
 
-def wav2vec2_for_ctc(speech, p: Params, cfg, attention_mask=None, spec_mask=None):
+def wav2vec2_for_ctc(speech, p: Params, cfg, attention_mask=None, spec_mask=None, drop=None):
     """Wav2Vec2ForCTC.call (modeling.py:239-255); variables live under ``wav2vec2-ctc/``
     in the reference, here the inner model keeps the ``wav2vec2/`` prefix."""
-    h = wav2vec2_model(speech, p, cfg, attention_mask, spec_mask)
-    return dense(h, p["lm_head/kernel"], p["lm_head/bias"])
+    h = wav2vec2_model(speech, p, cfg, attention_mask, spec_mask, drop=drop)
+    return dense(_drop(h, drop, "head"), p["lm_head/kernel"], p["lm_head/bias"])          # modeling.py:252-254
 
 
 # --------------------------------------------------------------------------- CTC loss

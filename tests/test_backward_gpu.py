@@ -283,3 +283,133 @@ def test_stage2_step_updates_weights_and_lowers_loss():
     assert m.variables["lm_head/kernel"].data_ptr() >= trainer.flat_w.data_ptr()
     logits = m(x)
     assert torch.isfinite(logits).all()
+
+
+# ------------------------------------------------------------------------------------------------ dropout
+def test_dropout_rows_and_mask_statistics():
+    ops = _ops()
+    torch.manual_seed(6)
+    rows, d = 500, 768
+    x = torch.randn(rows, d, device=DEV)
+    r = torch.randn(rows, d, device=DEV)
+    drop = (0.1, 1234567, 7)
+    out = torch.empty_like(x)
+    hi = torch.empty(rows, d, dtype=torch.bfloat16, device=DEV)
+    ops.dropout_rows(x, drop, resid=r, out_f32=out, out_hi=hi)
+    keep = ops.dropout_mask(rows * d, drop, DEV).view(rows, d).float()
+    torch.cuda.synchronize()
+    scale = 65536.0 / (65536.0 - round(0.1 * 65536))
+    assert (out - (r + x * keep * scale)).abs().max().item() < 1e-6
+    assert (hi.float() - out).abs().max().item() <= out.abs().max().item() * 2 ** -8
+    assert abs(keep.mean().item() - 0.9) < 3e-3                         # 384000 Bernoulli(0.9) draws
+    assert abs(keep[:, ::4].mean().item() - 0.9) < 6e-3                 # every 16-bit lane of the 64-bit draw
+    other = ops.dropout_mask(rows * d, (0.1, 1234567, 8), DEV).view(rows, d).float()
+    assert 0.7 < (keep == other).float().mean().item() < 0.9            # independent streams agree with p^2 + q^2 = 0.82
+    # the same (seed, site) regenerates the mask: applying it to a gradient is the backward pass
+    g = torch.randn(rows, d, device=DEV)
+    ops.dropout_rows(g, drop, out_f32=g)
+    torch.cuda.synchronize()
+    assert ((g == 0) == (keep == 0)).all()
+
+
+@pytest.mark.parametrize("T", [145, 768])
+def test_attention_dropout_forward_and_backward(T):
+    """w2v2_attn_fwd_train / w2v2_attn_bwd with dropout on the probabilities vs autograd with the exported mask."""
+    ops = _ops()
+    from wav2vec2.ops import Pair
+    torch.manual_seed(7)
+    B, H, dh = 2, 3, 64
+    d = H * dh
+    raw = torch.randn(B, T, 3 * d, device=DEV) * 1.2
+    raw[:, :, :d] *= dh ** -0.5
+    qkv = _bf(raw)
+    drop = (0.1, 99, 18)
+    keep = ops.attn_dropout_mask(B * H, T, drop, DEV).view(B, H, T, T).double()
+    scale = 65536.0 / (65536.0 - round(0.1 * 65536))
+    x = qkv.double().requires_grad_()
+    q, k, v = (t.reshape(B, T, H, dh).permute(0, 2, 1, 3) for t in x.split(d, dim=-1))
+    p = torch.softmax(q @ k.transpose(-1, -2), -1) * keep * scale
+    ctx_ref = (p @ v).permute(0, 2, 1, 3).reshape(B, T, d)
+    ctx = Pair(torch.zeros(B, T, d, dtype=torch.bfloat16, device=DEV))
+    ops.attn_fwd_train(Pair(qkv), B, T, H, dh, None, ctx, 1, drop)
+    torch.cuda.synchronize()
+    assert abs(keep.mean().item() - 0.9) < 5e-3
+    err = (ctx.hi.double() - ctx_ref).abs().max().item()
+    print(f"attention dropout fwd T={T}: max err {err:.3e}")
+    assert err < 3e-2
+    dctx = _bf(torch.randn(B, T, d, device=DEV))
+    ctx_ref.backward(dctx.double())
+    got = torch.empty(B, T, 3 * d, dtype=torch.bfloat16, device=DEV)
+    ops.attn_bwd(qkv, _bf(ctx_ref.detach().float()), dctx, B, T, H, dh, None, 1.0, got, drop=drop)
+    torch.cuda.synchronize()
+    for name, sl in (("dq", slice(0, d)), ("dk", slice(d, 2 * d)), ("dv", slice(2 * d, 3 * d))):
+        r = _rel(got[..., sl].float(), x.grad[..., sl].float())
+        print(f"attention dropout bwd T={T} {name}: rel err {r:.3e}")
+        assert r < 2e-2
+
+
+def _export_dropout_masks(trainer, cfg, B, T):
+    """keep / (1 - rate) tensors of every dropout site of the NEXT step, in the oracle's layout."""
+    ops = _ops()
+    d, ffn, H = cfg.hidden_size, cfg.intermediate_size, cfg.num_heads
+    scale = 65536.0 / (65536.0 - round(cfg.dropout * 65536))
+
+    def rows(site, n):
+        return (ops.dropout_mask(B * T * n, trainer._drop(site), DEV).view(B, T, n).float() * scale).cpu().double()
+    drop = {"proj": rows(trainer.SITE_PROJ, d), "enc": rows(trainer.SITE_ENC, d), "head": rows(trainer.SITE_HEAD, d)}
+    for i in range(cfg.num_layers):
+        drop[f"attn_out.{i}"] = rows(trainer.site_attn_out(i), d)
+        drop[f"ffn_mid.{i}"] = rows(trainer.site_ffn_mid(i), ffn)
+        m = ops.attn_dropout_mask(B * H, T, trainer._drop(trainer.site_attn_probs(i)), DEV).view(B, H, T, T)
+        drop[f"attn_probs.{i}"] = (m.float() * scale).cpu().double()
+    return drop
+
+
+def test_stage2_with_dropout_matches_oracle_autograd():
+    """The reference's default training configuration (dropout 0.1 at all six sites + SpecAugment): loss and every gradient
+    vs fp64 autograd through the oracle fed with the masks the kernels' generator produces for this step."""
+    import numpy as np
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC
+    from wav2vec2.training import Stage2Trainer
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.1, apply_spec_augment=True)
+    params = O.random_params(cfg, seed=4)
+    m = Wav2Vec2ForCTC(cfg, input_shape=(1, 2048), precision="bf16x3")
+    m.set_variables(params)
+    B, L = 3, 16000
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(1))
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 12))).int()
+    T = cfg.num_frames(L)
+    spec_mask = torch.zeros(B, T, dtype=torch.bool)
+    spec_mask[0, 3:13] = True
+    spec_mask[2, 35:45] = True
+    trainer = Stage2Trainer(m, CTCLoss(cfg, (B, L), division_factor=B), seed=1234)
+    drop = _export_dropout_masks(trainer, cfg, B, T)
+    loss = trainer.loss_and_gradients(x.cuda(), labels.cuda(), spec_mask=spec_mask)
+    torch.cuda.synchronize()
+    p = {k: t.double().clone().requires_grad_(True) for k, t in params.items()}
+    logits = O.wav2vec2_for_ctc(x.double(), p, cfg, spec_mask=spec_mask, drop=drop)
+    lp = torch.log_softmax(logits, -1).transpose(0, 1)
+    ref_loss = torch.nn.functional.ctc_loss(lp, labels.long(), torch.full((B,), T), (labels != 0).sum(-1), blank=0,
+                                            reduction="sum") / B
+    ref_loss.backward()
+    print(f"stage-2 dropout: loss {loss.item():.4f} vs oracle {ref_loss.item():.4f}")
+    assert abs(loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    worst = ("", 0.0)
+    for name in trainer.names:
+        want = p[name].grad
+        got = trainer.G[name].cpu().double()
+        if want is None or want.norm().item() < 1e-12:
+            assert got.norm().item() < 2e-2, name
+            continue
+        r = _rel(got, want)
+        worst = max(worst, (name, r), key=lambda t: t[1])
+        assert r < 3e-2, f"{name}: relative gradient error {r:.3e}"
+    print(f"stage-2 dropout: worst relative L2 gradient error {worst[1]:.3e} ({worst[0]})")
+    # a different step draws different masks; the same step is reproducible
+    l1 = trainer.loss_and_gradients(x.cuda(), labels.cuda(), spec_mask=spec_mask).item()
+    assert abs(l1 - loss.item()) < 1e-4 * abs(l1)
+    trainer.t += 1
+    l2 = trainer.loss_and_gradients(x.cuda(), labels.cuda(), spec_mask=spec_mask).item()
+    assert abs(l2 - loss.item()) > 1e-4 * abs(l2)

@@ -11,7 +11,7 @@ from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC, ops  # noqa: E402
 from wav2vec2.training import Stage2Trainer  # noqa: E402
 
 B, L = int(os.environ.get("BATCH", "8")), int(os.environ.get("SEQ", "246000"))
-cfg = Wav2Vec2Config(dropout=0.0)
+cfg = Wav2Vec2Config(dropout=float(os.environ.get("DROPOUT", "0.1")))
 model = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision="bf16").init_random(0)
 tr = Stage2Trainer(model, CTCLoss(cfg, (B, L), division_factor=B))
 x = torch.randn(B, L, generator=torch.Generator().manual_seed(0)).cuda()
@@ -52,7 +52,7 @@ print({k: round(v, 3) for k, v in acc.items()})
 records = []
 orig = {}
 for name in ("gemm", "ln_bwd", "dact_colsum", "transpose_bf16", "attn_bwd", "posconv_train", "posconv_wgrad", "lm_head_wgrad",
-             "lm_head_dgrad", "split_bf16", "gelu_rows", "ln_rows", "attn_fwd"):
+             "lm_head_dgrad", "split_bf16", "gelu_rows", "ln_rows", "attn_fwd", "attn_fwd_train", "dropout_rows"):
     fn = getattr(ops, name)
     orig[name] = fn
 
