@@ -382,14 +382,25 @@ __device__ __forceinline__ void gelu_x2(float& x0, float& x1) {
 }
 
 // --------------------------------------------------------------------------- dropout RNG
-// Counter-based: 64 random bits per group of FOUR consecutive elements = splitmix64(seed, site, element_index / 4); element e
+// Counter-based: 64 random bits per group of FOUR consecutive elements = hash(seed, site, element_index / 4); element e
 // of the group is KEPT when its 16-bit lane >= thr16 (thr16 = round(p * 65536)).  Stateless, so the backward pass (and the
 // test oracle, through w2v2_dropout_mask) regenerates exactly the mask of the forward pass.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {   // murmur3 finaliser: full avalanche on 32 bits
+  h ^= h >> 16;
+  h *= 0x85EBCA6Bu;
+  h ^= h >> 13;
+  h *= 0xC2B2AE35u;
+  h ^= h >> 16;
+  return h;
+}
 __device__ __forceinline__ uint64_t drop_bits4(uint64_t seed, uint32_t site, uint64_t group) {
-  uint64_t z = seed + (group + ((uint64_t)site << 48)) * 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
+  // two chained 32-bit hashes of (seed, site, group): 32-bit integer multiplies only (the 64-bit splitmix version cost
+  // 2.2 ms per train step inside the attention backward, one draw per element pair there)
+  const uint32_t glo = (uint32_t)group, ghi = (uint32_t)(group >> 32);
+  const uint32_t k = mix32((uint32_t)seed ^ (site * 0x9E3779B9u)) ^ mix32((uint32_t)(seed >> 32) + ghi * 0x85EBCA77u + 0x7F4A7C15u);
+  const uint32_t r0 = mix32(glo ^ k);
+  const uint32_t r1 = mix32((glo * 0x9E3779B1u + 0x6A09E667u) ^ (k * 0xC2B2AE3Du));
+  return (uint64_t)r0 | ((uint64_t)r1 << 32);
 }
 __device__ __forceinline__ bool drop_keep(uint64_t bits, int e, uint32_t thr16) {
   return ((uint32_t)(bits >> (16 * e)) & 0xFFFFu) >= thr16;

@@ -219,7 +219,7 @@ int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void* dctx_hi, i
                   uint64_t seed, uint32_t site, void* stream);   /* drop_p, seed, site: those of w2v2_attn_fwd_train */
 /* Dropout (tf.keras.layers.Dropout at feature_extractor.py:95, encoder.py:42,118,128,270, modeling.py:253; rate config.py:9).
  * Masks come from a stateless counter-based generator: 64 bits per group of 4 consecutive elements =
- * splitmix64(seed, site, index / 4), element kept when its 16-bit lane >= round(p * 65536), kept values scaled by 1 / (1 - p).
+ * hash(seed, site, index / 4) (two chained murmur3 finalisers), element kept when its 16-bit lane >= round(p * 65536), kept values scaled by 1 / (1 - p).
  * The backward pass regenerates the mask from (seed, site); w2v2_dropout_mask / w2v2_attn_dropout_mask export it (tests).
  *   w2v2_dropout_rows : out = (resid ? resid : 0) + dropout(x)  (fp32, optional bf16 copy; in place allowed)
  *   w2v2_attn_fwd_train : w2v2_attn_fwd with dropout on the attention probabilities (after the softmax, encoder.py:41-43) */
