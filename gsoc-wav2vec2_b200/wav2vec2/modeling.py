@@ -378,7 +378,8 @@ class _B200Model:
     def _encode(self, batch, attention_mask, training):
         cfg, v = self.config, self.variables
         if training and cfg.dropout:
-            raise NotImplementedError("training-mode forward (dropout RNG) is not built yet; use dropout=0")
+            raise NotImplementedError("training-mode forward with dropout needs the base architecture without an attention mask "
+                                      "(see _training_forward); use dropout=0 here")
         last_f32, B, T = self._features(batch)
         P, A = self._packed, self._arena
         passes = _PRECISIONS[self.precision]
@@ -499,6 +500,21 @@ class _B200Model:
         graph.replay()
         return outs
 
+    def _training_forward(self, batch):
+        """``training=True`` with dropout: the training forward of ``training.Stage2Trainer`` (dropout at the reference's
+        six sites from a per-call mask stream, SpecAugment).  Returns (logits or None, hidden fp32 [B*T', d], (B, T', d))."""
+        from .training import Stage2Trainer
+        if not Stage2Trainer.supports(self.config):
+            raise NotImplementedError("training-mode forward with dropout covers the base architecture (group-norm extractor, "
+                                      "post-norm encoder) without an attention mask; use dropout=0 otherwise")
+        if getattr(self, "_train_fwd", None) is None:
+            self._train_fwd = Stage2Trainer.forward_only(self, seed=int(os.environ.get("W2V2_SEED", "0")))
+        fw = self._train_fwd
+        fw.t += 1                                   # a fresh mask stream per call
+        logits = fw._forward(batch.to(self.device))
+        S = fw.saved
+        return logits, S["hidden_f32"], (S["B"], S["T"], self.config.hidden_size)
+
     def _warn_mask(self, attention_mask):
         # modeling.py:183-186
         if self.config.is_robust and attention_mask is None:
@@ -523,6 +539,9 @@ class Wav2Vec2Model(_B200Model):
         self._warn_mask(attention_mask)
         if self._use_graph and not training:
             return self._graphed(self._hidden_eager, batch, attention_mask).clone()
+        if training and self.config.dropout and attention_mask is None:
+            _, x_f32, (B, T, d) = self._training_forward(batch)
+            return x_f32.view(B, T, d).clone()
         x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
         return x_f32.view(B, T, d).clone()
 
@@ -552,6 +571,9 @@ class Wav2Vec2ForCTC(_B200Model):
         return self._forward_impl(batch, attention_mask, training)
 
     def _forward_impl(self, batch, attention_mask, training):
+        if training and self.config.dropout and attention_mask is None:
+            logits, hidden, _ = self._training_forward(batch)      # hidden = the (dropped) input of lm_head
+            return logits.clone(), hidden
         hidden, xs, (B, T, d) = self._encode(batch, attention_mask, training)
         V = self.config.vocab_size
         logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device)

@@ -117,6 +117,17 @@ class Stage2Trainer:
         """(rate, seed, site) of this step's mask stream; rate 0 = off."""
         return (float(self.model.config.dropout), self.seed + 0x9E3779B1 * (self.t + 1), site)
 
+    @classmethod
+    def forward_only(cls, model, seed=0):
+        """The training-mode forward (dropout + SpecAugment) without optimizer state: what ``model(x, training=True)`` runs."""
+        self = cls.__new__(cls)
+        self.model, self.loss_fn, self.seed, self.t, self.saved, self._wt = model, None, int(seed), 0, None, None
+        return self
+
+    @staticmethod
+    def supports(cfg):
+        return cfg.attention_norm_type == "postnorm" and cfg.feature_extractor_norm_type == "group"
+
     def __init__(self, model: Wav2Vec2ForCTC, loss_fn: CTCLoss, learning_rate=5e-5, beta_1=0.9, beta_2=0.999,
                  epsilon=1e-7, seed=0):
         cfg = model.config
@@ -259,6 +270,10 @@ class Stage2Trainer:
                         out_hi=nxt.hi, out_lo=nxt.lo)
             L.append(dict(xs=xs, qkv=qkv, ctx=ctx, y1=y1, x1=x1, pre=pre, mid=mid, y2=y2))
             xs = nxt
+        S["layers"], S["hidden_f32"] = L, xs_f32
+        self.saved = S
+        if not model.with_head:                             # Wav2Vec2Model: hidden states, no head dropout
+            return None
         V = cfg.vocab_size
         logits = A.get("t.logits", (B, T, V), f32)
         hidden_f32 = xs_f32

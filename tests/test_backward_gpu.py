@@ -413,3 +413,26 @@ def test_stage2_with_dropout_matches_oracle_autograd():
     trainer.t += 1
     l2 = trainer.loss_and_gradients(x.cuda(), labels.cuda(), spec_mask=spec_mask).item()
     assert abs(l2 - loss.item()) > 1e-4 * abs(l2)
+
+
+def test_model_call_training_true_applies_dropout():
+    """Wav2Vec2ForCTC.__call__(training=True) with the reference's default dropout 0.1 (modeling.py:239-255): stochastic
+    per call, close to the eval logits in expectation, and exactly the oracle's output for the masks of that call."""
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import Wav2Vec2Config, Wav2Vec2ForCTC
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.1, apply_spec_augment=False)
+    params = O.random_params(cfg, seed=4)
+    m = Wav2Vec2ForCTC(cfg, input_shape=(1, 2048), precision="bf16x3")
+    m.set_variables(params)
+    B, L = 2, 16000
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(1))
+    ev = m(x.cuda(), training=False)
+    t1 = m(x.cuda(), training=True).clone()
+    t2 = m(x.cuda(), training=True).clone()
+    fw = m._train_fwd                                     # its step counter still identifies the mask stream of call 2
+    assert not torch.equal(t1, t2) and not torch.equal(t1, ev)
+    assert torch.isfinite(t1).all() and (t1 - ev).abs().mean().item() < 0.5 * ev.abs().mean().item() + 0.5
+    T = cfg.num_frames(L)
+    drop = _export_dropout_masks(fw, cfg, B, T)
+    ref = O.wav2vec2_for_ctc(x.double(), {k: v.double() for k, v in params.items()}, cfg, drop=drop).float()
+    assert (t2.cpu() - ref).abs().max().item() < 1e-3
