@@ -304,7 +304,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         for (int pc = 0; pc < 4; ++pc) {
 #pragma unroll
           for (int i4 = 0; i4 < 8; ++i4) {
-            const uint64_t bits = drop_bits4(p.drop.seed, p.drop.site, rg + pc * 8 + i4);
+            const uint64_t bits = drop_bits4(p.drop, rg + pc * 8 + i4);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float v = __uint_as_float(sr[pc][4 * i4 + e]);

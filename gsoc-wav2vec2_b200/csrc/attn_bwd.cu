@@ -255,7 +255,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const float p = (key < klen) ? ex2_approx(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
           float dpv = dp[j][2 * r + e];
           if (dr.thr16) {   // dP = dP_dropped o mask / (1 - p_drop)
-            const uint64_t bits = drop_bits4(dr.seed, dr.site, attn_row_group(bh, t0 + m0 + g + 8 * r, T) + (key >> 2));
+            const uint64_t bits = drop_bits4(dr, attn_row_group(bh, t0 + m0 + g + 8 * r, T) + (key >> 2));
             dpv = drop_keep(bits, key & 3, dr.thr16) ? dpv * dr.scale : 0.0f;
           }
           ds[2 * r + e] = p * (dpv - dsum[r]);
@@ -381,7 +381,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           float keep = 1.0f;
           if (dr.thr16) {
             const int key = k0 + m0 + g + 8 * r;
-            const uint64_t bits = drop_bits4(dr.seed, dr.site, attn_row_group(bh, qb * AB_BLK + qi, T) + (key >> 2));
+            const uint64_t bits = drop_bits4(dr, attn_row_group(bh, qb * AB_BLK + qi, T) + (key >> 2));
             keep = drop_keep(bits, key & 3, dr.thr16) ? dr.scale : 0.0f;
           }
           p[2 * r + e] = pv * keep;                                   // dV uses the dropped probabilities

@@ -128,7 +128,7 @@ gelu_rows_kernel(const float* __restrict__ pre, size_t n4, __nv_bfloat16* __rest
     gelu_x2<FAST>(v.x, v.y);
     gelu_x2<FAST>(v.z, v.w);
     if (dr.thr16) {   // encoder.py:128: dropout on the activated intermediate
-      const uint64_t bits = drop_bits4(dr.seed, dr.site, i);
+      const uint64_t bits = drop_bits4(dr, i);
       v.x = drop_keep(bits, 0, dr.thr16) ? v.x * dr.scale : 0.0f;
       v.y = drop_keep(bits, 1, dr.thr16) ? v.y * dr.scale : 0.0f;
       v.z = drop_keep(bits, 2, dr.thr16) ? v.z * dr.scale : 0.0f;
@@ -162,7 +162,7 @@ dact_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
     const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dy + off));
     float4 g = make_float4(bf16_lo_to_f32(raw.x), bf16_hi_to_f32(raw.x), bf16_lo_to_f32(raw.y), bf16_hi_to_f32(raw.y));
     if (dr.thr16) {   // gradient of a dropout that sat AFTER the activation (or after a Dense when pre == null)
-      const uint64_t bits = drop_bits4(dr.seed, dr.site, off >> 2);
+      const uint64_t bits = drop_bits4(dr, off >> 2);
       g.x = drop_keep(bits, 0, dr.thr16) ? g.x * dr.scale : 0.0f;
       g.y = drop_keep(bits, 1, dr.thr16) ? g.y * dr.scale : 0.0f;
       g.z = drop_keep(bits, 2, dr.thr16) ? g.z * dr.scale : 0.0f;
@@ -194,7 +194,7 @@ dropout_rows_kernel(const float* __restrict__ x, const float* __restrict__ resid
                     __nv_bfloat16* __restrict__ out_hi, DropSpec dr) {
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (size_t)gridDim.x * 256) {
     float4 v = reinterpret_cast<const float4*>(x)[i];
-    const uint64_t bits = drop_bits4(dr.seed, dr.site, i);
+    const uint64_t bits = drop_bits4(dr, i);
     v.x = drop_keep(bits, 0, dr.thr16) ? v.x * dr.scale : 0.0f;
     v.y = drop_keep(bits, 1, dr.thr16) ? v.y * dr.scale : 0.0f;
     v.z = drop_keep(bits, 2, dr.thr16) ? v.z * dr.scale : 0.0f;
@@ -210,7 +210,7 @@ dropout_rows_kernel(const float* __restrict__ x, const float* __restrict__ resid
 // the keep mask itself (1 = kept), for tests: elementwise sites use index = flat element index
 __global__ void dropout_mask_kernel(size_t n, uint8_t* __restrict__ out, DropSpec dr) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    out[i] = drop_keep(drop_bits4(dr.seed, dr.site, i >> 2), (int)(i & 3), dr.thr16) ? 1 : 0;
+    out[i] = drop_keep(drop_bits4(dr, i >> 2), (int)(i & 3), dr.thr16) ? 1 : 0;
 }
 
 // keep mask of the attention-probability dropout, out[bh][q][k]
@@ -220,7 +220,7 @@ __global__ void attn_dropout_mask_kernel(int BH, int T, uint8_t* __restrict__ ou
     const int k = (int)(i % T);
     const size_t row = i / T;
     const int q = (int)(row % T), bh = (int)(row / T);
-    out[i] = drop_keep(drop_bits4(dr.seed, dr.site, attn_row_group(bh, q, T) + (k >> 2)), k & 3, dr.thr16) ? 1 : 0;
+    out[i] = drop_keep(drop_bits4(dr, attn_row_group(bh, q, T) + (k >> 2)), k & 3, dr.thr16) ? 1 : 0;
   }
 }
 

@@ -385,7 +385,7 @@ __device__ __forceinline__ void gelu_x2(float& x0, float& x1) {
 // Counter-based: 64 random bits per group of FOUR consecutive elements = hash(seed, site, element_index / 4); element e
 // of the group is KEPT when its 16-bit lane >= thr16 (thr16 = round(p * 65536)).  Stateless, so the backward pass (and the
 // test oracle, through w2v2_dropout_mask) regenerates exactly the mask of the forward pass.
-__device__ __forceinline__ uint32_t mix32(uint32_t h) {   // murmur3 finaliser: full avalanche on 32 bits
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t h) {   // murmur3 finaliser: full avalanche on 32 bits
   h ^= h >> 16;
   h *= 0x85EBCA6Bu;
   h ^= h >> 13;
@@ -393,28 +393,26 @@ __device__ __forceinline__ uint32_t mix32(uint32_t h) {   // murmur3 finaliser: 
   h ^= h >> 16;
   return h;
 }
-__device__ __forceinline__ uint64_t drop_bits4(uint64_t seed, uint32_t site, uint64_t group) {
-  // two chained 32-bit hashes of (seed, site, group): 32-bit integer multiplies only (the 64-bit splitmix version cost
-  // 2.2 ms per train step inside the attention backward, one draw per element pair there)
-  const uint32_t glo = (uint32_t)group, ghi = (uint32_t)(group >> 32);
-  const uint32_t k = mix32((uint32_t)seed ^ (site * 0x9E3779B9u)) ^ mix32((uint32_t)(seed >> 32) + ghi * 0x85EBCA77u + 0x7F4A7C15u);
-  const uint32_t r0 = mix32(glo ^ k);
-  const uint32_t r1 = mix32((glo * 0x9E3779B1u + 0x6A09E667u) ^ (k * 0xC2B2AE3Du));
-  return (uint64_t)r0 | ((uint64_t)r1 << 32);
-}
 __device__ __forceinline__ bool drop_keep(uint64_t bits, int e, uint32_t thr16) {
   return ((uint32_t)(bits >> (16 * e)) & 0xFFFFu) >= thr16;
 }
 struct DropSpec {       // thr16 == 0: dropout off
-  uint64_t seed;
-  uint32_t site;
+  uint32_t key0, key1;  // host-side hashes of (seed, site): the per-stream keys
   uint32_t thr16;
   float scale;          // 1 / (1 - p)
 };
+// 64 bits for group `group` of stream (key0, key1): two murmur3 finalisers on 32-bit integer multiplies (a 64-bit splitmix
+// per element pair cost 2.2 ms per train step inside the attention backward)
+__device__ __forceinline__ uint64_t drop_bits4(const DropSpec& d, uint64_t group) {
+  const uint32_t h = (uint32_t)group ^ ((uint32_t)(group >> 32) * 0x85EBCA77u);
+  const uint32_t r0 = mix32(h ^ d.key0);
+  const uint32_t r1 = mix32((h + 0x9E3779B9u) ^ d.key1);
+  return (uint64_t)r0 | ((uint64_t)r1 << 32);
+}
 inline DropSpec make_drop(float p, uint64_t seed, uint32_t site) {
   DropSpec d;
-  d.seed = seed;
-  d.site = site;
+  d.key0 = mix32((uint32_t)seed ^ mix32(site * 0x9E3779B9u + 0x7F4A7C15u));
+  d.key1 = mix32((uint32_t)(seed >> 32) + 0x6A09E667u + mix32(d.key0 ^ site));
   d.thr16 = (p > 0.0f) ? (uint32_t)(p * 65536.0f + 0.5f) : 0u;
   if (d.thr16 > 65535u) d.thr16 = 65535u;
   d.scale = (d.thr16 > 0u) ? 65536.0f / (65536.0f - (float)d.thr16) : 1.0f;

@@ -13,6 +13,7 @@ requires ``config.dropout == 0`` (SpecAugment, main.py/modeling.py:193-199, is a
 """
 import os
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -94,7 +95,8 @@ class Stage2Trainer:
     intermediate, after the encoder LayerNorm and before ``lm_head`` - with masks from a stateless counter-based generator
     (``include/w2v2.h``), so the backward pass regenerates them instead of storing them.
     Limits: post-norm encoder with the group-norm extractor (the base architecture of BASELINE config 3), no attention
-    mask, ``survival_prob == 1``; SpecAugment masks (host RNG like the reference) are supported.
+    mask; SpecAugment masks and the StochasticDepth draw of the FFN branch (``survival_prob``) use the host RNG like the
+    reference's numpy / Keras RNG.
     Backward products run single-pass bf16 with fp32 accumulation; LayerNorm / softmax / GELU derivatives in fp32.
     """
 
@@ -180,7 +182,7 @@ class Stage2Trainer:
         return W
 
     # ------------------------------------------------------------------ forward keeping what the backward needs
-    def _forward(self, speech, spec_mask=None):
+    def _forward(self, speech, spec_mask=None, layer_keep=None):
         model = self.model
         cfg, v = model.config, model.variables
         last_f32, B, T = model._features(speech)          # frozen extractor: the inference kernels, nothing kept
@@ -256,19 +258,30 @@ class Stage2Trainer:
             x1 = A.pair(f"t.x1.{i}", (M, d), lo)
             ops.ln_rows(y1, v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"], eps, M, d, out_f32=x1_f32, out_hi=x1.hi,
                         out_lo=x1.lo)
-            pre = A.get(f"t.pre.{i}", (M, ffn), f32)
-            ops.gemm(x1, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
-                     out_f32=pre, passes=passes)
-            mid = A.pair(f"t.mid.{i}", (M, ffn), lo)
-            ops.gelu_rows(pre, mid.hi, fast=(passes == 1), out_lo=mid.lo,
-                          drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
+            # StochasticDepth on the FFN branch (encoder.py:130, tensorflow_addons.py:374-394): ONE Bernoulli(survival_prob)
+            # draw per layer call decides whether the branch is added at all (host RNG, numpy like SpecAugment)
+            keep = True
+            if layer_keep is not None:
+                keep = bool(layer_keep[i])
+            elif cfg.survival_prob < 1.0:
+                keep = bool(np.random.rand() < cfg.survival_prob)
             y2 = A.get(f"t.y2.{i}", (M, d), f32)
-            ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=v[lb + "feed_forward/output_dense/bias"],
-                     residual=x1_f32, out_f32=y2, passes=passes)
+            pre = mid = None
+            if keep:
+                pre = A.get(f"t.pre.{i}", (M, ffn), f32)
+                ops.gemm(x1, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
+                         out_f32=pre, passes=passes)
+                mid = A.pair(f"t.mid.{i}", (M, ffn), lo)
+                ops.gelu_rows(pre, mid.hi, fast=(passes == 1), out_lo=mid.lo,
+                              drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
+                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=v[lb + "feed_forward/output_dense/bias"],
+                         residual=x1_f32, out_f32=y2, passes=passes)
+            else:
+                y2.copy_(x1_f32)
             nxt = A.pair(f"t.xs.{i + 1}", (M, d), lo)
             ops.ln_rows(y2, v[lb + "final_layer_norm/gamma"], v[lb + "final_layer_norm/beta"], eps, M, d, out_f32=xs_f32,
                         out_hi=nxt.hi, out_lo=nxt.lo)
-            L.append(dict(xs=xs, qkv=qkv, ctx=ctx, y1=y1, x1=x1, pre=pre, mid=mid, y2=y2))
+            L.append(dict(xs=xs, qkv=qkv, ctx=ctx, y1=y1, x1=x1, pre=pre, mid=mid, y2=y2, ffn_on=keep))
             xs = nxt
         S["layers"], S["hidden_f32"] = L, xs_f32
         self.saved = S
@@ -326,18 +339,22 @@ class Stage2Trainer:
             lb = f"{enc}layers/{i}/"
             ff, at = lb + "feed_forward/", lb + "attention/"
             # x_{i+1} = LN2(y2),  y2 = x1 + mid W2 + b2
+            on = Li["ffn_on"]
             ops.ln_bwd(Li["y2"], v[lb + "final_layer_norm/gamma"], g, eps, M, d, dx_f32=dy, dx_hi=dyh,
                        dgamma=G[lb + "final_layer_norm/gamma"], dbeta=G[lb + "final_layer_norm/beta"],
-                       colsum=G[ff + "output_dense/bias"])
-            ops.gemm(Pair(dyh), W[f"l{i}.ff2"], K=d, N=ffn, rows_per_batch=M, out_hi=dmid)
-            ops.transpose_bf16(dyh, M, d, dyT, Mp)
-            self._wgrad(Li["mid"].hi, dyT, M, Mp, ffn, G[ff + "output_dense/kernel"])
-            # mid = gelu(pre),  pre = x1 W1 + b1
-            ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"],
-                            drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
-            ops.gemm(Pair(dpre), W[f"l{i}.ff1"], K=ffn, N=d, rows_per_batch=M, residual=dy, out_f32=g1)
-            ops.transpose_bf16(dpre, M, ffn, dffT, Mp)
-            self._wgrad(Li["x1"].hi, dffT, M, Mp, d, G[ff + "intermediate_dense/kernel"])
+                       colsum=G[ff + "output_dense/bias"] if on else None)
+            if on:
+                ops.gemm(Pair(dyh), W[f"l{i}.ff2"], K=d, N=ffn, rows_per_batch=M, out_hi=dmid)
+                ops.transpose_bf16(dyh, M, d, dyT, Mp)
+                self._wgrad(Li["mid"].hi, dyT, M, Mp, ffn, G[ff + "output_dense/kernel"])
+                # mid = dropout(gelu(pre)),  pre = x1 W1 + b1
+                ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"],
+                                drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
+                ops.gemm(Pair(dpre), W[f"l{i}.ff1"], K=ffn, N=d, rows_per_batch=M, residual=dy, out_f32=g1)
+                ops.transpose_bf16(dpre, M, ffn, dffT, Mp)
+                self._wgrad(Li["x1"].hi, dffT, M, Mp, d, G[ff + "intermediate_dense/kernel"])
+            else:
+                g1.copy_(dy)                # the branch was dropped by StochasticDepth: only the shortcut carries gradient
             # x1 = LN1(y1),  y1 = x + ctx Wo + bo
             if p_drop:
                 # the attention branch sees the gradient through its dropout mask, the residual branch sees all of it
@@ -402,10 +419,10 @@ class Stage2Trainer:
 
     # ------------------------------------------------------------------ one optimisation step
     @torch.no_grad()
-    def loss_and_gradients(self, speech, labels, spec_mask=None):
+    def loss_and_gradients(self, speech, labels, spec_mask=None, layer_keep=None):
         """Forward + CTC loss + backward on this rank's shard; gradients land in ``self.G`` (views of ``flat_g``).
         ``spec_mask`` [B, T'] overrides the sampled SpecAugment mask (tests)."""
-        logits = self._forward(speech.to(self.model.device), spec_mask)
+        logits = self._forward(speech.to(self.model.device), spec_mask, layer_keep)
         loss, dlogits = self.loss_fn(labels, logits, return_grad=True)
         self._backward(dlogits)
         return loss

@@ -162,8 +162,10 @@ def transformer_layer(x, p: Params, cfg, i: int, additive_mask=None, prefix="wav
         x = layer_norm(x, p[base + "final_layer_norm/gamma"], p[base + "final_layer_norm/beta"], eps)
     h = _drop(gelu_erf(dense(x, p[base + "feed_forward/intermediate_dense/kernel"],
                              p[base + "feed_forward/intermediate_dense/bias"])), drop, f"ffn_mid.{i}")             # :127-128
-    x = res + dense(h, p[base + "feed_forward/output_dense/kernel"],
-                    p[base + "feed_forward/output_dense/bias"])
+    branch = dense(h, p[base + "feed_forward/output_dense/kernel"], p[base + "feed_forward/output_dense/bias"])
+    # StochasticDepth (tensorflow_addons.py:374-394): eval = plain add; training = shortcut + b * residual with ONE Bernoulli
+    # draw b per layer call (explicit here: drop["stochastic_depth.<i>"] in {0, 1})
+    x = res + _drop(branch, drop, f"stochastic_depth.{i}")
     if not pre:
         x = layer_norm(x, p[base + "final_layer_norm/gamma"], p[base + "final_layer_norm/beta"], eps)
     return x

@@ -436,3 +436,40 @@ def test_model_call_training_true_applies_dropout():
     drop = _export_dropout_masks(fw, cfg, B, T)
     ref = O.wav2vec2_for_ctc(x.double(), {k: v.double() for k, v in params.items()}, cfg, drop=drop).float()
     assert (t2.cpu() - ref).abs().max().item() < 1e-3
+
+
+def test_stage2_stochastic_depth_drops_the_ffn_branch():
+    """StochasticDepth (tensorflow_addons.py:374-394) in training: one Bernoulli draw per layer call; a dropped FFN branch
+    contributes neither to the forward nor to any gradient.  Explicit draws [keep, drop] vs the oracle."""
+    import numpy as np
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC
+    from wav2vec2.training import Stage2Trainer
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.0, apply_spec_augment=False, survival_prob=0.5)
+    params = O.random_params(cfg, seed=4)
+    m = Wav2Vec2ForCTC(cfg, input_shape=(1, 2048), precision="bf16x3")
+    m.set_variables(params)
+    B, L = 2, 16000
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(1))
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 12))).int()
+    trainer = Stage2Trainer(m, CTCLoss(cfg, (B, L), division_factor=B))
+    loss = trainer.loss_and_gradients(x.cuda(), labels.cuda(), layer_keep=[True, False])
+    torch.cuda.synchronize()
+    p = {k: t.double().clone().requires_grad_(True) for k, t in params.items()}
+    drop = {"stochastic_depth.0": torch.ones(()), "stochastic_depth.1": torch.zeros(())}
+    logits = O.wav2vec2_for_ctc(x.double(), p, cfg, drop=drop)
+    T = logits.shape[1]
+    lp = torch.log_softmax(logits, -1).transpose(0, 1)
+    ref_loss = torch.nn.functional.ctc_loss(lp, labels.long(), torch.full((B,), T), (labels != 0).sum(-1), blank=0,
+                                            reduction="sum") / B
+    ref_loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 2e-3 * abs(ref_loss.item())
+    ff1 = "wav2vec2/encoder/layers/1/feed_forward/"
+    for n in ("intermediate_dense/kernel", "intermediate_dense/bias", "output_dense/kernel", "output_dense/bias"):
+        assert trainer.G[ff1 + n].abs().max().item() == 0.0
+    for name in trainer.names:
+        want = p[name].grad
+        if want is None or want.norm().item() < 1e-12:
+            continue
+        assert _rel(trainer.G[name].cpu().double(), want) < 3e-2, name
