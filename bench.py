@@ -111,6 +111,47 @@ def flops_forward(cfg, L):
     return {"convs": convs, "per_layer": per_layer, "other": other, "total": total, "frames": fr}
 
 
+def run_reference_train(args, cfg, params, x, cores, world):
+    """CPU arm of --mode train: forward + CTC + autograd backward + Adam of the oracle port (torch CPU fp32, stage-2
+    trainable set: everything but the conv extractor) on a bounded sample of the step's batch."""
+    import numpy as np
+    from oracle import w2v2_oracle as O
+    names = [k for k in params if "/feature_extractor/" not in k]
+    p = {k: (t.clone().requires_grad_(True) if k in names else t) for k, t in params.items()}
+    opt = torch.optim.Adam([p[k] for k in names], lr=5e-5, eps=1e-7)
+    B = x.shape[0]
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 24)))
+    T = cfg.num_frames(args.seq)
+    steps = max(1, min(args.steps, 2))
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        lp = torch.log_softmax(O.wav2vec2_for_ctc(x, p, cfg), -1).transpose(0, 1)
+        loss = torch.nn.functional.ctc_loss(lp, labels, torch.full((B,), T), torch.full((B,), 24), blank=0, reduction="sum") / B
+        loss.backward()
+        opt.step()
+        return float(loss)
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = B * args.seq / SAMPLE_RATE / dt
+    sample = f"oracle port (torch CPU fp32 autograd + Adam, dropout 0) on {B} x {args.seq} samples per step, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": "audio-sec/s", "value": val, "unit": "audio-sec/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"wav2vec2-base stage-2 CTC fine-tune step (forward + CTC + backward + all-reduce + Adam), "
+                               f"batch={args.batch}/GPU, seq={args.seq}", "global_batch": args.batch * max(world, 1),
+                   "seq_len": args.seq, "note": f"CPU arm: each step is a bounded sample of {B} utterances of that workload"},
+        "cpu_baseline": {"value": val, "unit": "audio-sec/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-sec/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
 def run_reference(args, rank, world):
     """--impl reference: the CPU restatement of the reference path (oracle port; TensorFlow is not installable
     here), all host threads, on a bounded sample of the same workload."""
@@ -124,6 +165,8 @@ def run_reference(args, rank, world):
     params = O.random_params(cfg, seed=0)
     g = torch.Generator().manual_seed(0)
     x = torch.randn(CPU_SAMPLE_BATCH, args.seq, generator=g)
+    if args.mode == "train":
+        return run_reference_train(args, cfg, params, x, cores, world)
     with torch.no_grad():
         for _ in range(min(args.warmup, 1)):
             O.wav2vec2_for_ctc(x, params, cfg)
