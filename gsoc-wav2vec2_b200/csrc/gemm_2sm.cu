@@ -24,7 +24,7 @@ constexpr int GEMM2_REGS_CONTROL = 32, GEMM2_REGS_EPILOGUE = 112;
 template <int EPI>
 struct Gemm2Smem {
   static constexpr bool TMA_RES = (EPI == (EPI_RESID | EPI_F32 | EPI_TMARES));
-  static constexpr int STAGES = TMA_RES ? 4 : GEMM2_STAGES;
+  static constexpr int STAGES = GEMM2_STAGES;
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;           // 16 KB
   static constexpr int B_BYTES = (GEMM2_BLOCK_N / 2) * GEMM_BLOCK_K * 2;     // 16 KB: this CTA's half of the n-tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -35,10 +35,14 @@ struct Gemm2Smem {
   static constexpr int EPI_BYTES = GEMM2_EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int BAR_OFF = EPI_OFF + EPI_BYTES;
   static constexpr int RES_BAR_OFF = BAR_OFF + 128;            // 2 residual-slab barriers per epilogue warp
-  static constexpr int BAR_BYTES = 512;
+  static constexpr int BAR_BYTES = 384;
   static constexpr int BIAS_OFF = BAR_OFF + BAR_BYTES;
-  static constexpr int BIAS_BYTES = 4 * GEMM2_BLOCK_N * 4;     // per accumulator stage: bias slice, then scale slices
-  static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + 1024;
+  // per accumulator stage: bias slice, then scale slices (the residual recipe has no scale: half the space)
+  static constexpr int BIAS_BYTES = (TMA_RES ? 2 : 4) * GEMM2_BLOCK_N * 4;
+  // the double staging blocks of the residual recipe only fit next to the 5-stage ring without alignment slack: that
+  // instance requires (and checks) a 1024-byte aligned dynamic smem base
+  static constexpr int ALIGN_SLACK = TMA_RES ? 0 : 1024;
+  static constexpr int TOTAL = BIAS_OFF + BIAS_BYTES + ALIGN_SLACK;
   static_assert(TOTAL <= 232448, "exceeds the 227 KB of dynamic shared memory per CTA");
 };
 
@@ -250,8 +254,12 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   constexpr int STAGES = S::STAGES;
   constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;  // 512
 
-  extern __shared__ uint8_t smem_raw[];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (S::ALIGN_SLACK == 0) {
+    smem = smem_raw;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();   // SW128 tiles need 1024-byte alignment
+  }
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -520,9 +528,9 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
     if (!gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_F32>(a, s);
     if (!gelu && !res && f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_F32 | EPI_HI | LO>(a, s);
     if (!gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, EPI_HI | LO>(a, s);
-    // short-K tiles (out-proj) cannot hide per-lane residual loads behind the MMAs: TMA-fetched slabs (4-stage ring);
-    // long-K tiles (FFN2) keep the 5-stage ring and the L2-prefetched per-lane loads
-    if (!gelu && res && f32 && !hi && a->N % 64 == 0 && a->K * PASSES <= 1536)
+    // residual slabs fetched by TMA into double staging blocks (W2V2_RES_TMA_MAXK bounds K; default: every K)
+    static const int maxk = [] { const char* e = getenv("W2V2_RES_TMA_MAXK"); return e ? atoi(e) : (1 << 30); }();
+    if (!gelu && res && f32 && !hi && a->N % 64 == 0 && a->K * PASSES <= maxk)
       return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32 | EPI_TMARES>(a, s);
     if (!gelu && res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32>(a, s);
   }
