@@ -69,12 +69,25 @@ def pack_posconv(kern: torch.Tensor, groups: int) -> torch.Tensor:
     return pack_posconv_kernel(kern, groups).to(torch.bfloat16)
 
 
-def pack_posconv_transposed(kern: torch.Tensor, groups: int) -> torch.Tensor:
-    """Taps flipped and in/out channels swapped inside each group: fed to the forward posconv kernel (linear=1, shift=1)
-    this computes the INPUT gradient of the convolution, dx[u] = sum_j W_j^T dpre[u - j + k/2]."""
+def transposed_conv_kernel(kern: torch.Tensor, groups: int) -> torch.Tensor:
+    """TF grouped-conv kernel [k, cin/groups, cout] -> the kernel of its input gradient in the same layout: taps flipped,
+    in/out channels swapped inside each group.  A forward convolution with it, the tap window shifted by one frame
+    (``shift=1``), computes dx[u] = sum_j W_j^T dpre[u - j + k/2]."""
     k, cpg, d = kern.shape
-    kt = kern.reshape(k, cpg, groups, cpg).flip(0).permute(0, 3, 2, 1).reshape(k, cpg, d)
-    return pack_posconv(kt, groups)
+    return kern.reshape(k, cpg, groups, cpg).flip(0).permute(0, 3, 2, 1).reshape(k, cpg, d)
+
+
+def pack_posconv_transposed(kern: torch.Tensor, groups: int) -> torch.Tensor:
+    """``transposed_conv_kernel`` in the posconv kernel's bf16 layout (fed to w2v2_posconv with linear=1, shift=1)."""
+    return pack_posconv(transposed_conv_kernel(kern, groups), groups)
+
+
+def weight_norm_backward(d_kernel: torch.Tensor, weight_v: torch.Tensor, weight_g: torch.Tensor):
+    """Chain rule of Conv1DWithWeightNorm (tensorflow_addons.py:16-21): kernel = g * v / ||v||, the norm taken over axes
+    (1, 2) of every tap with l2_normalize's 1e-12 floor.  Returns (d weight_v, d weight_g)."""
+    nrm = torch.sqrt(torch.clamp(weight_v.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12))
+    dot = (d_kernel * weight_v).sum(dim=(1, 2), keepdim=True)
+    return weight_g / nrm * (d_kernel - weight_v * dot / (nrm * nrm)), dot / nrm
 
 
 class Stage2Trainer:
@@ -395,11 +408,9 @@ class Stage2Trainer:
         dwn = A.get("b.dwn", (ktaps, d // groups, d), f32)
         ops.posconv_wgrad(S["h"].hi, dpc, B, T, d, groups, ktaps, dwn)
         # weight-norm chain rule (tensorflow_addons.py:16-21: W = g * v / ||v||, norm over axes (1, 2) of every tap)
-        wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
-        nrm = torch.sqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12))
-        dot = (dwn * wv).sum(dim=(1, 2), keepdim=True)
-        G[pc + "weight_g"].copy_(dot / nrm)
-        G[pc + "weight_v"].copy_(wg / nrm * (dwn - wv * dot / (nrm * nrm)))
+        dv, dg = weight_norm_backward(dwn, v[pc + "weight_v"], v[pc + "weight_g"])
+        G[pc + "weight_v"].copy_(dv)
+        G[pc + "weight_g"].copy_(dg)
         if S["spec_mask"] is not None:                      # masked frames were replaced by masked_spec_embed (modeling.py:193-199)
             msk = S["spec_mask"]
             G["wav2vec2/masked_spec_embed"].copy_((dh_f32 * msk[:, None]).sum(0))

@@ -160,3 +160,34 @@ def test_ctc_loss_surface():
     if torch.cuda.is_available():
         with pytest.raises(ValueError):
             loss(torch.ones(2, 8, dtype=torch.int32).cuda(), torch.zeros(2, 100, 32).cuda())
+
+
+def test_posconv_backward_host_algebra():
+    """Host-side pieces of the stage-2 backward (wav2vec2/training.py): the kernel of the positional conv's input gradient
+    (flipped taps, in/out swapped per group, window shifted by one frame) and the weight-norm chain rule
+    (tensorflow_addons.py:16-21), both against torch autograd on CPU."""
+    import torch
+    import torch.nn.functional as F
+    from wav2vec2.training import transposed_conv_kernel, weight_norm_backward
+    torch.manual_seed(0)
+    B, T, G, cpg, k = 2, 37, 4, 8, 16
+    d = G * cpg
+    x = torch.randn(B, T, d, dtype=torch.float64, requires_grad=True)
+    wv = torch.randn(k, cpg, d, dtype=torch.float64, requires_grad=True)
+    wg = (1 + 0.3 * torch.rand(k, 1, 1, dtype=torch.float64)).requires_grad_()
+    kern = wv * torch.rsqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12)) * wg   # [k, cin/g, cout]
+
+    def conv(inp, kr, left):           # out[t] = sum_j kr[j] . inp[t + j - left], zero outside [0, T)
+        w = kr.permute(2, 1, 0)        # torch layout [cout, cin/g, k]
+        xp = F.pad(inp.transpose(1, 2), (left, k - 1 - left))
+        return F.conv1d(xp, w, groups=G).transpose(1, 2)
+    pre = conv(x, kern, k // 2)        # encoder.py:177-181: pad k/2 both sides, drop the last frame
+    dpre = torch.randn(B, T, d, dtype=torch.float64)
+    pre.backward(dpre)
+    # input gradient = forward conv of dpre with the transposed kernel, window shifted by one frame (left pad k/2 - 1)
+    dx = conv(dpre, transposed_conv_kernel(kern.detach(), G), k // 2 - 1)
+    assert torch.allclose(dx, x.grad, atol=1e-10)
+    # weight-norm chain rule from the gradient w.r.t. the normalised kernel
+    dkern = torch.autograd.grad(conv(x.detach(), kern, k // 2), kern, dpre)[0]
+    dv, dg = weight_norm_backward(dkern, wv.detach(), wg.detach())
+    assert torch.allclose(dv, wv.grad, atol=1e-10) and torch.allclose(dg, wg.grad, atol=1e-10)
