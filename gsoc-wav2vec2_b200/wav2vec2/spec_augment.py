@@ -14,7 +14,7 @@ def _compute_mask_indices(shape, mask_prob, mask_length, min_masks=2):
     batch_size, seqlen = shape
     if mask_length > seqlen:
         raise ValueError(f"`mask_length` ({mask_length}) must be smaller than `seq_length` ({seqlen}).")
-    num_spans = max(int(mask_prob * (seqlen / mask_length) + np.random.rand(1)), min_masks)
+    num_spans = max(int(mask_prob * (seqlen / mask_length) + float(np.random.rand(1)[0])), min_masks)
     if num_spans * mask_length > seqlen:
         num_spans = seqlen // mask_length
     # gumbel top-k over a uniform distribution == sampling start indices without replacement

@@ -473,3 +473,41 @@ def test_stage2_stochastic_depth_drops_the_ffn_branch():
         if want is None or want.norm().item() < 1e-12:
             continue
         assert _rel(trainer.G[name].cpu().double(), want) < 3e-2, name
+
+
+def test_two_stage_fine_tune_recipe(tmp_path):
+    """src/main.py:192-258 end to end on a tiny model: stage 1 moves only lm_head, stage 2 everything but the conv
+    extractor, the scheduler switches the learning rate, a checkpoint per stage is written and reloads."""
+    import numpy as np
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC
+    from wav2vec2.finetune import FineTuneArgs, fine_tune
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.1, apply_spec_augment=True)
+    m = Wav2Vec2ForCTC(cfg, input_shape=(1, 2048), precision="bf16")
+    m.set_variables(O.random_params(cfg, seed=4))
+    B, L = 2, 16000
+    g = torch.Generator().manual_seed(1)
+    np.random.seed(0)
+    batches = [(torch.randn(B, L, generator=g), torch.from_numpy(np.random.randint(1, 30, size=(B, 10))).int()) for _ in range(3)]
+    before = {k: v.clone() for k, v in m.variables.items()}
+    logs = []
+    args = FineTuneArgs(stage1_lr=1e-3, stage1_epochs=1, stage2_lr1=1e-4, stage2_lr2=5e-5, stage2_transition_epochs=0,
+                        stage2_epochs=2, logging_steps=2, ckpt_path=str(tmp_path / "ckpt"))
+    loss_fn = CTCLoss(cfg, (B, L), division_factor=B)
+    snap = {}
+
+    def log(entry):
+        logs.append(entry)
+        if entry.get("stage") == 1 and "val_loss" in entry:            # end of stage 1
+            snap.update({k: v.clone() for k, v in m.variables.items()})
+    hist = fine_tune(m, loss_fn, lambda: batches, lambda: batches[:1], args, log)
+    assert [h["stage"] for h in hist] == [1, 2, 2] and [h["lr"] for h in hist] == [1e-3, 1e-4, 5e-5]
+    assert all(np.isfinite(h["loss"]) and np.isfinite(h["val_loss"]) for h in hist)
+    body = "wav2vec2/encoder/layers/0/attention/q_proj/kernel"
+    conv = "wav2vec2/feature_extractor/conv_layers/1/conv/kernel"
+    assert not torch.equal(snap["lm_head/kernel"], before["lm_head/kernel"]) and torch.equal(snap[body], before[body])
+    assert not torch.equal(m.variables[body], before[body]) and torch.equal(m.variables[conv], before[conv])
+    m2 = Wav2Vec2ForCTC.from_pretrained(str(tmp_path / "ckpt_stage2"), precision="bf16")
+    x = batches[0][0].cuda()
+    assert torch.equal(m2(x), m(x))
+    assert any("step" in e for e in logs)

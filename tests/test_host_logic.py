@@ -191,3 +191,10 @@ def test_posconv_backward_host_algebra():
     dkern = torch.autograd.grad(conv(x.detach(), kern, k // 2), kern, dpre)[0]
     dv, dg = weight_norm_backward(dkern, wv.detach(), wg.detach())
     assert torch.allclose(dv, wv.grad, atol=1e-10) and torch.allclose(dg, wg.grad, atol=1e-10)
+
+
+def test_stage2_learning_rate_schedule():
+    """training_utils.py:23-25."""
+    from wav2vec2.finetune import FineTuneArgs, stage2_learning_rate
+    a = FineTuneArgs(stage2_lr1=1e-4, stage2_lr2=5e-5, stage2_transition_epochs=2)
+    assert [stage2_learning_rate(e, a) for e in range(5)] == [1e-4, 1e-4, 1e-4, 5e-5, 5e-5]
