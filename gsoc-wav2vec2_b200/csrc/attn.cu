@@ -34,6 +34,9 @@ constexpr int AT_THREADS = 256; // warpgroup 0 (warps 0-3): softmax; warpgroup 1
 constexpr int AT_REGS_SOFTMAX = 208;  // setmaxnreg split (2 CTAs/SM): 128 x 208 + 128 x 40 registers per CTA
 constexpr int AT_REGS_CONTROL = 40;
 constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
+#ifndef AT_P_IN_TMEM
+#define AT_P_IN_TMEM 1   // single-pass mode: keep the probabilities in TMEM (A operand of the PV MMAs) instead of smem
+#endif
 
 template <int PASSES>
 struct AttnSmem {
@@ -64,7 +67,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
                 const AttnParams p) {
   using S = AttnSmem<PASSES>;
   constexpr int KV_STAGES = S::KV_STAGES;
-  constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192)
+  constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192), P (single-pass mode): columns [192,256)
+  constexpr bool P_IN_TMEM = (PASSES == 1) && AT_P_IN_TMEM;
   constexpr float LOG2E = 1.4426950408889634f;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -115,6 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   pdl_trigger();
   pdl_wait();
   const uint32_t tmem_o = tmem_base + 128;
+  const uint32_t tmem_p = tmem_base + 192;
 
   if (warp >= 4) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AT_REGS_CONTROL));
@@ -181,15 +186,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         // ---- O += P V
         mbar_wait(p_full, par);
         tc_fence_after();
-#pragma unroll
-        for (int pass = 0; pass < PASSES; ++pass) {
-          const uint32_t pa = p_addr + ((pass == 1) ? 2 * AT_TILE : 0);
-          const uint32_t va = v_addr + ((pass == 2) ? AT_TILE : 0);
+        if (P_IN_TMEM) {
+          // single-pass mode: P was written to TMEM columns [192, 256) by tcgen05.st (two bf16 per column) and is the A operand
 #pragma unroll
           for (int ks = 0; ks < AT_BN / 16; ++ks) {
-            const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
-            const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
-            umma_f16(tmem_o, dp, dv, idesc_pv, (j | pass | ks) != 0);
+            const uint64_t dv = desc_mnmajor_sw128(v_addr + ks * 2048, 1024, 1024);
+            umma_f16_tmem_a(tmem_o, tmem_p + ks * 8, dv, idesc_pv, (j | ks) != 0);
+          }
+        } else {
+#pragma unroll
+          for (int pass = 0; pass < PASSES; ++pass) {
+            const uint32_t pa = p_addr + ((pass == 1) ? 2 * AT_TILE : 0);
+            const uint32_t va = v_addr + ((pass == 2) ? AT_TILE : 0);
+#pragma unroll
+            for (int ks = 0; ks < AT_BN / 16; ++ks) {
+              const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
+              const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
+              umma_f16(tmem_o, dp, dv, idesc_pv, (j | pass | ks) != 0);
+            }
           }
         }
         umma_commit(pv_done);
@@ -315,22 +329,35 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       }
       // ---- P -> smem (bf16, SW128 K-major image) once the previous PV has consumed the buffer
       mbar_wait(p_empty, par ^ 1);
+      if (P_IN_TMEM) {
+        // P (bf16 pairs) -> TMEM: no smem round trip, no proxy fence; the PV MMAs read it as their A operand
+        tc_fence_after();
+        uint32_t pk[2][32];
 #pragma unroll
-      for (int pc = 0; pc < 4; ++pc) {
-        const uint32_t half_off = (uint32_t)(pc >> 1) * AT_TILE + row_off;
+        for (int c = 0; c < 64; ++c)
+          pk[c >> 5][c & 31] = pack_bf16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]));
+        tmem_st_32x32b_x32(tmem_p + lane_sel, pk[0]);
+        tmem_st_32x32b_x32(tmem_p + lane_sel + 32, pk[1]);
+        tmem_st_wait();
+        tc_fence_before();
+      } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t hi[4], lo[4];
+        for (int pc = 0; pc < 4; ++pc) {
+          const uint32_t half_off = (uint32_t)(pc >> 1) * AT_TILE + row_off;
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            hi[e] = split_bf16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e]);
-          const uint32_t chunk = (uint32_t)((pc & 1) * 4 + q);
-          const uint32_t off = half_off + ((chunk ^ swz) << 4);
-          *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (PASSES == 3) *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int q = 0; q < 4; ++q) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              hi[e] = split_bf16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e]);
+            const uint32_t chunk = (uint32_t)((pc & 1) * 4 + q);
+            const uint32_t off = half_off + ((chunk ^ swz) << 4);
+            *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            if (PASSES == 3) *reinterpret_cast<uint4*>(p_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
         }
+        fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       }
-      fence_proxy_async_smem();   // generic-proxy P writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
     }

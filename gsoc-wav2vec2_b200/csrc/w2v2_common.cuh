@@ -207,6 +207,18 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows = TMEM lanes, K packed two 16-bit elements per
+// 32-bit column) is read from tensor memory - used for O += P V with the probabilities written by tcgen05.st.
+__device__ __forceinline__ void umma_f16_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Same, but the arrive is multicast to the mbarrier at the same offset in every CTA of cta_mask.
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
