@@ -41,12 +41,13 @@ constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
 template <int PASSES>
 struct AttnSmem {
   static constexpr int NPL = (PASSES == 3) ? 2 : 1;         // planes (hi, lo)
-  static constexpr int KV_STAGES = 2;
+  static constexpr bool P_TMEM = (PASSES == 1) && AT_P_IN_TMEM;       // no P buffer in smem: a third K/V stage instead
+  static constexpr int KV_STAGES = P_TMEM ? 3 : 2;
   static constexpr int Q_OFF = 0;
   static constexpr int KV_OFF = Q_OFF + NPL * AT_TILE;
   static constexpr int KV_STAGE_BYTES = 2 * NPL * AT_TILE;  // K and V, each NPL planes
   static constexpr int P_OFF = KV_OFF + KV_STAGES * KV_STAGE_BYTES;
-  static constexpr int P_BYTES = NPL * 2 * AT_TILE;         // [128][128] bf16 = two [128][64] halves per plane
+  static constexpr int P_BYTES = P_TMEM ? 0 : NPL * 2 * AT_TILE;   // [128][128] bf16 = two [128][64] halves per plane
   static constexpr int BAR_OFF = P_OFF + P_BYTES;
   static constexpr int TOTAL = BAR_OFF + 128;   // 2 x (TOTAL + 1 KB reserved) must fit in 228 KB
 };
@@ -76,14 +77,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   if ((smem_u32(smem) & 1023u) != 0) __trap();  // SW128 tiles need 1024-byte alignment (no slack is reserved)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;             // [KV_STAGES]
-  uint64_t* kv_empty = bars + 3;            // [KV_STAGES]
-  uint64_t* s_full = bars + 5;
-  uint64_t* s_empty = bars + 6;
-  uint64_t* p_full = bars + 7;
-  uint64_t* p_empty = bars + 8;
-  uint64_t* pv_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* kv_full = bars + 1;             // [KV_STAGES <= 3]
+  uint64_t* kv_empty = bars + 4;            // [KV_STAGES <= 3]
+  uint64_t* s_full = bars + 7;
+  uint64_t* s_empty = bars + 8;
+  uint64_t* p_full = bars + 9;
+  uint64_t* p_empty = bars + 10;
+  uint64_t* pv_done = bars + 11;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
@@ -168,20 +169,21 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         }
         umma_commit(s_full);
       };
-      // kv stage of chunk j is j % 2 with phase (j / 2) & 1
+      // kv stage of chunk j is j % KV_STAGES with phase (j / KV_STAGES) & 1
       mbar_wait(&kv_full[0], 0);
       tc_fence_after();
       issue_qk(0);
       for (int j = 0; j < nchunks; ++j) {
         const uint32_t par = j & 1;
-        const int stage = j & 1;
+        const int stage = j % KV_STAGES;
         const uint32_t v_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES) + S::NPL * AT_TILE;
         if (j + 1 < nchunks) {
           // S(j) has been copied to registers -> overwrite it with Q K(j+1)^T while the softmax math runs
-          mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+          const int nstage = (j + 1) % KV_STAGES;
+          mbar_wait(&kv_full[nstage], ((j + 1) / KV_STAGES) & 1);
           mbar_wait(s_empty, par);
           tc_fence_after();
-          issue_qk((j + 1) & 1);
+          issue_qk(nstage);
         }
         // ---- O += P V
         mbar_wait(p_full, par);
