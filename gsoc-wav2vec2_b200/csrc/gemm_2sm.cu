@@ -100,6 +100,13 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   }
   if (rows_valid <= 0 || n >= p.N) return;
   const size_t orow0 = (size_t)b * p.rows_per_batch + t_warp0;
+  const bool f_ln = f_res && p.ln_stats != nullptr;
+  float ln_mean = 0.0f, ln_rstd = 0.0f;
+  if (f_ln && lane < rows_valid) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow0 + lane);
+    ln_mean = st.x;
+    ln_rstd = st.y;
+  }
 
   if constexpr (Gemm2Smem<EPI>::TMA_RES) {
     // out = acc + bias + residual, fp32.  Slab q (16 columns, 64-byte rows) of the residual was TMA-loaded into block
@@ -114,7 +121,8 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
       mbar_wait(&res_bar[q & 1], (uint32_t)(q >> 1));   // each barrier completes exactly twice per tile
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 rr = *reinterpret_cast<const float4*>(bslot(j));
+        float4 rr = *reinterpret_cast<const float4*>(bslot(j));
+        if (f_ln) rr = ln_of_residual(rr, ln_mean, ln_rstd, p.ln_gamma, p.ln_beta, n0 + c0 + 4 * j);
         const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
         float4 o;
         o.x = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x + rr.x;
@@ -166,7 +174,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
       // this row's 64-byte residual slab (pulled into L2 by the per-tile prefetch)
       const float4* gres = reinterpret_cast<const float4*>(p.residual + (orow0 + lane) * p.N + n0 + c0);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) rr[j] = __ldg(gres + j);
+      for (int j = 0; j < 4; ++j) {
+        rr[j] = __ldg(gres + j);
+        if (f_ln) rr[j] = ln_of_residual(rr[j], ln_mean, ln_rstd, p.ln_gamma, p.ln_beta, n0 + c0 + 4 * j);
+      }
     }
     float v[16];
 #pragma unroll

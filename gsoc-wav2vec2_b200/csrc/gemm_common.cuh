@@ -36,11 +36,23 @@ struct GemmParams {
   const float* scale;     // optional per-column scale applied before the bias, [N] or [batch][N]
   int bias_bstride;       // elements between batch entries of bias / scale (0 = shared)
   const float* residual;  // fp32 [batch*rows_per_batch, N] or null
+  const float* ln_stats;  // optional [rows][2] (mean, rstd): the residual term is LayerNorm(residual) recomputed on the fly
+  const float* ln_gamma;  // [N]
+  const float* ln_beta;   // [N]
   const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
   float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
 };
+
+// residual term "LayerNorm(r)" with the statistics written by w2v2_ln_rows_stats: the SAME expression as ln_rows_kernel, so
+// the value is bit-identical to the fp32 LayerNorm output it replaces
+__device__ __forceinline__ float4 ln_of_residual(float4 r, float mean, float rstd, const float* gamma, const float* beta, int col) {
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
+  return make_float4(fmaf((r.x - mean) * rstd, g.x, b.x), fmaf((r.y - mean) * rstd, g.y, b.y),
+                     fmaf((r.z - mean) * rstd, g.z, b.z), fmaf((r.w - mean) * rstd, g.w, b.w));
+}
 
 // Epilogue of one 128 x BLOCK_N accumulator tile for one warp (32 rows; lane = row).  The two warps that share a
 // TMEM lane quadrant take alternate PAIRS of 32-column chunks (grp = 0 / 1).
@@ -88,6 +100,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   if (rows_valid <= 0) return;
   const bool row_ok = lane < rows_valid;
   const size_t orow0 = orow - lane;  // first row of this warp's block
+  const bool f_ln = f_res && p.ln_stats != nullptr;
+  float ln_mean = 0.0f, ln_rstd = 0.0f;
+  if (f_ln && row_ok) {
+    const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
+    ln_mean = st.x;
+    ln_rstd = st.y;
+  }
 
   // staged 32 x 128 B block -> global, 8 lanes per row (PIECES = 8) or 4 lanes per row (PIECES = 4: 64-byte rows)
   auto flush = [&](uint8_t* gbase, size_t row_stride_bytes, int pieces) {
@@ -156,6 +175,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           const size_t off = orow * p.N + n + 16 * hf;
 #pragma unroll
           for (int j = 0; j < 16; ++j) rf[j] = (row_ok && n + 16 * hf + j < p.N) ? __ldg(p.residual + off + j) : 0.0f;
+        }
+        if (f_ln) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n + 16 * hf + j;
+            if (col < p.N) rf[j] = fmaf((rf[j] - ln_mean) * ln_rstd, __ldg(p.ln_gamma + col), __ldg(p.ln_beta + col));
+          }
         }
       }
       float v[16];

@@ -278,6 +278,9 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.scale = a->scale;
   p.bias_bstride = a->bias_batch_stride;
   p.residual = a->residual;
+  p.ln_stats = a->res_ln_stats;
+  p.ln_gamma = a->res_ln_gamma;
+  p.ln_beta = a->res_ln_beta;
   p.row_valid = a->row_valid;
   p.out_f32 = a->out_f32;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
@@ -345,6 +348,8 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   W2V2_CHECK_ARG(a->a_row_len >= a->K || a->kb_split > 0, "a_row_len must cover K");
   W2V2_CHECK_ARG(a->out_f32 || a->out_hi, "at least one output is required");
   W2V2_CHECK_ARG(a->out_lo == nullptr || a->out_hi != nullptr, "out_lo requires out_hi");
+  W2V2_CHECK_ARG(a->res_ln_stats == nullptr || (a->residual && a->res_ln_gamma && a->res_ln_beta && a->N % 4 == 0),
+                 "res_ln_stats needs residual, res_ln_gamma, res_ln_beta and N % 4 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
   if (bn == 0) bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;

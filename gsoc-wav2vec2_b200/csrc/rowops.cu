@@ -241,7 +241,7 @@ template <int MAXV>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                int rows, int d, int gelu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-               __nv_bfloat16* __restrict__ out_lo) {
+               __nv_bfloat16* __restrict__ out_lo, float* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -271,6 +271,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
     }
   }
   const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+  if (stats != nullptr && lane == 0) *reinterpret_cast<float2*>(stats + 2 * (size_t)row) = make_float2(mean, rstd);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
@@ -424,9 +425,14 @@ extern "C" int w2v2_conv0(const float* wave, int batch, int num_samples, int cha
 
 extern "C" int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
                             int gelu, float* out_f32, void* out_hi, void* out_lo, void* stream) {
+  return w2v2_ln_rows_stats(x, gamma, beta, eps, rows, d, gelu, out_f32, out_hi, out_lo, nullptr, stream);
+}
+
+extern "C" int w2v2_ln_rows_stats(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
+                                  int gelu, float* out_f32, void* out_hi, void* out_lo, float* stats, void* stream) {
   W2V2_CHECK_ARG(x && gamma && beta, "null pointer");
   W2V2_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 2048, "d must be a multiple of 4, at most 2048");
-  W2V2_CHECK_ARG(out_f32 || out_hi, "at least one output");
+  W2V2_CHECK_ARG(out_f32 || out_hi || stats, "at least one output");
   W2V2_CHECK_ARG(out_lo == nullptr || out_hi != nullptr, "out_lo requires out_hi");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -434,9 +440,9 @@ extern "C" int w2v2_ln_rows(const float* x, const float* gamma, const float* bet
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   if (d <= 1024)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
   else
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
   return 0;
 }
 

@@ -28,6 +28,7 @@ class GemmArgs(C.Structure):
         ("bias", C.c_void_p), ("scale", C.c_void_p), ("bias_batch_stride", C.c_int64),
         ("residual", C.c_void_p), ("row_valid", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
+        ("res_ln_stats", C.c_void_p), ("res_ln_gamma", C.c_void_p), ("res_ln_beta", C.c_void_p),
     ]
 
 
@@ -57,6 +58,7 @@ SIGNATURES = {
     "w2v2_conv0_gn_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
+    "w2v2_ln_rows_stats": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _P],
     "w2v2_normalize_utterances": [_P, _P, _I, _I, _F, _P, _P],
     "w2v2_split_bf16": [_P, _L, _P, _P, _P],
     "w2v2_attn_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],

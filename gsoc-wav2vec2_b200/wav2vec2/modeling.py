@@ -421,16 +421,24 @@ class _B200Model:
                     cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes)
         xs_f32 = A.get("x.f32", (M, d), f32)      # residual stream
         xs = A.pair("x", (M, d), lo)              # GEMM operand view of the (normalised) stream
+        st = res_ln = None
         if pre:
             xs_f32, y = y, xs_f32                 # stream = h + posconv(h); LN happens inside the layers
         else:
-            ops.ln_rows(y, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=xs_f32,
-                        out_hi=xs.hi, out_lo=xs.lo)
+            # Post-norm: the residual of every block is a LayerNorm OUTPUT.  It is never materialised in fp32: each LayerNorm
+            # writes its bf16 GEMM operand plus (mean, rstd) per row, and the next residual GEMM recomputes LN(y) from the
+            # pre-norm sum `y` in its epilogue (bit-identical arithmetic) and overwrites `y` in place with the new sum.
+            st = A.get("ln.stats", (M, 2), f32)
+            g0, b0 = v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"]
+            ops.ln_rows(y, g0, b0, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st)
+            res_ln = (st, g0, b0)
         qkv = A.pair("qkv", (M, 3 * d), lo)
         ctx = A.pair("ctx", (M, d), lo)
         mid = A.pair("mid", (M, cfg.intermediate_size), lo)
-        x1_f32 = A.get("x1.f32", (M, d), f32)
+        x1_f32 = A.get("x1.f32", (M, d), f32) if pre else None
         H, dh, ffn = cfg.num_heads, cfg.head_size, cfg.intermediate_size
+        if not pre and cfg.num_layers == 0:
+            ops.ln_rows(y, res_ln[1], res_ln[2], eps, M, d, out_f32=xs_f32)
         for i in range(cfg.num_layers):
             lb = f"{enc}layers/{i}/"
             g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
@@ -446,9 +454,11 @@ class _B200Model:
                          residual=xs_f32, out_f32=x1_f32, passes=passes)
                 ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo)
             else:
+                # y <- LN(y) + out_proj(ctx);  x1 = LN1(y) as bf16 operand + row statistics
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
-                         residual=xs_f32, out_f32=y, passes=passes)
-                ops.ln_rows(y, g1, b1, eps, M, d, out_f32=x1_f32, out_hi=xs.hi, out_lo=xs.lo)
+                         residual=y, res_ln=res_ln, out_f32=y, passes=passes)
+                ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st)
+                res_ln = (st, g1, b1)
             ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M,
                      bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, out_hi=mid.hi, out_lo=mid.lo,
                      passes=passes)
@@ -456,9 +466,13 @@ class _B200Model:
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
                          bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=xs_f32, passes=passes)
             else:
+                # y <- LN1(y) + FFN(x1);  the last layer's LayerNorm also writes the fp32 hidden states
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
-                         bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=y, passes=passes)
-                ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32, out_hi=xs.hi, out_lo=xs.lo)
+                         bias=v[lb + "feed_forward/output_dense/bias"], residual=y, res_ln=res_ln, out_f32=y, passes=passes)
+                last = i == cfg.num_layers - 1
+                ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32 if last else None, out_hi=xs.hi, out_lo=xs.lo,
+                            stats=None if last else st)
+                res_ln = (st, g2, b2)
         if pre:
             out_f32 = A.get("enc.out", (M, d), f32)
             ops.ln_rows(xs_f32, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=out_f32,

@@ -58,8 +58,10 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          a_row_len: Optional[int] = None, a_rows: Optional[int] = None, a_row_stride: Optional[int] = None,
          a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
          row_valid=None, gelu=False,
-         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0):
-    """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major."""
+         out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
+         res_ln=None):
+    """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
+    ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
     args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if passes == 3 else None
@@ -75,6 +77,9 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
+    if res_ln is not None:
+        _need_cuda(*res_ln)
+        args.res_ln_stats, args.res_ln_gamma, args.res_ln_beta = (_ptr(t) for t in res_ln)
     _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
 
 
@@ -125,10 +130,11 @@ def normalize_utterances(wave, lengths=None, eps=1e-5, out=None):
     return out
 
 
-def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None):
-    _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo)
-    _count(); _lib.check(_lib.load().w2v2_ln_rows(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,
-                                        _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _stream()), "w2v2_ln_rows")
+def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None, stats=None):
+    """``stats`` [rows, 2] fp32 (optional) receives (mean, rstd) per row for ``gemm(..., res_ln=(stats, gamma, beta))``."""
+    _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo, stats)
+    _count(); _lib.check(_lib.load().w2v2_ln_rows_stats(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,
+                                              _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(stats), _stream()), "w2v2_ln_rows")
 
 
 def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1):

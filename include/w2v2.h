@@ -71,6 +71,12 @@ typedef struct w2v2_gemm_args {
   float* out_f32;          /* any subset of the three outputs; out_lo requires out_hi */
   void* out_hi;
   void* out_lo;
+  /* optional: the residual term is LayerNorm(residual) recomputed on the fly, fmaf((r - mean) * rstd, gamma, beta) with the
+   * per-row (mean, rstd) that w2v2_ln_rows wrote to `stats` - so a post-norm layer never materialises the fp32 LayerNorm
+   * output: x1 = LN(y) is consumed as bf16 by the next GEMM and as "LN(y)" by the next residual add (encoder.py:119-132). */
+  const float* res_ln_stats;  /* [batch*rows_per_batch][2] or NULL */
+  const float* res_ln_gamma;  /* [N] */
+  const float* res_ln_beta;   /* [N] */
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
@@ -111,6 +117,9 @@ int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, cons
  * 116,121,126,132,232-234,268,275 and feature_extractor.py:50,86-88,93. */
 int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
                  float* out_f32, void* out_hi, void* out_lo, void* stream);
+/* same, additionally writing the per-row (mean, rstd) to stats[rows][2] (see w2v2_gemm_args.res_ln_stats) */
+int w2v2_ln_rows_stats(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
+                       float* out_f32, void* out_hi, void* out_lo, float* stats, void* stream);
 
 /* Wav2Vec2Processor._normalize (processor.py:101-106) on the device: per utterance (x - mean) / sqrt(var + eps) with the
  * biased variance over its lengths[b] real samples (NULL: all num_samples); the padded tail is written as 0

@@ -331,3 +331,26 @@ def test_processor_normalize_on_device_matches_golden():
         ref = torch.from_numpy(O.normalize_utterance(batch[b, :n].numpy()))
         assert (out[b, :n] - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
         assert torch.all(out[b, n:] == 0)
+
+
+@pytest.mark.parametrize("M,K,N,cluster", [(128 * 9 + 17, 768, 768, 0), (300, 3072, 768, 0), (98, 768, 768, 1), (257, 256, 192, 1)])
+def test_gemm_residual_is_layernorm_recomputed(M, K, N, cluster):
+    """w2v2_gemm_args.res_ln_*: out = A W^T + bias + LayerNorm(residual) with the (mean, rstd) of w2v2_ln_rows_stats, also IN PLACE
+    (out == residual), in the 2-SM kernel (TMA-fetched and per-lane residual paths) and the 1-SM kernel."""
+    torch.manual_seed(11)
+    a = _pair(torch.randn(M, K, device=DEV), False)
+    w = _pair(torch.randn(N, K, device=DEV) / K ** 0.5, False)
+    bias = torch.randn(N, device=DEV)
+    y = torch.randn(M, N, device=DEV) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * torch.randn(N, device=DEV), 0.1 * torch.randn(N, device=DEV)
+    ln_f32 = torch.empty(M, N, device=DEV)
+    stats = torch.empty(M, 2, device=DEV)
+    ops.ln_rows(y, gamma, beta, 1e-5, M, N, out_f32=ln_f32, stats=stats)
+    want = torch.empty(M, N, device=DEV)
+    ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, residual=ln_f32, out_f32=want, cluster=cluster)
+    got = y.clone()
+    ops.gemm(a, w, K=K, N=N, rows_per_batch=M, bias=bias, residual=got, res_ln=(stats, gamma, beta), out_f32=got, cluster=cluster)
+    torch.cuda.synchronize()
+    mean, var = y.mean(-1), y.var(-1, unbiased=False)
+    assert (stats[:, 0] - mean).abs().max().item() < 1e-5 and (stats[:, 1] - torch.rsqrt(var + 1e-5)).abs().max().item() < 1e-4
+    assert torch.equal(got, want)              # same arithmetic as the LayerNorm kernel: bit-identical
