@@ -164,3 +164,25 @@ def test_cuda_graph_replay_is_bit_identical():
     assert torch.equal(m(x2, attention_mask=am), eager2)      # replay with new data in the static input buffer
     assert torch.equal(m(x1, attention_mask=am), eager1)
     assert len(m._graphs) == 1
+
+
+@pytest.mark.parametrize("L,B", [(400, 1), (719, 3), (1039, 5), (5000, 2)])
+def test_tiny_and_ragged_inputs_match_oracle(L, B):
+    """Edge shapes: the shortest waveform the extractor accepts (400 samples -> ONE frame), 1 / 2 / 3 frames, odd batch sizes,
+    every kernel running a single ragged tile."""
+    cfg = Wav2Vec2Config(num_layers=2)
+    m, params = _build(Wav2Vec2ForCTC, cfg, "bf16x3")
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(L))
+    got = m(x.cuda()).cpu()
+    ref = O.wav2vec2_for_ctc(x, params, cfg)
+    assert got.shape == ref.shape == (B, cfg.num_frames(L), cfg.vocab_size)
+    err = (got - ref).abs().max().item()
+    print(f"L={L} B={B}: {ref.shape[1]} frames, logits max-abs err {err:.3e}")
+    assert err < 1e-3
+
+
+def test_too_short_input_raises():
+    cfg = Wav2Vec2Config(num_layers=1)
+    m, _ = _build(Wav2Vec2ForCTC, cfg, "bf16")
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 399).cuda())
