@@ -91,3 +91,60 @@ extern "C" int w2v2_adam(float* weights, const float* grads, float* m, float* v,
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }
+
+// ------------------------------------------------------------------------------------ batched weight re-packing
+// After every optimizer step the fp32 master weights (one flat buffer) must be re-expressed in the kernels' operand
+// layouts: forward GEMMs want W[out][in] bf16 (the transpose of the TF Dense kernel, q rows pre-scaled by dh^-1/2,
+// q/k/v fused), the dgrad GEMMs want the TF kernel itself as bf16 (q/k/v side by side).  Done tensor by tensor from the
+// host this is ~270 tiny launches (1.5 ms per step); here it is ONE launch over a job table that never changes
+// (w2v2_pack_weights).  A job copies a [rows x cols] fp32 matrix to a bf16 (or fp32) destination with its own leading
+// dimension, optionally transposed, optionally scaled; tiles of 64 x 64 go through shared memory.
+namespace w2v2 {
+
+struct PackTile {
+  int job, r0, c0;
+};
+
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const w2v2_pack_job* __restrict__ jobs, const PackTile* __restrict__ tiles) {
+  __shared__ float tile[64][65];
+  const PackTile t = tiles[blockIdx.x];
+  const w2v2_pack_job j = jobs[t.job];
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;   // 64 x 4
+  const float* src = reinterpret_cast<const float*>(j.src);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = t.r0 + ty + 4 * i, c = t.c0 + tx;
+    tile[ty + 4 * i][tx] = (r < j.rows && c < j.cols) ? src[(size_t)r * j.src_ld + c] * j.scale : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    // destination element (dr, dc): transposed jobs write dst[c][r], plain jobs dst[r][c]; tx runs along the dst row
+    int sr, sc, dr, dc;
+    if (j.transpose) {
+      sc = ty + 4 * i; sr = tx;                // dst row = source column
+      dr = t.c0 + sc; dc = t.r0 + sr;
+      if (dr >= j.cols || dc >= j.rows) continue;
+    } else {
+      sr = ty + 4 * i; sc = tx;
+      dr = t.r0 + sr; dc = t.c0 + sc;
+      if (dr >= j.rows || dc >= j.cols) continue;
+    }
+    const float v = tile[sr][sc];
+    const size_t o = (size_t)dr * j.dst_ld + dc;
+    if (j.dst_f32) reinterpret_cast<float*>(j.dst)[o] = v;
+    else reinterpret_cast<__nv_bfloat16*>(j.dst)[o] = __float2bfloat16_rn(v);
+  }
+}
+
+}  // namespace w2v2
+
+extern "C" int w2v2_pack_weights(const w2v2_pack_job* jobs_dev, const int32_t* tiles_dev, int num_tiles, void* stream) {
+  W2V2_CHECK_ARG(jobs_dev && tiles_dev, "null pointer");
+  if (num_tiles <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  pack_weights_kernel<<<num_tiles, 256, 0, s>>>(jobs_dev, reinterpret_cast<const PackTile*>(tiles_dev));
+  W2V2_CUDA(cudaGetLastError());
+  return 0;
+}

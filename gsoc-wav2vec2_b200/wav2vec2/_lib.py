@@ -43,6 +43,13 @@ class PosconvArgs(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    """Mirror of ``w2v2_pack_job`` (include/w2v2.h)."""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("rows", C.c_int32), ("cols", C.c_int32), ("src_ld", C.c_int32),
+                ("dst_ld", C.c_int32), ("transpose", C.c_int32), ("dst_f32", C.c_int32), ("scale", C.c_float),
+                ("reserved", C.c_int32)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
 _U64, _U32 = C.c_uint64, C.c_uint32
 
@@ -68,6 +75,7 @@ SIGNATURES = {
     "w2v2_frame_argmax": [_P, _L, _I, _P, _P],
     "w2v2_lm_head_wgrad": [_P, _P, _L, _I, _I, _P, _P, _P],
     "w2v2_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _P],
+    "w2v2_pack_weights": [_P, _P, _I, _P],
     "w2v2_ln_bwd": [_P, _P, _P, _F, _L, _I, _P, _P, _P, _P, _P, _P],
     "w2v2_gelu_rows": [_P, _L, _I, _P, _P, _F, _U64, _U32, _P],
     "w2v2_dact_colsum": [_P, _P, _L, _I, _P, _P, _F, _U64, _U32, _P],

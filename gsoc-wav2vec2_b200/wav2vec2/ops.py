@@ -285,3 +285,9 @@ def posconv_wgrad(x_hi, dpre_hi, B, T, d, groups, ktaps, grad_kernel):
     _need_cuda(x_hi, dpre_hi, grad_kernel)
     _count(); _lib.check(_lib.load().w2v2_posconv_wgrad(_ptr(x_hi), _ptr(dpre_hi), B, T, d, groups, ktaps, _ptr(grad_kernel),
                                               _stream()), "w2v2_posconv_wgrad")
+
+
+def pack_weights(jobs_dev, tiles_dev, num_tiles):
+    """ONE launch re-packing every updated weight (job / tile tables built once by training.Stage2Trainer)."""
+    _need_cuda(jobs_dev, tiles_dev)
+    _count(); _lib.check(_lib.load().w2v2_pack_weights(_ptr(jobs_dev), _ptr(tiles_dev), int(num_tiles), _stream()), "w2v2_pack_weights")

@@ -182,8 +182,8 @@ class Stage2Trainer:
         W = {"proj": Pair(v["wav2vec2/feature_projection/projection/kernel"].to(bf))}
         pc = "wav2vec2/encoder/pos_conv_embed/conv/"
         wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
-        nrm = torch.sqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12))
-        W["pos.T"] = Pair(pack_posconv_transposed(wv / nrm * wg, cfg.num_conv_pos_embedding_groups))
+        kern = wv * torch.rsqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12)) * wg
+        W["pos.T"] = Pair(pack_posconv_transposed(kern, cfg.num_conv_pos_embedding_groups))
         for i in range(cfg.num_layers):
             a = f"wav2vec2/encoder/layers/{i}/attention/"
             f = f"wav2vec2/encoder/layers/{i}/feed_forward/"
@@ -193,6 +193,80 @@ class Stage2Trainer:
             W[f"l{i}.ff2"] = Pair(v[f + "output_dense/kernel"].to(bf))
         self._wt = W
         return W
+
+    # ------------------------------------------------------------------ one-launch re-packing after the optimizer step
+    def _build_pack_jobs(self):
+        """Job / tile tables of w2v2_pack_weights: every trainable Dense kernel -> its forward operand (transposed, q rows
+        scaled, q/k/v fused) and its dgrad operand (the TF kernel as bf16).  The tables are static: variables are views
+        of ``flat_w`` and the packed operands are persistent tensors that are overwritten in place."""
+        import ctypes as C
+
+        import numpy as np
+
+        from ._lib import PackJob
+        m, v, cfg = self.model, self.model.variables, self.model.config
+        P, W = m._packed, self._wt
+        d = cfg.hidden_size
+        scale = cfg.head_size ** (-0.5)
+        jobs = []
+
+        def job(src, dst, dst_off, rows, cols, dst_ld, transpose, s=1.0, f32=False):
+            esz = 4 if f32 else 2
+            jobs.append(PackJob(src.data_ptr(), dst.data_ptr() + dst_off * esz, rows, cols, cols, dst_ld, int(transpose),
+                                int(f32), float(s), 0))
+        fp = "wav2vec2/feature_projection/projection/kernel"
+        Cl = v[fp].shape[0]
+        job(v[fp], P["proj.w"].hi, 0, Cl, d, Cl, True)
+        job(v[fp], W["proj"].hi, 0, Cl, d, d, False)
+        for i in range(cfg.num_layers):
+            a = f"wav2vec2/encoder/layers/{i}/attention/"
+            f = f"wav2vec2/encoder/layers/{i}/feed_forward/"
+            ff = v[f + "intermediate_dense/kernel"].shape[1]
+            for j, n in enumerate(("q", "k", "v")):
+                sc = scale if n == "q" else 1.0
+                job(v[a + f"{n}_proj/kernel"], P[f"l{i}.qkv.w"].hi, j * d * d, d, d, d, True, sc)
+                job(v[a + f"{n}_proj/bias"], P[f"l{i}.qkv.b"], j * d, 1, d, d, False, sc, f32=True)
+                job(v[a + f"{n}_proj/kernel"], W[f"l{i}.qkv"].hi, j * d, d, d, 3 * d, False)
+            job(v[a + "out_proj/kernel"], P[f"l{i}.out.w"].hi, 0, d, d, d, True)
+            job(v[a + "out_proj/kernel"], W[f"l{i}.out"].hi, 0, d, d, d, False)
+            job(v[f + "intermediate_dense/kernel"], P[f"l{i}.ff1.w"].hi, 0, d, ff, d, True)
+            job(v[f + "intermediate_dense/kernel"], W[f"l{i}.ff1"].hi, 0, d, ff, ff, False)
+            job(v[f + "output_dense/kernel"], P[f"l{i}.ff2.w"].hi, 0, ff, d, ff, True)
+            job(v[f + "output_dense/kernel"], W[f"l{i}.ff2"].hi, 0, ff, d, d, False)
+        V = v["lm_head/kernel"].shape[1]
+        job(v["lm_head/kernel"], P["lm.w"].hi, 0, d, V, d, True)
+        tiles = []
+        for ji, jb in enumerate(jobs):
+            rr, cc = np.meshgrid(np.arange(0, jb.rows, 64), np.arange(0, jb.cols, 64), indexing="ij")
+            tiles.append(np.stack([np.full(rr.size, ji), rr.ravel(), cc.ravel()], 1))
+        tiles = np.concatenate(tiles).astype(np.int32)
+        raw = (PackJob * len(jobs))(*jobs)
+        jobs_dev = torch.frombuffer(bytearray(bytes(raw)), dtype=torch.uint8).to(m.device)
+        self._pack_tables = (jobs_dev, torch.from_numpy(tiles).to(m.device), int(tiles.shape[0]))
+        self._pack_refs = (P, W)                      # the packed tensors the job table points into stay alive
+
+    def _repack(self):
+        """Kernel-layout copies follow the optimizer step: one w2v2_pack_weights launch for every Dense kernel, host torch
+        algebra for the weight-normalised positional conv (4.7 M parameters)."""
+        model = self.model
+        if _PRECISIONS[model.precision] != 1 or os.environ.get("W2V2_TORCH_REPACK", "0") == "1":
+            model._packed = None                      # split-bf16 (hi + lo) operands: re-packed by the host at the next forward
+            self._wt = None
+            return
+        if model._packed is None:
+            model._pack()
+        if self._wt is None:
+            self._pack_backward()
+        if getattr(self, "_pack_tables", None) is None or self._pack_refs[0] is not model._packed or self._pack_refs[1] is not self._wt:
+            self._build_pack_jobs()
+        ops.pack_weights(*self._pack_tables)
+        cfg, v = model.config, model.variables
+        pc = "wav2vec2/encoder/pos_conv_embed/conv/"
+        wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]
+        kern = wv * torch.rsqrt(torch.clamp(wv.pow(2).sum(dim=(1, 2), keepdim=True), min=1e-12)) * wg
+        G_ = cfg.num_conv_pos_embedding_groups
+        model._packed["pos.w"].hi.copy_(pack_posconv(kern, G_))
+        self._wt["pos.T"].hi.copy_(pack_posconv_transposed(kern, G_))
 
     # ------------------------------------------------------------------ forward keeping what the backward needs
     def _forward(self, speech, spec_mask=None, layer_keep=None):
@@ -446,6 +520,5 @@ class Stage2Trainer:
         self.t += 1
         lr_t = self.lr * (1.0 - self.b2 ** self.t) ** 0.5 / (1.0 - self.b1 ** self.t)
         ops.adam(self.flat_w, self.flat_g, self.m, self.v, lr_t, self.b1, self.b2, self.eps)
-        self.model._packed = None          # kernel-layout copies follow the update at the next forward
-        self._wt = None
+        self._repack()                     # kernel-layout copies follow the update
         return loss

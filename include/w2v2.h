@@ -246,6 +246,20 @@ int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int batch, int f
 int w2v2_posconv_wgrad(const void* x_hi, const void* dpre_hi, int batch, int frames, int hidden, int groups, int ktaps,
                        float* grad_kernel, void* stream);
 
+/* Re-packing of the updated fp32 master weights into the kernels' operand layouts, ONE launch per optimizer step.
+ * jobs_dev: device array of jobs; tiles_dev: device array of int32 triples (job index, first row, first column) - one
+ * 64 x 64 tile per CTA.  Both tables are built once by the host (the pointers never change: the variables are views of
+ * one flat buffer and the packed operands are persistent). */
+typedef struct w2v2_pack_job {
+  const void* src;       /* fp32 [rows][src_ld] */
+  void* dst;             /* bf16 (or fp32 when dst_f32) with leading dimension dst_ld; transposed jobs write dst[c][r] */
+  int32_t rows, cols, src_ld, dst_ld;
+  int32_t transpose, dst_f32;
+  float scale;
+  int32_t reserved;
+} w2v2_pack_job;
+int w2v2_pack_weights(const w2v2_pack_job* jobs_dev, const int32_t* tiles_dev, int num_tiles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -511,3 +511,33 @@ def test_two_stage_fine_tune_recipe(tmp_path):
     x = batches[0][0].cuda()
     assert torch.equal(m2(x), m(x))
     assert any("step" in e for e in logs)
+
+
+def test_one_launch_weight_repack_equals_host_packing():
+    """w2v2_pack_weights (one launch after the optimizer step) reproduces, bit for bit, the operand layouts the host packs
+    with torch ops at load time: forward operands (transposed, q rows scaled, q/k/v fused, biases) and dgrad operands."""
+    import numpy as np
+    from oracle import w2v2_oracle as O
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC
+    from wav2vec2.training import Stage2Trainer
+    cfg = Wav2Vec2Config(num_layers=2, dropout=0.0, apply_spec_augment=False)
+    m = Wav2Vec2ForCTC(cfg, input_shape=(1, 2048), precision="bf16")
+    m.set_variables(O.random_params(cfg, seed=4))
+    B, L = 2, 16000
+    x = torch.randn(B, L, generator=torch.Generator().manual_seed(1)).cuda()
+    np.random.seed(0)
+    labels = torch.from_numpy(np.random.randint(1, 30, size=(B, 10))).int().cuda()
+    tr = Stage2Trainer(m, CTCLoss(cfg, (B, L), division_factor=B), learning_rate=1e-3)
+    for _ in range(2):
+        tr.step(x, labels)
+    assert getattr(tr, "_pack_tables", None) is not None            # the fast path ran
+    fast_P = {k: (t.hi.clone() if hasattr(t, "hi") else t.clone()) for k, t in m._packed.items()}
+    fast_W = {k: t.hi.clone() for k, t in tr._wt.items()}
+    m._packed = None
+    tr._wt = None
+    P, W = m._pack(), tr._pack_backward()
+    for k, t in P.items():
+        ref = t.hi if hasattr(t, "hi") else t
+        assert torch.equal(fast_P[k], ref), k
+    for k, t in W.items():
+        assert torch.equal(fast_W[k], t.hi), k
