@@ -377,4 +377,4 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
 }
 
 extern "C" const char* w2v2_last_error_string(void) { return w2v2::g_last_error; }
-extern "C" int w2v2_version(void) { return 100; }
+extern "C" int w2v2_version(void) { return 120; }   // 1.2: training entry points, res_ln_* in w2v2_gemm_args, dropout

@@ -36,7 +36,8 @@ const char* w2v2_last_error_string(void);
  * tf.keras.layers.Conv1D for extractor layers 1..6 at feature_extractor.py:31-37,55 as an implicit
  * GEMM (A rows = overlapping k*Cin windows of the channels-last input).
  * ------------------------------------------------------------------------------------------- */
-#define W2V2_GEMM_GELU 1u /* exact-erf GELU after bias (feature_extractor.py:58, encoder.py:127) */
+#define W2V2_GEMM_GELU 1u /* GELU after bias (feature_extractor.py:58, encoder.py:127): erf-exact in 3-pass (parity) mode;
+                             single-pass mode uses the bf16-grade tanh form (|err| < 5e-4) */
 
 typedef struct w2v2_gemm_args {
   /* A operand: bf16 planes, logical shape [batch][a_rows][a_row_len], element strides given. */
