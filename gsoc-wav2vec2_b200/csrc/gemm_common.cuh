@@ -32,6 +32,7 @@ struct GemmParams {
   int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form (single-pass mode)
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
   int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
+  int mn_major;         // 1: both operands are MN-major (reduction over the ROW index of two row-major matrices: wgrad)
   const float* bias;      // [N] (or [batch][N] with bias_bstride = N) or null
   const float* scale;     // optional per-column scale applied before the bias, [N] or [batch][N]
   int bias_bstride;       // elements between batch entries of bias / scale (0 = shared)

@@ -119,12 +119,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           uint8_t* sa = smem + stage * S::STAGE_BYTES;
           uint8_t* sb = sa + S::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
+          if (CLUSTER == 1 && p.mn_major) {
+            // D = X^T Y over the row index: X [rows][m], Y [rows][n] row-major.  A k-block is 64 ROWS; each operand tile is a
+            // set of [64 rows x 64 columns] boxes = 128-byte-swizzled MN-major atoms of 8 KB, 64 columns apart.
+#pragma unroll
+            for (int at = 0; at < GEMM_BLOCK_M / 64; ++at) tma_load_2d(sa + at * 8192, ma, &full_bar[stage], t0 + 64 * at, kb * GEMM_BLOCK_K);
+#pragma unroll
+            for (int at = 0; at < BLOCK_N / 64; ++at) tma_load_2d(sb + at * 8192, mb, &full_bar[stage], n0 + 64 * at, kb * GEMM_BLOCK_K);
+          } else {
           tma_load_3d(sa, ma, &full_bar[stage], kc, trow, b);
           if (CLUSTER == 1)
             tma_load_2d(sb, mb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
           else  // my slice of the weight tile, delivered to every CTA of the cluster
             tma_load_2d_mcast(sb + crank * (B_SLICE_ROWS * 128), mb, &full_bar[stage], kb * GEMM_BLOCK_K,
                               n0 + crank * B_SLICE_ROWS, kMask);
+          }
           if (++stage == S::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -135,7 +144,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc_k = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
+      constexpr uint32_t idesc_mn = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 1, 1);
+      const bool mn = (CLUSTER == 1) && p.mn_major;
+      const uint32_t idesc = mn ? idesc_mn : idesc_k;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -150,10 +162,19 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
           const uint64_t da = desc_kmajor_sw128(sa);
           const uint64_t db = desc_kmajor_sw128(sa + S::A_BYTES);
+          if (mn) {
+            // MN-major atoms: 64 columns per 128-byte row, 8 rows per 1 KB group (SBO), atoms 8 KB apart (LBO); one UMMA_K
+            // step = 16 rows = 2 KB further
+#pragma unroll
+            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
+              umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, 8192, 1024), desc_mnmajor_sw128(sa + S::A_BYTES + k * 2048, 8192, 1024),
+                       idesc, (it | k) != 0);
+          } else {
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
             // +32 bytes per UMMA_K step inside the swizzle row -> +2 in the (addr >> 4) field
             umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+          }
           }
           if (CLUSTER == 1) umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           else umma_commit_mcast(&empty_bar[stage], kMask);   // ... in every CTA that multicasts into it
@@ -274,6 +295,7 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.gelu = (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form (single-pass mode)
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
+  p.mn_major = (a->flags & W2V2_GEMM_MN_MAJOR) ? 1 : 0;
   p.bias = a->bias;
   p.scale = a->scale;
   p.bias_bstride = a->bias_batch_stride;
@@ -293,10 +315,21 @@ template <int BLOCK_N, int PASSES, int CLUSTER>
 static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
+  int rc;
+  if (a->flags & W2V2_GEMM_MN_MAJOR) {
+    // X [a_rows][rows_per_batch] and Y [a_rows][N] row-major, reduced over their a_rows rows: boxes of 64 rows x 64 columns
+    const uint64_t xd[2] = {(uint64_t)a->rows_per_batch, (uint64_t)a->a_rows}, yd[2] = {(uint64_t)a->N, (uint64_t)a->a_rows};
+    const uint64_t xs[1] = {(uint64_t)a->a_row_stride * 2}, ys[1] = {(uint64_t)a->w_row_stride * 2};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap(&tmA_hi, a->a_hi, 2, xd, xs, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    if ((rc = make_tmap(&tmB_hi, a->w_hi, 2, yd, ys, box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    tmA_lo = tmA_hi;
+    tmB_lo = tmB_hi;
+  } else {
   const uint64_t a_dims[3] = {(uint64_t)a->a_row_len, (uint64_t)a->a_rows, (uint64_t)a->batch};
   const uint64_t a_strides[2] = {(uint64_t)a->a_row_stride * 2, (uint64_t)a->a_batch_stride * 2};
   const uint32_t a_box[3] = {GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
-  int rc = make_tmap(&tmA_hi, a->a_hi, 3, a_dims, a_strides, a_box, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_tmap(&tmA_hi, a->a_hi, 3, a_dims, a_strides, a_box, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   tmA_lo = tmA_hi;
   if (PASSES == 3) {
@@ -312,6 +345,7 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   if (PASSES == 3) {
     rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
+  }
   }
   GemmParams p = make_gemm_params(a, BLOCK_N);
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES, CLUSTER>;
@@ -352,6 +386,17 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
                  "res_ln_stats needs residual, res_ln_gamma, res_ln_beta and N % 4 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int bn = a->block_n;
+  if (a->flags & W2V2_GEMM_MN_MAJOR) {
+    // D[m][n] = sum_r X[r][m] Y[r][n]  (weight gradients: X = layer input, Y = output gradient, both row-major as stored)
+    W2V2_CHECK_ARG(a->passes == 1 && a->batch == 1 && a->kb_split == 0, "MN-major mode: single pass, one batch entry");
+    W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->w_row_stride % 8 == 0 && a->w_row_stride >= a->N && a->a_row_stride >= a->rows_per_batch,
+                   "MN-major mode: leading dimensions must cover the tile and be multiples of 8 elements");
+    W2V2_CHECK_ARG(a->a_rows > 0 && a->K >= a->a_rows, "MN-major mode: K (rounded up to 64) must cover the a_rows reduction rows");
+    if (bn == 0 || bn > 128) bn = 128;
+    if (bn == 128) return launch_gemm<128, 1, 1>(a, s);
+    if (bn == 64) return launch_gemm<64, 1, 1>(a, s);
+    return fail(-1, "%s: MN-major mode supports block_n 64 or 128", __func__);
+  }
   if (bn == 0) bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;
   W2V2_CHECK_ARG(a->w_rows >= ((a->N + bn - 1) / bn) * bn, "weight matrix must be padded to a multiple of block_n rows");
   // clusters of 2 (weight-tile multicast) for the wide tiles whenever there are at least two m-tiles

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_ROOT, "lib", "libw2v2_sm100.so")
 CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 GEMM_GELU = 1
+GEMM_MN_MAJOR = 2
 
 
 class GemmArgs(C.Structure):
@@ -29,6 +30,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("row_valid", C.c_void_p),
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("res_ln_stats", C.c_void_p), ("res_ln_gamma", C.c_void_p), ("res_ln_beta", C.c_void_p),
+        ("w_row_stride", C.c_int64),
     ]
 
 

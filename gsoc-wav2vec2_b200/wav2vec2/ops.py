@@ -59,9 +59,10 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
          row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
-         res_ln=None):
+         res_ln=None, mn_major=False, w_row_stride=0):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
-    ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``."""
+    ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
+    ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride]."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
     args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if passes == 3 else None
@@ -73,7 +74,8 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.w_rows = w.hi.shape[0]
     args.K, args.N, args.rows_per_batch, args.batch = K, N, rows_per_batch, batch
     args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
-    args.flags = (_lib.GEMM_GELU if gelu else 0) | (debug << 8)
+    args.flags = (_lib.GEMM_GELU if gelu else 0) | (_lib.GEMM_MN_MAJOR if mn_major else 0) | (debug << 8)
+    args.w_row_stride = w_row_stride
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)

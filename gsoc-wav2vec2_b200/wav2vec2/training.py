@@ -98,7 +98,7 @@ class Stage2Trainer:
 
     Every arithmetic step of forward and backward is a kernel behind the C ABI: the inference kernels (forward, with the
     activations the backward needs kept in the arena), ``w2v2_ctc_loss`` (loss + dlogits), the tcgen05 GEMM for every
-    dgrad / wgrad product (operands transposed by ``w2v2_transpose_bf16``), ``w2v2_ln_bwd``, ``w2v2_dact_colsum``,
+    dgrad / wgrad product (wgrad with MN-major operands: no transposed copies), ``w2v2_ln_bwd``, ``w2v2_dact_colsum``,
     ``w2v2_attn_bwd``, ``w2v2_posconv`` (transposed-conv mode) + ``w2v2_posconv_wgrad``, then ONE ``all_reduce(SUM)``
     over the flat fp32 gradient buffer and ONE ``w2v2_adam`` launch.  Parameter-sized algebra (weight-norm chain rule,
     bf16 casts of the updated kernels) is host-side torch on the parameter tensors.
@@ -170,9 +170,6 @@ class Stage2Trainer:
         model._packed = None
         self._wt = None
         self.saved = None
-        # weight-gradient GEMMs have few output tiles and a long K (= all frames): 1-SM 128 x 128 tiles spread them over
-        # 4x as many SMs as the 256 x 256 CTA-pair tiles of the forward
-        self.wgrad_tiles = dict(cluster=int(os.environ.get("W2V2_WGRAD_CLUSTER", "1")), block_n=int(os.environ.get("W2V2_WGRAD_BN", "128")))
 
     # ------------------------------------------------------------------ operand packs of the backward GEMMs
     def _pack_backward(self):
@@ -388,12 +385,11 @@ class Stage2Trainer:
         return logits
 
     # ------------------------------------------------------------------ backward
-    def _wgrad(self, x_hi, dy_t, M, Mp, n_in, out):
-        """out[n_in][n_out] = x^T dy: A = x^T [n_in][Mp] (made here), weight operand = dy^T rows [n_out][Mp]."""
-        A = self.model._arena
-        xt = A.get(f"b.T.{n_in}", (n_in, Mp), torch.bfloat16)
-        ops.transpose_bf16(x_hi, M, n_in, xt, Mp)
-        ops.gemm(Pair(xt), Pair(dy_t), K=Mp, N=dy_t.shape[0], rows_per_batch=n_in, out_f32=out, **self.wgrad_tiles)
+    def _wgrad(self, x_hi, dy_hi, M, n_in, n_out, out, dy_ld=None):
+        """out[n_in][n_out] = x^T dy (the TF Dense kernel layout) straight from the row-major activations: MN-major operands,
+        the reduction runs over the M rows (W2V2_GEMM_MN_MAJOR), no transposed copies."""
+        ops.gemm(Pair(x_hi), Pair(dy_hi), K=((M + 63) // 64) * 64, N=n_out, rows_per_batch=n_in, a_rows=M, a_row_stride=n_in,
+                 out_f32=out, mn_major=True, w_row_stride=n_out if dy_ld is None else dy_ld, cluster=1, block_n=128)
 
     def _backward(self, dlogits):
         model, G, S = self.model, self.G, self.saved
@@ -401,7 +397,6 @@ class Stage2Trainer:
         W = self._wt or self._pack_backward()
         B, T = S["B"], S["T"]
         M = B * T
-        Mp = ((M + 63) // 64) * 64
         f32, bf, eps = torch.float32, torch.bfloat16, cfg.layer_norm_eps
         Cl, d, ffn = cfg.filter_sizes[-1], cfg.hidden_size, cfg.intermediate_size
         H, dh, V = cfg.num_heads, cfg.head_size, cfg.vocab_size
@@ -416,8 +411,6 @@ class Stage2Trainer:
         g1 = A.get("b.g1", (M, d), f32)
         dmid, dpre = A.get("b.dmid", (M, ffn), bf), A.get("b.dpre", (M, ffn), bf)
         dctx, dqkv = A.get("b.dctx", (M, d), bf), A.get("b.dqkv", (M, 3 * d), bf)
-        dyT, dffT = A.get("b.dyT", (d, Mp), bf), A.get("b.dffT", (ffn, Mp), bf)
-        dqkvT = A.get("b.dqkvT", (3 * d, Mp), bf)
         qkv_bias = A.get("b.qkvb", (3 * d,), f32)
         ws = A.get("b.attn.ws", (2 * B * H * T,), f32)
         enc = "wav2vec2/encoder/"
@@ -432,14 +425,12 @@ class Stage2Trainer:
                        colsum=G[ff + "output_dense/bias"] if on else None)
             if on:
                 ops.gemm(Pair(dyh), W[f"l{i}.ff2"], K=d, N=ffn, rows_per_batch=M, out_hi=dmid)
-                ops.transpose_bf16(dyh, M, d, dyT, Mp)
-                self._wgrad(Li["mid"].hi, dyT, M, Mp, ffn, G[ff + "output_dense/kernel"])
+                self._wgrad(Li["mid"].hi, dyh, M, ffn, d, G[ff + "output_dense/kernel"])
                 # mid = dropout(gelu(pre)),  pre = x1 W1 + b1
                 ops.dact_colsum(dmid, Li["pre"], M, ffn, out_hi=dpre, colsum=G[ff + "intermediate_dense/bias"],
                                 drop=self._drop(self.site_ffn_mid(i)) if p_drop else ops.NO_DROP)
                 ops.gemm(Pair(dpre), W[f"l{i}.ff1"], K=ffn, N=d, rows_per_batch=M, residual=dy, out_f32=g1)
-                ops.transpose_bf16(dpre, M, ffn, dffT, Mp)
-                self._wgrad(Li["x1"].hi, dffT, M, Mp, d, G[ff + "intermediate_dense/kernel"])
+                self._wgrad(Li["x1"].hi, dpre, M, d, ffn, G[ff + "intermediate_dense/kernel"])
             else:
                 g1.copy_(dy)                # the branch was dropped by StochasticDepth: only the shortcut carries gradient
             # x1 = LN1(y1),  y1 = x + ctx Wo + bo
@@ -452,8 +443,7 @@ class Stage2Trainer:
                 ops.ln_bwd(Li["y1"], v[lb + "layer_norm/gamma"], g1, eps, M, d, dx_f32=dy, dx_hi=dyh,
                            dgamma=G[lb + "layer_norm/gamma"], dbeta=G[lb + "layer_norm/beta"], colsum=G[at + "out_proj/bias"])
             ops.gemm(Pair(dyh), W[f"l{i}.out"], K=d, N=d, rows_per_batch=M, out_hi=dctx)
-            ops.transpose_bf16(dyh, M, d, dyT, Mp)
-            self._wgrad(Li["ctx"].hi, dyT, M, Mp, d, G[at + "out_proj/kernel"])
+            self._wgrad(Li["ctx"].hi, dyh, M, d, d, G[at + "out_proj/kernel"])
             # ctx = softmax(q k^T) v  (q carries dh^-1/2: encoder.py:28 folded into the packed q projection)
             ops.attn_bwd(Li["qkv"].hi, Li["ctx"].hi, dctx, B, T, H, dh, None, dh ** -0.5, dqkv, workspace=ws,
                          drop=self._drop(self.site_attn_probs(i)) if p_drop else ops.NO_DROP)
@@ -462,12 +452,8 @@ class Stage2Trainer:
             for j, n in enumerate(("q", "k", "v")):
                 G[at + f"{n}_proj/bias"].copy_(qkv_bias[j * d:(j + 1) * d])
             ops.gemm(Pair(dqkv), W[f"l{i}.qkv"], K=3 * d, N=d, rows_per_batch=M, residual=dy, out_f32=g)
-            ops.transpose_bf16(dqkv, M, 3 * d, dqkvT, Mp)
-            xt = A.get(f"b.T.{d}", (d, Mp), bf)
-            ops.transpose_bf16(Li["xs"].hi, M, d, xt, Mp)
             for j, n in enumerate(("q", "k", "v")):
-                ops.gemm(Pair(xt), Pair(dqkvT[j * d:(j + 1) * d]), K=Mp, N=d, rows_per_batch=d, out_f32=G[at + f"{n}_proj/kernel"],
-                         **self.wgrad_tiles)
+                self._wgrad(Li["xs"].hi, dqkv[:, j * d:(j + 1) * d], M, d, d, G[at + f"{n}_proj/kernel"], dy_ld=3 * d)
         # x_0 = dropout(LN_enc(y0)),  y0 = h + gelu(pos_pre),  pos_pre = conv(h) + b
         if p_drop:
             ops.dropout_rows(g, self._drop(self.SITE_ENC), out_f32=g)
@@ -495,8 +481,7 @@ class Stage2Trainer:
             ops.dropout_rows(dh_f32, self._drop(self.SITE_PROJ), out_f32=dh_f32)
         dhh = ops.split_bf16(dh_f32, False).hi
         ops.dact_colsum(dhh, None, M, d, colsum=G[fp + "projection/bias"])
-        ops.transpose_bf16(dhh, M, d, dyT, Mp)
-        self._wgrad(S["pn"].hi, dyT, M, Mp, Cl, G[fp + "projection/kernel"])
+        self._wgrad(S["pn"].hi, dhh, M, Cl, d, G[fp + "projection/kernel"])
         dpn = A.get("b.dpn", (M, Cl), f32)
         ops.gemm(Pair(dhh), W["proj"], K=d, N=Cl, rows_per_batch=M, out_f32=dpn)
         ops.ln_bwd(S["last_f32"], v[fp + "layer_norm/gamma"], dpn, eps, M, Cl, dgamma=G[fp + "layer_norm/gamma"],

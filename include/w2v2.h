@@ -36,6 +36,11 @@ const char* w2v2_last_error_string(void);
  * tf.keras.layers.Conv1D for extractor layers 1..6 at feature_extractor.py:31-37,55 as an implicit
  * GEMM (A rows = overlapping k*Cin windows of the channels-last input).
  * ------------------------------------------------------------------------------------------- */
+#define W2V2_GEMM_MN_MAJOR 2u /* D[m][n] = sum_r X[r][m] Y[r][n]: both operands row-major [reduction rows][columns] as the forward
+                                stores them (weight gradients dW = X^T dY without transposed copies).  a_hi = X, a_rows = number
+                                of reduction rows, a_row_stride = leading dimension of X, rows_per_batch = columns of X (= output
+                                rows); w_hi = Y with leading dimension w_row_stride, N = columns of Y; K = a_rows rounded up to 64;
+                                single pass, batch 1, 1-SM tiles (block_n 64 / 128). */
 #define W2V2_GEMM_GELU 1u /* GELU after bias (feature_extractor.py:58, encoder.py:127): erf-exact in 3-pass (parity) mode;
                              single-pass mode uses the bf16-grade tanh form (|err| < 5e-4) */
 
@@ -78,6 +83,7 @@ typedef struct w2v2_gemm_args {
   const float* res_ln_stats;  /* [batch*rows_per_batch][2] or NULL */
   const float* res_ln_gamma;  /* [N] */
   const float* res_ln_beta;   /* [N] */
+  int64_t w_row_stride;       /* W2V2_GEMM_MN_MAJOR only: leading dimension (elements) of Y */
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
@@ -196,7 +202,7 @@ int w2v2_adam(float* weights, const float* grads, float* m, float* v, int64_t n,
  * Stage-2 fine-tune step (src/main.py:234-250: Keras `fit` differentiates the whole encoder; the conv extractor
  * stays frozen, main.py:236-237).  The matrix products of the backward pass reuse w2v2_gemm_bf16:
  *   dgrad  dX = dY . W^T    A = dY [rows][out], weight operand = the TF Dense kernel itself ([in][out] is W^T, K-major)
- *   wgrad  dW = X^T . dY    A = X^T [in][rows], weight operand = dY^T [out][rows]  (w2v2_transpose_bf16 makes both),
+ *   wgrad  dW = X^T . dY    W2V2_GEMM_MN_MAJOR: a_hi = X [rows][in], w_hi = dY [rows][out] as stored (MN-major operands),
  *                           out_f32 = the gradient in the TF layout [in][out]
  * and these kernels supply everything else.
  * ------------------------------------------------------------------------------------------- */

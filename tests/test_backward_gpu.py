@@ -541,3 +541,25 @@ def test_one_launch_weight_repack_equals_host_packing():
         assert torch.equal(fast_P[k], ref), k
     for k, t in W.items():
         assert torch.equal(fast_W[k], t.hi), k
+
+
+@pytest.mark.parametrize("M,din,dout", [(290, 768, 3072), (6144, 768, 768), (98, 3072, 768), (145, 512, 768)])
+def test_wgrad_mn_major_without_transposes(M, din, dout):
+    """W2V2_GEMM_MN_MAJOR: dW[in][out] = sum_rows X[r][in] dY[r][out] straight from the row-major activations (MN-major tcgen05
+    operands, TMA zero-fills the rows past M), also on a column slice of a wider matrix (the packed dqkv)."""
+    ops = _ops()
+    from wav2vec2.ops import Pair
+    torch.manual_seed(13)
+    X = _bf(torch.randn(M, din, device=DEV))
+    wide = _bf(torch.randn(M, 3 * dout, device=DEV) * 0.1)
+    Kp = ((M + 63) // 64) * 64
+    for j in (0, 2):
+        dY = wide[:, j * dout:(j + 1) * dout]
+        dW = torch.full((din, dout), 5.0, device=DEV)
+        ops.gemm(Pair(X), Pair(dY), K=Kp, N=dout, rows_per_batch=din, a_rows=M, a_row_stride=din, out_f32=dW,
+                 mn_major=True, w_row_stride=3 * dout, cluster=1, block_n=128)
+        torch.cuda.synchronize()
+        ref = X.float().t() @ dY.float()
+        r = _rel(dW, ref)
+        print(f"wgrad mn-major M={M} {din}x{dout} slice {j}: rel err {r:.3e}")
+        assert r < 1e-4

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match_header():
     # 64-bit pointers / int64 first, then int32 fields: sizes are what the C struct has on LP64
-    assert C.sizeof(_lib.GemmArgs) == 8 * 8 + 11 * 4 + 4 + 8 * 8 + 3 * 8
+    assert C.sizeof(_lib.GemmArgs) == 8 * 8 + 11 * 4 + 4 + 8 * 8 + 3 * 8 + 8
     assert C.sizeof(_lib.PackJob) == 2 * 8 + 8 * 4
     assert C.sizeof(_lib.PosconvArgs) == 7 * 8 + 6 * 4 + 8 + 2 * 4
 

@@ -39,8 +39,7 @@ for _ in range(5):
     tr._backward(dl); e.append(ev())
     tr.t += 1
     ops.adam(tr.flat_w, tr.flat_g, tr.m, tr.v, 1e-5, 0.9, 0.999, 1e-7); e.append(ev())
-    model._packed = None; tr._wt = None
-    model._pack(); tr._pack_backward(); e.append(ev())
+    tr._repack(); e.append(ev())
     torch.cuda.synchronize()
     host = (time.perf_counter() - t0) * 1e3
     for name, a, b in zip(("forward", "ctc", "backward", "adam", "repack"), e[:-1], e[1:]):
@@ -52,7 +51,7 @@ print({k: round(v, 3) for k, v in acc.items()})
 records = []
 orig = {}
 for name in ("gemm", "ln_bwd", "dact_colsum", "transpose_bf16", "attn_bwd", "posconv_train", "posconv_wgrad", "lm_head_wgrad",
-             "lm_head_dgrad", "split_bf16", "gelu_rows", "ln_rows", "attn_fwd", "attn_fwd_train", "dropout_rows"):
+             "lm_head_dgrad", "split_bf16", "gelu_rows", "ln_rows", "attn_fwd", "attn_fwd_train", "dropout_rows", "pack_weights"):
     fn = getattr(ops, name)
     orig[name] = fn
 
