@@ -92,6 +92,21 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// Dropout keep bits of one [64 queries x 64 keys] tile, computed cooperatively: byte [q][kg] holds the 4 keep bits of keys
+// 4 kg .. 4 kg + 3 of query row q (one hash per byte, 8 per thread) - the MMA fragments own 1 or 2 keys of a 4-key group, so
+// hashing per fragment element would repeat every draw 2 to 4 times.
+__device__ __forceinline__ void fill_keep_tile(uint8_t (*keep)[16], const DropSpec& dr, int bh, int q_first, int k_first, int T,
+                                               int tid) {
+  for (int i = tid; i < AB_BLK * 16; i += 128) {
+    const int ql = i >> 4, kg = i & 15;
+    const uint64_t bits = drop_bits4(dr, attn_row_group(bh, q_first + ql, T) + ((k_first >> 2) + kg));
+    uint32_t m = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) m |= drop_keep(bits, e, dr.thr16) ? (1u << e) : 0u;
+    keep[ql][kg] = (uint8_t)m;
+  }
+}
+
 // ------------------------------------------------------------------------------------ dQ (+ lse2, D)
 __global__ void __launch_bounds__(128)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
@@ -212,6 +227,11 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   }
 
   // ---- sweep 2: dQ += (P o (dO V^T - D)) K
+  __shared__ uint8_t s_keep[2][AB_BLK][16];    // dropout keep bits of the current / next tile
+  if (dr.thr16) {
+    fill_keep_tile(s_keep[0], dr, bh, t0, 0, T, tid);
+    __syncthreads();
+  }
   float dq[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
@@ -226,6 +246,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __syncthreads();
     const __nv_bfloat16* sK = bufK[stage & 1];
     const __nv_bfloat16* sV = bufV[stage & 1];
+    if (dr.thr16 && kb + 1 < nkb) fill_keep_tile(s_keep[(kb + 1) & 1], dr, bh, t0, (kb + 1) * AB_BLK, T, tid);   // visible after the loop's closing barrier
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -255,8 +276,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const float p = (key < klen) ? ex2_approx(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
           float dpv = dp[j][2 * r + e];
           if (dr.thr16) {   // dP = dP_dropped o mask / (1 - p_drop)
-            const uint64_t bits = drop_bits4(dr, attn_row_group(bh, t0 + m0 + g + 8 * r, T) + (key >> 2));
-            dpv = drop_keep(bits, key & 3, dr.thr16) ? dpv * dr.scale : 0.0f;
+            const uint32_t kb4 = s_keep[kb & 1][m0 + g + 8 * r][2 * j + (q >> 1)];
+            dpv = ((kb4 >> (2 * (q & 1) + e)) & 1u) ? dpv * dr.scale : 0.0f;
           }
           ds[2 * r + e] = p * (dpv - dsum[r]);
         }
@@ -337,6 +358,11 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     cp_async_f32(tid < 64 ? &s_lse2[qb2 & 1][tid] : &s_ds2[qb2 & 1][tid - 64], src, t < T);
     cp_async_commit();
   };
+  __shared__ uint8_t s_keep[2][AB_BLK][16];    // dropout keep bits [query][key group] of the current / next tile
+  if (dr.thr16) {
+    fill_keep_tile(s_keep[0], dr, bh, 0, k0, T, tid);
+    __syncthreads();
+  }
   issue(0);
   for (int qb = 0; qb < nqb; ++qb) {
     if (qb + 1 < nqb) {
@@ -350,6 +376,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     const __nv_bfloat16* sdO = bufdO[qb & 1];
     const float* s_lse = s_lse2[qb & 1];
     const float* s_ds = s_ds2[qb & 1];
+    if (dr.thr16 && qb + 1 < nqb) fill_keep_tile(s_keep[(qb + 1) & 1], dr, bh, (qb + 1) * AB_BLK, k0, T, tid);
     // S^T = K Q^T and dP^T = V dO^T : [16 keys] x [64 queries]
     float st[8][4], dpt[8][4];
 #pragma unroll
@@ -380,9 +407,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
           const float pv = ok ? ex2_approx(st[j][2 * r + e] * AB_LOG2E - s_lse[qi]) : 0.0f;
           float keep = 1.0f;
           if (dr.thr16) {
-            const int key = k0 + m0 + g + 8 * r;
-            const uint64_t bits = drop_bits4(dr, attn_row_group(bh, qb * AB_BLK + qi, T) + (key >> 2));
-            keep = drop_keep(bits, key & 3, dr.thr16) ? dr.scale : 0.0f;
+            const int kl = m0 + g + 8 * r;           // key inside this CTA's 64-key block
+            keep = ((s_keep[qb & 1][qi][kl >> 2] >> (kl & 3)) & 1u) ? dr.scale : 0.0f;
           }
           p[2 * r + e] = pv * keep;                                   // dV uses the dropped probabilities
           ds[2 * r + e] = pv * (dpt[j][2 * r + e] * keep - s_ds[qi]);
