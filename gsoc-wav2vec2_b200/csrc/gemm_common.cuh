@@ -32,6 +32,7 @@ struct GemmParams {
   int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form (single-pass mode)
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
   int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
+  int atomic_f32;       // 1: out_f32 += result with fp32 atomics (split-K partial sums into a zeroed buffer)
   int mn_major;         // 1: both operands are MN-major (reduction over the ROW index of two row-major matrices: wgrad)
   const float* bias;      // [N] (or [batch][N] with bias_bstride = N) or null
   const float* scale;     // optional per-column scale applied before the bias, [N] or [batch][N]
@@ -110,14 +111,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   }
 
   // staged 32 x 128 B block -> global, 8 lanes per row (PIECES = 8) or 4 lanes per row (PIECES = 4: 64-byte rows)
-  auto flush = [&](uint8_t* gbase, size_t row_stride_bytes, int pieces) {
+  auto flush = [&](uint8_t* gbase, size_t row_stride_bytes, int pieces, bool atomic = false) {
     __syncwarp();
     if (pieces == 8) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int row = 4 * k + (lane >> 3), pc = lane & 7;
         const uint4 val = *reinterpret_cast<const uint4*>(stage + row * 128 + ((pc ^ (row & 7)) << 4));
-        if (row < rows_valid) *reinterpret_cast<uint4*>(gbase + row * row_stride_bytes + pc * 16) = val;
+        if (row < rows_valid) {
+          if (atomic) {
+            float* g = reinterpret_cast<float*>(gbase + row * row_stride_bytes + pc * 16);
+            atomicAdd(g + 0, __uint_as_float(val.x));
+            atomicAdd(g + 1, __uint_as_float(val.y));
+            atomicAdd(g + 2, __uint_as_float(val.z));
+            atomicAdd(g + 3, __uint_as_float(val.w));
+          } else {
+            *reinterpret_cast<uint4*>(gbase + row * row_stride_bytes + pc * 16) = val;
+          }
+        }
       }
     } else {
 #pragma unroll
@@ -238,7 +249,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         for (int j = 0; j < 32; ++j) {
           if (n + j >= p.N) continue;
           const float v = __uint_as_float(r[i][j]);
-          if (f_f32) p.out_f32[orow * p.N + n + j] = v;
+          if (f_f32) {
+            if (p.atomic_f32) atomicAdd(p.out_f32 + orow * p.N + n + j, v);
+            else p.out_f32[orow * p.N + n + j] = v;
+          }
           if (f_hi) {
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             p.out_hi[orow * p.N + n + j] = h;
@@ -251,7 +265,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
     if (f_f32) {  // 32 fp32 columns = one 128-byte row segment
 #pragma unroll
       for (int j = 0; j < 8; ++j) put(j, make_uint4(r[i][4 * j], r[i][4 * j + 1], r[i][4 * j + 2], r[i][4 * j + 3]));
-      flush(reinterpret_cast<uint8_t*>(p.out_f32 + orow0 * p.N + n), (size_t)p.N * 4, 8);
+      flush(reinterpret_cast<uint8_t*>(p.out_f32 + orow0 * p.N + n), (size_t)p.N * 4, 8, p.atomic_f32 != 0);
     }
     if (f_hi) {
       // bf16: an even/odd chunk pair forms one 128-byte row segment; a lone chunk is a 64-byte segment

@@ -121,11 +121,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           mbar_arrive_expect_tx(&full_bar[stage], S::STAGE_BYTES);
           if (CLUSTER == 1 && p.mn_major) {
             // D = X^T Y over the row index: X [rows][m], Y [rows][n] row-major.  A k-block is 64 ROWS; each operand tile is a
-            // set of [64 rows x 64 columns] boxes = 128-byte-swizzled MN-major atoms of 8 KB, 64 columns apart.
+            // set of [64 rows x 64 columns] boxes = 128-byte-swizzled MN-major atoms of 8 KB, 64 columns apart.  The batch index is
+            // the split-K slice: slice b reduces rows [b K, (b + 1) K) and all slices add into the same output.
 #pragma unroll
-            for (int at = 0; at < GEMM_BLOCK_M / 64; ++at) tma_load_2d(sa + at * 8192, ma, &full_bar[stage], t0 + 64 * at, kb * GEMM_BLOCK_K);
+            for (int at = 0; at < GEMM_BLOCK_M / 64; ++at) tma_load_2d(sa + at * 8192, ma, &full_bar[stage], t0 + 64 * at, (b * p.num_kb + kb) * GEMM_BLOCK_K);
 #pragma unroll
-            for (int at = 0; at < BLOCK_N / 64; ++at) tma_load_2d(sb + at * 8192, mb, &full_bar[stage], n0 + 64 * at, kb * GEMM_BLOCK_K);
+            for (int at = 0; at < BLOCK_N / 64; ++at) tma_load_2d(sb + at * 8192, mb, &full_bar[stage], n0 + 64 * at, (b * p.num_kb + kb) * GEMM_BLOCK_K);
           } else {
           tma_load_3d(sa, ma, &full_bar[stage], kc, trow, b);
           if (CLUSTER == 1)
@@ -217,7 +218,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       const int rows_valid = (m_raw < total_m_tiles) ? min(32, p.rows_per_batch - (t - lane)) : 0;
       uint8_t* stage = smem + S::EPI_OFF + (warp - 4) * 4096;
       const bool zero_row = p.row_valid != nullptr && t >= p.row_valid[b];
-      const size_t orow = (size_t)b * p.rows_per_batch + t;
+      const size_t orow = (p.mn_major ? (size_t)0 : (size_t)b * p.rows_per_batch) + t;
       float* sb = s_bias + acc * BLOCK_N;
       gemm_epilogue_prepare<BLOCK_N, EPI_RUNTIME>(p, et, grp, n0, orow, row_ok, sb, b);
 
@@ -296,6 +297,7 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.mn_major = (a->flags & W2V2_GEMM_MN_MAJOR) ? 1 : 0;
+  p.atomic_f32 = (p.mn_major && a->batch > 1) ? 1 : 0;
   p.bias = a->bias;
   p.scale = a->scale;
   p.bias_bstride = a->bias_batch_stride;
@@ -388,10 +390,12 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   int bn = a->block_n;
   if (a->flags & W2V2_GEMM_MN_MAJOR) {
     // D[m][n] = sum_r X[r][m] Y[r][n]  (weight gradients: X = layer input, Y = output gradient, both row-major as stored)
-    W2V2_CHECK_ARG(a->passes == 1 && a->batch == 1 && a->kb_split == 0, "MN-major mode: single pass, one batch entry");
+    W2V2_CHECK_ARG(a->passes == 1 && a->kb_split == 0, "MN-major mode: single pass");
+    W2V2_CHECK_ARG(a->batch == 1 || (a->out_f32 && !a->out_hi && !a->bias && !a->residual),
+                   "MN-major split-K (batch > 1): only out_f32 (accumulated atomically into a zeroed buffer), no bias / residual");
     W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->w_row_stride % 8 == 0 && a->w_row_stride >= a->N && a->a_row_stride >= a->rows_per_batch,
                    "MN-major mode: leading dimensions must cover the tile and be multiples of 8 elements");
-    W2V2_CHECK_ARG(a->a_rows > 0 && a->K >= a->a_rows, "MN-major mode: K (rounded up to 64) must cover the a_rows reduction rows");
+    W2V2_CHECK_ARG(a->a_rows > 0 && (int64_t)a->K * a->batch >= a->a_rows, "MN-major mode: K x batch must cover the a_rows reduction rows");
     if (bn == 0 || bn > 128) bn = 128;
     if (bn == 128) return launch_gemm<128, 1, 1>(a, s);
     if (bn == 64) return launch_gemm<64, 1, 1>(a, s);

@@ -388,8 +388,15 @@ class Stage2Trainer:
     def _wgrad(self, x_hi, dy_hi, M, n_in, n_out, out, dy_ld=None):
         """out[n_in][n_out] = x^T dy (the TF Dense kernel layout) straight from the row-major activations: MN-major operands,
         the reduction runs over the M rows (W2V2_GEMM_MN_MAJOR), no transposed copies."""
-        ops.gemm(Pair(x_hi), Pair(dy_hi), K=((M + 63) // 64) * 64, N=n_out, rows_per_batch=n_in, a_rows=M, a_row_stride=n_in,
-                 out_f32=out, mn_major=True, w_row_stride=n_out if dy_ld is None else dy_ld, cluster=1, block_n=128)
+        # few output tiles, long reduction: split the M rows over up to 8 slices so that ~all SMs work; the slices add into the
+        # (zeroed) gradient buffer with fp32 atomics
+        tiles = ((n_in + 127) // 128) * ((n_out + 127) // 128)
+        kb = (M + 63) // 64
+        splits = max(1, min(8, 148 // tiles, kb))
+        kb_per = (kb + splits - 1) // splits
+        splits = (kb + kb_per - 1) // kb_per
+        ops.gemm(Pair(x_hi), Pair(dy_hi), K=kb_per * 64, N=n_out, rows_per_batch=n_in, batch=splits, a_rows=M, a_row_stride=n_in,
+                 a_batch_stride=0, out_f32=out, mn_major=True, w_row_stride=n_out if dy_ld is None else dy_ld, cluster=1, block_n=128)
 
     def _backward(self, dlogits):
         model, G, S = self.model, self.G, self.saved

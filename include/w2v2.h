@@ -39,8 +39,10 @@ const char* w2v2_last_error_string(void);
 #define W2V2_GEMM_MN_MAJOR 2u /* D[m][n] = sum_r X[r][m] Y[r][n]: both operands row-major [reduction rows][columns] as the forward
                                 stores them (weight gradients dW = X^T dY without transposed copies).  a_hi = X, a_rows = number
                                 of reduction rows, a_row_stride = leading dimension of X, rows_per_batch = columns of X (= output
-                                rows); w_hi = Y with leading dimension w_row_stride, N = columns of Y; K = a_rows rounded up to 64;
-                                single pass, batch 1, 1-SM tiles (block_n 64 / 128). */
+                                rows); w_hi = Y with leading dimension w_row_stride, N = columns of Y; single pass, 1-SM tiles
+                                (block_n 64 / 128).  batch = number of split-K slices: slice b reduces rows [b K, (b+1) K), K x batch
+                                >= a_rows (rounded up to 64 per slice); with batch > 1 the slices ADD into out_f32 with fp32 atomics
+                                (the caller zeroes it; no bias / residual / bf16 output). */
 #define W2V2_GEMM_GELU 1u /* GELU after bias (feature_extractor.py:58, encoder.py:127): erf-exact in 3-pass (parity) mode;
                              single-pass mode uses the bf16-grade tanh form (|err| < 5e-4) */
 

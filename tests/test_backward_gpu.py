@@ -563,3 +563,20 @@ def test_wgrad_mn_major_without_transposes(M, din, dout):
         r = _rel(dW, ref)
         print(f"wgrad mn-major M={M} {din}x{dout} slice {j}: rel err {r:.3e}")
         assert r < 1e-4
+
+
+@pytest.mark.parametrize("M,splits", [(6144, 4), (290, 3), (6144, 8)])
+def test_wgrad_split_k_accumulates_atomically(M, splits):
+    """MN-major split-K: `batch` slices of the row reduction add into a zeroed fp32 buffer (the last slice runs past M: zero fill)."""
+    ops = _ops()
+    from wav2vec2.ops import Pair
+    torch.manual_seed(14)
+    din, dout = 768, 768
+    X, dY = _bf(torch.randn(M, din, device=DEV)), _bf(torch.randn(M, dout, device=DEV) * 0.1)
+    kb = (M + 63) // 64
+    kb_per = (kb + splits - 1) // splits
+    dW = torch.zeros(din, dout, device=DEV)
+    ops.gemm(Pair(X), Pair(dY), K=kb_per * 64, N=dout, rows_per_batch=din, batch=splits, a_rows=M, a_row_stride=din, a_batch_stride=0,
+             out_f32=dW, mn_major=True, w_row_stride=dout, cluster=1, block_n=128)
+    torch.cuda.synchronize()
+    assert _rel(dW, X.float().t() @ dY.float()) < 1e-5
