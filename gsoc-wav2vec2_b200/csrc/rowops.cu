@@ -237,7 +237,8 @@ conv0_kernel(const float* __restrict__ wave, int L, int T0, int C, const float* 
 // ------------------------------------------------------------------------------------ ln_rows
 // y = (x - mean) * rsqrt(var + eps) * gamma + beta over the last axis (biased variance, two-pass in
 // registers), optional GELU, outputs fp32 and/or bf16 hi(/lo).  One warp per row, float4 accesses.
-template <int MAXV>
+// EXACT: d == 128 * MAXV (every lane owns exactly MAXV float4: 512 / 768 / 1024 channels) - no bounds predicates.
+template <int MAXV, bool EXACT = false>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                int rows, int d, int gelu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
@@ -254,7 +255,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
+    if (EXACT || idx < nvec) {
       v[i] = __ldg(xp + idx);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     } else {
@@ -265,7 +266,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   float q = 0.0f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    if (lane + 32 * i < nvec) {
+    if (EXACT || lane + 32 * i < nvec) {
       const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, e = v[i].w - mean;
       q += (a * a + b * b) + (c * c + e * e);
     }
@@ -275,7 +276,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
+    if (EXACT || idx < nvec) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
       const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + idx);
       float y0 = fmaf((v[i].x - mean) * rstd, g.x, bt.x);
@@ -439,7 +440,13 @@ extern "C" int w2v2_ln_rows_stats(const float* x, const float* gamma, const floa
   const unsigned grid = (unsigned)((rows + 7) / 8);
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  if (d <= 1024)
+  if (d == 512)
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<4, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+  else if (d == 768)
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<6, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+  else if (d == 1024)
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<8, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+  else if (d <= 1024)
     W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
   else
     W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
