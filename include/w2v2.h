@@ -177,7 +177,7 @@ int w2v2_posconv(const w2v2_posconv_args* args, void* stream);
  * CTCLoss.call, losses.py:29-45: blank = pad_id, label_length = #labels != pad, logit_length =
  * frames for every utterance, per-utterance negative log-likelihood scaled by `scale`
  * (= 1 / division_factor); the caller sums over the batch (Keras SUM reduction, losses.py:6).
- * workspace: w2v2_ctc_workspace_bytes(batch, frames, max_label_len) bytes.  grad_logits may be NULL.
+ * workspace: w2v2_ctc_workspace_bytes(batch, frames, max_label_len) bytes (the alpha and beta tables).  grad_logits may be NULL.
  * ------------------------------------------------------------------------------------------- */
 int64_t w2v2_ctc_workspace_bytes(int batch, int frames, int max_label_len);
 int w2v2_ctc_loss(const float* logits /*[batch][frames][vocab]*/, const int32_t* labels /*[batch][max_label_len]*/,

@@ -50,7 +50,7 @@ def test_argument_errors_are_reported_not_crashed(lib):
     assert lib.w2v2_posconv(None, None) < 0
     assert lib.w2v2_attn_fwd(None, None, 1, 1, 1, 64, None, None, None, 1, None) < 0
     assert lib.w2v2_ln_rows(None, None, None, 1e-5, 1, 768, 0, None, None, None, None) < 0
-    assert lib.w2v2_ctc_workspace_bytes(2, 768, 256) == 2 * 768 * 513 * 4
+    assert lib.w2v2_ctc_workspace_bytes(2, 768, 256) == 2 * 2 * 768 * 513 * 4      # alpha and beta tables
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
