@@ -20,7 +20,7 @@ namespace w2v2 {
 // dgamma = sum_rows dy * xh, dbeta = sum_rows dy.  One warp per row (statistics recomputed from x, two-pass in registers);
 // a CTA walks many rows and keeps its column partial sums in registers, then merges them through shared memory and issues
 // one atomicAdd per column.  `colsum` (optional) receives sum_rows dx: the bias gradient of the Dense that produced x.
-template <int MAXV>
+template <int MAXV, bool EXACT = false>   // EXACT: d == 128 * MAXV, no bounds predicates (512 / 768 / 1024 channels)
 __global__ void __launch_bounds__(256)
 ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy, float eps,
               int rows, int d, float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_hi,
@@ -36,7 +36,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   float4 gm[MAXV];
 #pragma unroll
   for (int i = 0; i < MAXV; ++i)
-    gm[i] = (lane + 32 * i < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    gm[i] = (EXACT || lane + 32 * i < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
     const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * d);
@@ -46,7 +46,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + 32 * i;
-      if (idx < nvec) {
+      if (EXACT || idx < nvec) {
         v[i] = __ldg(xp + idx);
         g[i] = __ldg(dp + idx);
         s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -58,7 +58,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
     float q = 0.0f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      if (lane + 32 * i < nvec) {
+      if (EXACT || lane + 32 * i < nvec) {
         v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
         q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
       }
@@ -80,7 +80,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + 32 * i;
-      if (idx < nvec) {
+      if (EXACT || idx < nvec) {
         float4 o;
         o.x = rstd * (g[i].x - ma - v[i].x * mb);
         o.y = rstd * (g[i].y - ma - v[i].y * mb);
@@ -98,7 +98,7 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int idx = lane + 32 * i;
-    if (idx < nvec) {
+    if (EXACT || idx < nvec) {
       const int c = 4 * idx;
       atomicAdd(&s_part[c + 0], ag[i].x); atomicAdd(&s_part[c + 1], ag[i].y);
       atomicAdd(&s_part[c + 2], ag[i].z); atomicAdd(&s_part[c + 3], ag[i].w);
@@ -144,8 +144,19 @@ gelu_rows_kernel(const float* __restrict__ pre, size_t n4, __nv_bfloat16* __rest
 // ------------------------------------------------------------------------------------ activation backward + column sums
 // gelu'(x) = Phi(x) + x phi(x)  (derivative of the exact erf form, config.py:14).
 __device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  const float pdf = 0.3989422804014327f * __expf(-0.5f * x * x);
+  // Phi through the erfc-as-exp2 polynomial of the forward (w2v2_common.cuh: erfc(a / sqrt2) = exp2(a R(a)), |err| 2.6e-7)
+  // and phi as one more exp2: two MUFU.EX2 + ~12 FMAs instead of erff + expf (the kernel was instruction-bound)
+  const float ax = fabsf(x);
+  const float a = fminf(ax, 6.0f);
+  float r = 3.2121541153173894e-05f;
+  r = fmaf(r, a, -0.0007558754878118634f);
+  r = fmaf(r, a, 0.008020005188882351f);
+  r = fmaf(r, a, -0.053288985043764114f);
+  r = fmaf(r, a, -0.45888903737068176f);
+  r = fmaf(r, a, -1.1511517763137817f);
+  const float half_erfc = 0.5f * ex2_approx(r * a);                 // Phi(-|x|)
+  const float cdf = (x >= 0.0f) ? 1.0f - half_erfc : half_erfc;
+  const float pdf = 0.3989422804014327f * ex2_approx(-0.7213475204444817f * x * x);
   return fmaf(x, pdf, cdf);
 }
 // thread = 4 consecutive columns, walks the rows of its chunk (blockIdx.y); dy bf16, pre fp32 (or null), out bf16 (or null)
@@ -292,8 +303,12 @@ extern "C" int w2v2_ln_bwd(const float* x, const float* gamma, const float* dy, 
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   int grid = (int)((rows + 7) / 8);
   if (grid > 148 * 2) grid = 148 * 2;
-  ln_bwd_kernel<8><<<grid, 256, 3 * d * sizeof(float), s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32,
-                                                            reinterpret_cast<__nv_bfloat16*>(dx_hi), dgamma, dbeta, colsum);
+  auto* hi = reinterpret_cast<__nv_bfloat16*>(dx_hi);
+  const size_t sm = 3 * d * sizeof(float);
+  if (d == 512) ln_bwd_kernel<4, true><<<grid, 256, sm, s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32, hi, dgamma, dbeta, colsum);
+  else if (d == 768) ln_bwd_kernel<6, true><<<grid, 256, sm, s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32, hi, dgamma, dbeta, colsum);
+  else if (d == 1024) ln_bwd_kernel<8, true><<<grid, 256, sm, s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32, hi, dgamma, dbeta, colsum);
+  else ln_bwd_kernel<8><<<grid, 256, sm, s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32, hi, dgamma, dbeta, colsum);
   W2V2_CUDA(cudaGetLastError());
   return 0;
 }
