@@ -90,3 +90,34 @@ def test_frame_lengths_formula():
     assert cfg.conv_frames(46797)[-1] == 145 and cfg.conv_frames(16000)[-1] == 49
     n = O.frame_lengths(cfg, torch.tensor([246000, 245000, 16000]))
     assert n.tolist() == [768, 765, 49]
+
+
+def test_oracle_training_masks_are_identity_when_all_kept():
+    """The oracle's explicit Dropout / StochasticDepth masks (checker of the stage-2 train step): all-ones masks reproduce
+    the eval forward bit for bit, a dropped FFN branch leaves its parameters without gradient, and a dropped unit of the
+    `head` mask removes exactly that unit's contribution."""
+    import torch
+    from oracle import w2v2_oracle as O
+    from wav2vec2.config import Wav2Vec2Config
+    cfg = Wav2Vec2Config(num_layers=2)
+    p = O.random_params(cfg, seed=3)
+    x = torch.randn(2, 4000, generator=torch.Generator().manual_seed(0))
+    ref = O.wav2vec2_for_ctc(x, p, cfg)
+    B, T, d, ffn, H = 2, ref.shape[1], cfg.hidden_size, cfg.intermediate_size, cfg.num_heads
+    ones = {"proj": torch.ones(B, T, d), "enc": torch.ones(B, T, d), "head": torch.ones(B, T, d)}
+    for i in range(cfg.num_layers):
+        ones.update({f"attn_probs.{i}": torch.ones(B, H, T, T), f"attn_out.{i}": torch.ones(B, T, d),
+                     f"ffn_mid.{i}": torch.ones(B, T, ffn), f"stochastic_depth.{i}": torch.ones(())})
+    assert torch.equal(O.wav2vec2_for_ctc(x, p, cfg, drop=ones), ref)
+    q = {k: t.clone().requires_grad_(True) for k, t in p.items()}
+    drop = dict(ones)
+    drop["stochastic_depth.1"] = torch.zeros(())
+    O.wav2vec2_for_ctc(x, q, cfg, drop=drop).sum().backward()
+    assert q["wav2vec2/encoder/layers/1/feed_forward/output_dense/kernel"].grad.abs().max() == 0
+    assert q["wav2vec2/encoder/layers/0/feed_forward/output_dense/kernel"].grad.abs().max() > 0
+    head = dict(ones)
+    head["head"] = torch.ones(B, T, d)
+    head["head"][:, :, 5] = 0.0
+    got = O.wav2vec2_for_ctc(x, p, cfg, drop=head)
+    hidden = O.wav2vec2_model(x, p, cfg)
+    assert torch.allclose(ref - got, hidden[:, :, 5:6] * p["lm_head/kernel"][5][None, None, :], atol=1e-5)
