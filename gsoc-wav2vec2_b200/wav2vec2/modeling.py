@@ -553,7 +553,7 @@ class Wav2Vec2Model(_B200Model):
         self._warn_mask(attention_mask)
         if self._use_graph and not training:
             return self._graphed(self._hidden_eager, batch, attention_mask).clone()
-        if training and self.config.dropout and attention_mask is None:
+        if training and (self.config.dropout or self.config.survival_prob < 1.0) and attention_mask is None:
             _, x_f32, (B, T, d) = self._training_forward(batch)
             return x_f32.view(B, T, d).clone()
         x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
@@ -585,7 +585,7 @@ class Wav2Vec2ForCTC(_B200Model):
         return self._forward_impl(batch, attention_mask, training)
 
     def _forward_impl(self, batch, attention_mask, training):
-        if training and self.config.dropout and attention_mask is None:
+        if training and (self.config.dropout or self.config.survival_prob < 1.0) and attention_mask is None:
             logits, hidden, _ = self._training_forward(batch)      # hidden = the (dropped) input of lm_head
             return logits.clone(), hidden
         hidden, xs, (B, T, d) = self._encode(batch, attention_mask, training)
