@@ -11,6 +11,7 @@ breakdown_ms, logits_max_abs_err*).
 """
 import argparse
 import json
+import logging
 import os
 import sys
 import threading
@@ -283,6 +284,7 @@ def main():
     ap.add_argument("--seq", type=int, default=246000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the bf16x3 / large / train sub-records of the default line")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~100 kernels of a forward eagerly instead of replaying one CUDA graph")
     args = ap.parse_args()
 
@@ -321,24 +323,31 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput
-    n0 = ops.LAUNCHES
-    model(x)                                   # eager: packs weights, sizes the arena, counts the kernels of one forward
-    launches_per_forward = ops.LAUNCHES - n0
-    if not args.no_graph:
-        model.enable_cuda_graph(True)          # public API: the same launch sequence replayed as one CUDA graph per step
-    for _ in range(W):
-        model(x)
-    barrier()
-    launches0 = ops.LAUNCHES
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        e0.record()
-        for _ in range(K):
-            logits = model(x)
-        e1.record()
+    def timed_forward(mdl, inp, steps, sample_clocks=False):
+        """W warm-ups, then `steps` forwards between CUDA events (barrier + synchronize on both sides)."""
+        n0 = ops.LAUNCHES
+        mdl(inp)                               # eager: packs weights, sizes the arena, counts the kernels of one forward
+        per_forward = ops.LAUNCHES - n0
+        if not args.no_graph:
+            mdl.enable_cuda_graph(True)        # public API: the same launch sequence replayed as one CUDA graph per step
+        for _ in range(W):
+            mdl(inp)
         barrier()
-    launches = (ops.LAUNCHES - launches0) if args.no_graph else launches_per_forward * K   # kernels inside the replays
-    ms = e0.elapsed_time(e1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.__enter__()
+        a.record()
+        for _ in range(steps):
+            out = mdl(inp)
+        b.record()
+        barrier()
+        if sampler:
+            sampler.__exit__()
+        return a.elapsed_time(b), out, per_forward, sampler
+
+    ms, logits, launches_per_forward, clk = timed_forward(model, x, K, sample_clocks=True)
+    launches = launches_per_forward * K        # kernels inside the timed region (eager launches or graph replays)
     # ---------------- end to end through the public API: pinned host input -> logits on the host, every step.
     # The input copy of step i+1 runs on a copy stream into the other of two device buffers while step i computes;
     # every step still pays its own H2D copy and its own D2H read inside the timed region.
@@ -382,7 +391,41 @@ def main():
 
     # ---------------- per-kernel-class device times (CUDA events on the launching stream)
     model.enable_cuda_graph(False)             # per-kernel events need the eager launch sequence
-    breakdown, gemm_ffn1 = profile_classes(model, x, cfg, steps=min(K, 5))
+    breakdown_eager, gemm_ffn1 = profile_classes(model, x, cfg, steps=min(K, 5))
+
+    # ---------------- the parity-green mode, timed on the same workload: precision="bf16x3" (the drop-in default)
+    sub = {}
+    if args.precision == "bf16" and not args.headline_only:
+        par = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision="bf16x3", device=dev)
+        par.set_variables(model.variables)
+        ms3, logits3, _, _ = timed_forward(par, x, K)
+        par.enable_cuda_graph(False)
+        bd3, ffn1_3 = profile_classes(par, x, cfg, steps=min(K, 3))
+        sub["bf16x3"] = (ms3, logits3[:CPU_SAMPLE_BATCH].float().cpu(), bd3, ffn1_3)
+        del par, logits3
+        torch.cuda.empty_cache()
+    # ---------------- BASELINE configs[3]: wav2vec2-large (robust, 24 layers, d = 1024) inference, batch 16 x 246000
+    if (B, L) == (32, 246000) and not args.headline_only:
+        from wav2vec2 import RobustWav2Vec2Config
+        lcfg = RobustWav2Vec2Config()
+        large = Wav2Vec2ForCTC(lcfg, input_shape=(16, L), precision=args.precision, device=dev).init_random(seed=0)
+        xl = x[:16].contiguous()
+        am = torch.ones(16, L, dtype=torch.int32, device=dev)
+        logging.getLogger("wav2vec2.modeling").setLevel(logging.ERROR)
+        ms_l, _, _, _ = timed_forward(large, xl, K)
+        large.enable_cuda_graph(False)
+        bd_l, ffn1_l = profile_classes(large, xl, lcfg, steps=min(K, 3))
+        sub["large"] = (ms_l, lcfg, bd_l, ffn1_l)
+        del large, am
+        torch.cuda.empty_cache()
+    # ---------------- BASELINE configs[2]: the stage-2 CTC fine-tune step, 8 utterances per GPU, ONE NCCL all-reduce per step
+    if (B, L) == (32, 246000) and not args.headline_only:
+        sub["train"] = train_subrecord(cfg, dev, rank, world, L, W, min(K, 10), barrier)
+    t = torch.tensor([sub["bf16x3"][0] if "bf16x3" in sub else 0.0, sub["large"][0] if "large" in sub else 0.0],
+                     device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms3_max, msl_max = t.tolist()
 
     if rank != 0:
         if world > 1:
@@ -418,8 +461,37 @@ def main():
                      "traffic": traffic.get("ffn1_gemm_bytes_per_launch") if (B, L) == (32, 246000) else None,
                      "algorithmic_flops_per_launch": ffn1_flops,
                      "peak_source": peaks["source"] + " (burst cuBLAS bf16; sustained %.0f)" % peaks["bf16_tflops_sustained"]},
-        "breakdown_ms": breakdown,
     }
+    # per-class device time: CUDA events around every eager launch give the SHARES; they are scaled to the graph-replayed step
+    # (eager launches lose the PDL overlap, so their raw sum exceeds ms_per_step - kept as breakdown_eager_ms)
+    result["breakdown_ms"] = scale_breakdown(breakdown_eager, ms / K)
+    result["breakdown_eager_ms"] = breakdown_eager
+    result["roofline_classes"] = class_rooflines(result["breakdown_ms"], cfg, B, L, peaks, passes=1 if args.precision == "bf16" else 3)
+    if "bf16x3" in sub:
+        _, _, bd3, ffn1_3 = sub["bf16x3"]
+        ach3 = ffn1_flops / (ffn1_3 * 1e-3) / 1e12 if ffn1_3 else None
+        result["value_bf16x3"] = audio_s / (ms3_max / K / 1e3)
+        result["ms_per_step_bf16x3"] = ms3_max / K
+        result["roofline_bf16x3"] = {"bound": "tensor", "kernel": "FFN1 GEMM, 3 MMAs per product (hi*hi + lo*hi + hi*lo)",
+                                     "achieved": ach3, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                     "frac": (ach3 / peaks["bf16_tflops"]) if ach3 else None,
+                                     "note": "ALGORITHMIC flops (2MKN counted once); the tensor pipe executes 3x that"}
+        result["breakdown_ms_bf16x3"] = scale_breakdown(bd3, ms3_max / K)
+    if "large" in sub:
+        _, lcfg, bd_l, ffn1_l = sub["large"]
+        lfl = flops_forward(lcfg, L)
+        lf1 = 2.0 * 16 * T * lcfg.hidden_size * lcfg.intermediate_size
+        ach_l = lf1 / (ffn1_l * 1e-3) / 1e12 if ffn1_l else None
+        result["large"] = {"workload": f"wav2vec2-large (robust: 24 layers, d=1024, layer-norm extractor, pre-norm, attention mask off) "
+                                       f"inference, batch=16/GPU, seq={L}", "dtype": args.precision,
+                           "ms_per_step": msl_max / K, "value": world * 16 * L / SAMPLE_RATE / (msl_max / K / 1e3),
+                           "unit": "audio-sec/s", "model_tflops": lfl["total"] * 16 * world / (msl_max / K / 1e3) / 1e12,
+                           "roofline": {"bound": "tensor", "kernel": f"FFN1 [{16 * T}x1024]x[1024x4096] + bias + GELU",
+                                        "achieved": ach_l, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                                        "frac": (ach_l / peaks["bf16_tflops"]) if ach_l else None},
+                           "breakdown_ms": scale_breakdown(bd_l, msl_max / K)}
+    if "train" in sub:
+        result["train"] = sub["train"]
     # conv0 (the HBM-bound kernel): algorithmic bytes = 4*L + 2*512*T0 per utterance
     if breakdown.get("conv0"):
         by = B * (4.0 * L + 2.0 * 512 * fl["frames"][0])
@@ -428,10 +500,104 @@ def main():
                                     "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": by,
                                     "traffic": traffic.get("conv0_bytes_per_launch") if (B, L) == (32, 246000) else None}
     if not args.no_cpu_baseline:
-        result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args))
+        result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args, sub.get("bf16x3")))
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
+
+
+def scale_breakdown(eager, step_ms):
+    tot = sum(eager.values())
+    return {k: round(v * step_ms / tot, 4) for k, v in eager.items()} if tot > 0 else {}
+
+
+def class_rooflines(breakdown, cfg, B, L, peaks, passes):
+    """Achieved fraction of the measured peak per kernel class: algorithmic FLOPs (2*MAC, counted once in 3-pass mode) against
+    the cuBLAS bf16 burst peak for the tensor-core classes, algorithmic bytes against the measured copy bandwidth for the
+    HBM-bound ones (conv0: 4 L in + 2 x 512 x T0 out per utterance; LayerNorm: 4 d in + 2 d out (+ planes) per row and launch)."""
+    fl = flops_forward(cfg, L)
+    T, d, nl = fl["frames"][-1], cfg.hidden_size, cfg.num_layers
+    planes = 2 if passes == 3 else 1
+    tensor = {"conv1-6 (implicit GEMM)": sum(fl["convs"][1:]), "gemm ffn1": nl * fl["per_layer"]["ffn"] / 2,
+              "gemm ffn2": nl * fl["per_layer"]["ffn"] / 2, "gemm qkv": nl * fl["per_layer"]["qkv"],
+              "gemm out_proj": nl * fl["per_layer"]["out"], "attention": nl * fl["per_layer"]["attn"],
+              "posconv": fl["other"]["posconv"], "gemm proj": fl["other"]["proj"], "gemm lm_head": fl["other"]["lm_head"]}
+    ln_launches = 2 * nl + 2
+    hbm = {"conv0": 4.0 * L + 2.0 * planes * cfg.filter_sizes[0] * fl["frames"][0],
+           "conv0 stats+fold": 4.0 * L,
+           "layernorm": ln_launches * T * d * (4.0 + 2.0 * planes)}
+    out = {}
+    for k, ms in breakdown.items():
+        if ms <= 0:
+            continue
+        if k in tensor:
+            a = tensor[k] * B / (ms * 1e-3) / 1e12
+            out[k] = {"bound": "tensor", "achieved": round(a, 1), "unit": "TFLOP/s", "frac": round(a / peaks["bf16_tflops"], 3)}
+        elif k in hbm:
+            a = hbm[k] * B / (ms * 1e-3) / 1e9
+            out[k] = {"bound": "hbm", "achieved": round(a, 1), "unit": "GB/s", "frac": round(a / peaks["hbm_gbs"], 3)}
+    return out
+
+
+def train_subrecord(cfg_unused, dev, rank, world, L, W, K, barrier):
+    """BASELINE configs[2] inside the default line: stage-2 CTC fine-tune step of wav2vec2-base (src/main.py:234-250) with the
+    reference's training defaults (dropout 0.1, SpecAugment), 8 utterances of 246000 samples per GPU, data parallel with ONE
+    NCCL all-reduce of the flat fp32 gradient buffer per step (world > 1).  Timed like the headline: W warm-ups, K steps between
+    CUDA events, max over ranks; the all-reduce is also timed alone on the same buffer."""
+    import numpy as np
+    import torch.distributed as dist
+    from wav2vec2 import CTCLoss, Wav2Vec2Config, Wav2Vec2ForCTC, ops
+    from wav2vec2.training import Stage2Trainer
+    Bt = 8
+    cfg = Wav2Vec2Config()
+    model = Wav2Vec2ForCTC(cfg, input_shape=(Bt, L), precision="bf16", device=dev).init_random(seed=0)
+    trainer = Stage2Trainer(model, CTCLoss(cfg, (Bt, L), division_factor=Bt * world), learning_rate=5e-5)
+    x = torch.randn(Bt, L, generator=torch.Generator().manual_seed(100 + rank)).to(dev)
+    np.random.seed(rank)
+    lab = np.zeros((Bt, 256), dtype=np.int32)               # main.py:51: labels padded to 256
+    lab[:, :24] = np.random.randint(1, 30, size=(Bt, 24))
+    labels = torch.from_numpy(lab).to(dev)
+    n0 = ops.LAUNCHES
+    losses = [trainer.step(x, labels).item()]
+    per_step = ops.LAUNCHES - n0
+    for _ in range(max(W, 3) - 1):
+        losses.append(trainer.step(x, labels).item())
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(K):
+        loss = trainer.step(x, labels)
+    b.record()
+    barrier()
+    losses.append(loss.item())
+    ms = a.elapsed_time(b)
+    ar_ms = 0.0
+    if world > 1:
+        for _ in range(2):
+            dist.all_reduce(trainer.flat_g)
+        barrier()
+        c, d_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c.record()
+        for _ in range(5):
+            dist.all_reduce(trainer.flat_g)
+        d_.record()
+        barrier()
+        ar_ms = c.elapsed_time(d_) / 5
+    t = torch.tensor([ms, ar_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ar_ms = t.tolist()
+    nbytes = trainer.flat_g.numel() * trainer.flat_g.element_size()
+    rec = {"workload": f"wav2vec2-base stage-2 CTC fine-tune step (forward + CTC + backward + all-reduce + Adam), batch={Bt}/GPU, "
+                       f"seq={L}, dropout {cfg.dropout}, SpecAugment on", "global_batch": Bt * world, "steps": K,
+           "dtype": "bf16", "ms_per_step": ms / K, "value": world * Bt * L / SAMPLE_RATE / (ms / K / 1e3), "unit": "audio-sec/s",
+           "allreduce_ms": ar_ms, "allreduce_bytes": nbytes,
+           "allreduce_busbw_gbs": (2.0 * (world - 1) / world * nbytes / (ar_ms * 1e-3) / 1e9) if ar_ms > 0 else None,
+           "gpu_launches": per_step * K, "trainable_params": int(trainer.flat_w.numel()),
+           "loss_first_last": [losses[0], losses[-1]]}
+    del trainer, model
+    torch.cuda.empty_cache()
+    return rec
 
 
 def profile_classes(model, x, cfg, steps):
@@ -496,7 +662,7 @@ def profile_classes(model, x, cfg, steps):
     return {k: round(v, 4) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}, ffn1
 
 
-def cpu_baseline_and_error(model, cfg, x_host, logits, args):
+def cpu_baseline_and_error(model, cfg, x_host, logits, args, par_run=None):
     """cpu_baseline leg: the oracle port timed on the host cores on a bounded sample of the same workload, and the
     logits error of the GPU path against it on those utterances (checker use of oracle/ only)."""
     from oracle import w2v2_oracle as O
@@ -521,9 +687,12 @@ def cpu_baseline_and_error(model, cfg, x_host, logits, args):
                                       f"{nb} x {args.seq} samples, best of 3"},
            f"logits_max_abs_err_{args.precision}": err_fast, "logits_max_abs": ref.abs().max().item()}
     if args.precision == "bf16":
-        par = Wav2Vec2ForCTC(cfg, input_shape=tuple(xs.shape), precision="bf16x3", device=model.device)
-        par.set_variables(model.variables)
-        out["logits_max_abs_err_bf16x3"] = (par(xs.to(model.device)).float().cpu() - ref).abs().max().item()
+        if par_run is not None:              # logits of the TIMED bf16x3 run (same batch, utterances 0..nb-1)
+            out["logits_max_abs_err_bf16x3"] = (par_run[1][:nb] - ref).abs().max().item()
+        else:
+            par = Wav2Vec2ForCTC(cfg, input_shape=tuple(xs.shape), precision="bf16x3", device=model.device)
+            par.set_variables(model.variables)
+            out["logits_max_abs_err_bf16x3"] = (par(xs.to(model.device)).float().cpu() - ref).abs().max().item()
         out["argmax_agreement_bf16"] = (logits[:nb].argmax(-1).cpu() == ref.argmax(-1)).float().mean().item()
     return out
 

@@ -91,8 +91,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   const int q0 = blockIdx.x * AT_BM;
   const int h = blockIdx.y;
   const int b = blockIdx.z;
-  const int kv_len = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
-  const int nchunks = (max(kv_len, 1) + AT_BN - 1) / AT_BN;
+  // An utterance with NO valid key: the reference adds the same -10000 to every score (encoder.py:256-263), which the
+  // softmax cancels - i.e. it attends over all T keys.  Reproduce that instead of producing exp(-inf - -inf) = NaN.
+  const int kv_raw = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
+  const int kv_len = (kv_raw <= 0) ? p.T : kv_raw;
+  const int nchunks = (kv_len + AT_BN - 1) / AT_BN;
 
   if (warp == 4 && elect_one()) {
     tma_prefetch_desc(&tm_hi);
@@ -422,11 +425,8 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
   p.drop = drop;
   p.H = H;
   auto kern = attn_fwd_kernel<PASSES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
+  W2V2_CUDA(ensure_dyn_smem(kern, S::TOTAL, smem_attr_done));
   dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
   W2V2_CUDA(launch_pdl(kern, grid, dim3(AT_THREADS), (size_t)S::TOTAL, stream, 0, tm_hi, tm_lo, p));
   return 0;

@@ -31,7 +31,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int PASSES>
+template <int PASSES, bool TF_APPROX = false>   // TF_APPROX: tf.nn.gelu(approximate=True), the reference's is_gelu_approx switch
 __global__ void __launch_bounds__(256, 2)
 conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __restrict__ kernel /*[10][512]*/,
                  const float* __restrict__ scale /*[B][512]*/, const float* __restrict__ shift /*[B][512]*/,
@@ -135,7 +135,13 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
       for (int r = 0; r < 2; ++r) {
         uint64_t v = fma2(pack2(acc[i][2 * r], acc[i][2 * r + 1]), sc[i], sh[i]);
         float v0, v1;
-        if (PASSES == 3) {
+        if (TF_APPROX) {
+          unpack2(v, v0, v1);
+          v0 = gelu_tanh_tf(v0);
+          v1 = gelu_tanh_tf(v1);
+          if (PASSES == 3) oh[r][i] = split_bf16x2(v0, v1, ol[r][i]);
+          else oh[r][i] = pack_bf16x2(v0, v1);
+        } else if (PASSES == 3) {
           unpack2(v, v0, v1);
           gelu_erf_x2(v0, v1);
           oh[r][i] = split_bf16x2(v0, v1, ol[r][i]);
@@ -169,7 +175,7 @@ using namespace w2v2;
 
 extern "C" int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples, int channels, const float* kernel,
                                   const float* scale, const float* shift, void* out_hi, void* out_lo, int passes,
-                                  void* stream) {
+                                  int gelu_approx, void* stream) {
   W2V2_CHECK_ARG(wave && kernel && scale && shift && out_hi, "null pointer");
   W2V2_CHECK_ARG(channels == CM_C, "extractor layer 0 is built for 512 output channels");
   W2V2_CHECK_ARG(batch > 0 && num_samples >= 10, "need batch > 0 and at least 10 samples");
@@ -180,7 +186,12 @@ extern "C" int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples,
   dim3 grid((T0 + CM_TT - 1) / CM_TT, batch);
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  if (passes == 1)
+  if (gelu_approx) {
+    if (passes == 1)
+      W2V2_CUDA(launch_pdl(conv0_mma_kernel<1, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+    else
+      W2V2_CUDA(launch_pdl(conv0_mma_kernel<3, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+  } else if (passes == 1)
     W2V2_CUDA(launch_pdl(conv0_mma_kernel<1>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
   else
     W2V2_CUDA(launch_pdl(conv0_mma_kernel<3>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));

@@ -197,7 +197,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
       }
     }
     if (f_gelu) {
-      if (f_fast) {
+      if (EPI < 0 && p.gelu == 3) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_tanh_tf(v[j]);
+      } else if (f_fast) {
 #pragma unroll
         for (int j = 0; j < 16; j += 2) gelu_x2<true>(v[j], v[j + 1]);
       } else {
@@ -205,6 +208,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         for (int j = 0; j < 16; j += 2) gelu_x2<false>(v[j], v[j + 1]);
       }
     }
+    if (EPI < 0 && p.drop.thr16) epilogue_dropout16(p.drop, (orow0 + lane) * p.N + n0 + c0, v);
     if (f_res && lane < rows_valid) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -213,6 +217,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         v[4 * j + 2] += rr[j].z;
         v[4 * j + 3] += rr[j].w;
       }
+    }
+    if (EPI < 0 && p.row_replace != nullptr && lane < rows_valid && p.row_replace[orow0 + lane]) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __ldg(p.row_value + n0 + c0 + j);   // N % 8 == 0 and n0 + c0 < N: a full 16-column slab unless N % 16
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
@@ -503,11 +511,8 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
     if (a->out_lo && (rc = make_tmap(&om.lo, a->out_lo, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   auto kern = gemm_bf16_2sm_kernel<PASSES, EPI>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
+  W2V2_CUDA(ensure_dyn_smem(kern, S::TOTAL, smem_attr_done));
   int dev = 0, sms = 0;
   W2V2_CUDA(cudaGetDevice(&dev));
   W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -529,6 +534,9 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
   const bool f32 = a->out_f32 != nullptr, hi = a->out_hi != nullptr, lo = a->out_lo != nullptr;
   constexpr int LO = (PASSES == 3) ? EPI_LO : 0;     // the model writes hi+lo planes exactly in 3-pass mode
   constexpr int G = EPI_GELU | ((PASSES == 1) ? EPI_FASTGELU : 0);   // single-pass mode: bf16-grade tanh-form GELU
+  // the rarely used epilogue options (tf-approximate GELU, dropout, SpecAugment row replacement) only exist in the run-time instance
+  if ((a->flags & W2V2_GEMM_GELU_TANH) || a->row_replace_mask != nullptr || a->drop_p > 0.0f)
+    return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
   if (sc) {
     if (gelu && !res && !f32 && hi && lo == (PASSES == 3)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | G | EPI_HI | LO>(a, s);
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);

@@ -29,7 +29,7 @@ struct GemmParams {
   int batch;
   int n_tiles;          // ceil(N / BLOCK_N)
   int N;                // valid output columns == leading dimension of every output / residual
-  int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form (single-pass mode)
+  int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form fit of the erf GELU (single-pass mode), 3 = tf "approximate" GELU
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
   int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
   int atomic_f32;       // 1: out_f32 += result with fp32 atomics (split-K partial sums into a zeroed buffer)
@@ -42,6 +42,9 @@ struct GemmParams {
   const float* ln_gamma;  // [N]
   const float* ln_beta;   // [N]
   const int* row_valid;   // [batch] or null: rows >= row_valid[b] are written as zeros
+  const uint8_t* row_replace;  // [batch*rows_per_batch] or null: rows with a non-zero byte are written as row_value[0:N] (SpecAugment)
+  const float* row_value;      // [N]
+  DropSpec drop;               // dropout on the activation (after bias / GELU, before the residual); thr16 == 0: off
   float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -54,6 +57,17 @@ __device__ __forceinline__ float4 ln_of_residual(float4 r, float mean, float rst
   const float4 b = __ldg(reinterpret_cast<const float4*>(beta + col));
   return make_float4(fmaf((r.x - mean) * rstd, g.x, b.x), fmaf((r.y - mean) * rstd, g.y, b.y),
                      fmaf((r.z - mean) * rstd, g.z, b.z), fmaf((r.w - mean) * rstd, g.w, b.w));
+}
+
+// Dropout on 16 consecutive elements of one output row starting at flat element index `e0` (a multiple of 4): the same
+// stateless stream as w2v2_dropout_rows - 64 bits per group of four consecutive elements (w2v2_common.cuh).
+__device__ __forceinline__ void epilogue_dropout16(const DropSpec& d, size_t e0, float (&v)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const uint64_t bits = drop_bits4(d, (uint64_t)(e0 >> 2) + g);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[4 * g + e] = drop_keep(bits, e, d.thr16) ? v[4 * g + e] * d.scale : 0.0f;
+  }
 }
 
 // Epilogue of one 128 x BLOCK_N accumulator tile for one warp (32 rows; lane = row).  The two warps that share a
@@ -214,7 +228,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
         }
       }
       if (f_gelu) {
-        if (f_fast) {
+        if (EPI < 0 && p.gelu == 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = gelu_tanh_tf(v[j]);
+        } else if (f_fast) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) gelu_x2<true>(v[j], v[j + 1]);
         } else {
@@ -222,9 +239,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           for (int j = 0; j < 16; j += 2) gelu_x2<false>(v[j], v[j + 1]);
         }
       }
+      if (EPI < 0 && p.drop.thr16) epilogue_dropout16(p.drop, orow * p.N + n + 16 * hf, v);
       if (f_res) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += rf[j];
+      }
+      if (EPI < 0 && p.row_replace != nullptr && row_ok && p.row_replace[orow]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = (n + 16 * hf + j < p.N) ? __ldg(p.row_value + n + 16 * hf + j) : 0.0f;
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);

@@ -293,7 +293,7 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.batch = a->batch;
   p.n_tiles = (a->N + block_n - 1) / block_n;
   p.N = a->N;
-  p.gelu = (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form (single-pass mode)
+  p.gelu = (a->flags & W2V2_GEMM_GELU_TANH) ? 3 : (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form fit (single-pass mode)
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.mn_major = (a->flags & W2V2_GEMM_MN_MAJOR) ? 1 : 0;
@@ -306,6 +306,9 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.ln_gamma = a->res_ln_gamma;
   p.ln_beta = a->res_ln_beta;
   p.row_valid = a->row_valid;
+  p.row_replace = a->row_replace_mask;
+  p.row_value = a->row_replace_value;
+  p.drop = make_drop(a->drop_p, a->drop_seed, a->drop_site);
   p.out_f32 = a->out_f32;
   p.out_hi = reinterpret_cast<__nv_bfloat16*>(a->out_hi);
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(a->out_lo);
@@ -351,11 +354,8 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
   }
   GemmParams p = make_gemm_params(a, BLOCK_N);
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES, CLUSTER>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    W2V2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_set = true;
-  }
+  static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
+  W2V2_CUDA(ensure_dyn_smem(kern, S::TOTAL, smem_attr_done));
   int dev = 0, sms = 0;
   W2V2_CUDA(cudaGetDevice(&dev));
   W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -384,6 +384,9 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   W2V2_CHECK_ARG(a->a_row_len >= a->K || a->kb_split > 0, "a_row_len must cover K");
   W2V2_CHECK_ARG(a->out_f32 || a->out_hi, "at least one output is required");
   W2V2_CHECK_ARG(a->out_lo == nullptr || a->out_hi != nullptr, "out_lo requires out_hi");
+  W2V2_CHECK_ARG(a->row_replace_mask == nullptr || (a->row_replace_value != nullptr && a->N % 16 == 0),
+                 "row_replace_mask needs row_replace_value and N % 16 == 0");
+  W2V2_CHECK_ARG(a->drop_p >= 0.0f && a->drop_p < 1.0f && (a->drop_p == 0.0f || a->N % 16 == 0), "drop_p must be in [0, 1) (and N % 16 == 0)");
   W2V2_CHECK_ARG(a->res_ln_stats == nullptr || (a->residual && a->res_ln_gamma && a->res_ln_beta && a->N % 4 == 0),
                  "res_ln_stats needs residual, res_ln_gamma, res_ln_beta and N % 4 == 0");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -426,4 +429,4 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
 }
 
 extern "C" const char* w2v2_last_error_string(void) { return w2v2::g_last_error; }
-extern "C" int w2v2_version(void) { return 120; }   // 1.2: training entry points, res_ln_* in w2v2_gemm_args, dropout
+extern "C" int w2v2_version(void) { return 130; }   // 1.3: epilogue dropout / row replacement / tf-approximate GELU in w2v2_gemm_args, gelu_kind arguments

@@ -38,6 +38,19 @@ PFN_encodeTiled get_encode_fn();
 int make_tmap(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
               const uint32_t* box, CUtensorMapSwizzle swz, CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 
+// The dynamic-smem opt-in is a PER-DEVICE function attribute: remember it per device (bit d of `done_mask`), not per process.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, int bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done_mask & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done_mask |= bit;
+  return e;
+}
+
 bool pdl_enabled();  // W2V2_PDL=0 disables programmatic dependent launch (A/B switch)
 
 // Launch with programmatic stream serialization (+ optional static cluster size).

@@ -27,6 +27,7 @@ struct PosconvParams {
   int stages;
   int shift;              // window starts at frame tf0 - ktaps/2 + shift (0 = forward; +1 = transposed conv of the backward)
   int linear;             // 1: out = resid + acc (no bias, no GELU): the dgrad of the conv
+  int gelu_approx;        // 1: tf.nn.gelu(approximate=True) (config.py:14, encoder.py:181)
   float* pre_out;         // optional fp32 [B, T, d]: bias + conv (pre-activation kept for the backward)
   const float* bias;      // [d]
   const float* resid;     // fp32 [B, T, d]
@@ -187,8 +188,13 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
               for (int i = 0; i < 4; ++i)
                 reinterpret_cast<float4*>(p.pre_out + o)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
             }
+            if (p.gelu_approx) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 2) gelu_erf_x2(v[i], v[i + 1]);
+              for (int i = 0; i < 16; ++i) v[i] = gelu_tanh_tf(v[i]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; i += 2) gelu_erf_x2(v[i], v[i + 1]);
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -232,6 +238,7 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
   p.mt = (a->frames > 128) ? 2 : 1;
   p.shift = a->shift;
   p.linear = a->linear;
+  p.gelu_approx = a->gelu_approx;
   p.pre_out = a->pre_out;
   p.bias = a->bias;
   p.resid = a->resid;

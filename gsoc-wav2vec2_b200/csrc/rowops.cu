@@ -22,21 +22,41 @@ constexpr int C0_NSTAT = 65;    // 10 sums + 55 upper-triangular Gram entries
 constexpr int STATS_WIN_PER_BLOCK = 2048;
 
 // ------------------------------------------------------------------------------------ wave_stats
-__global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict__ wave, int L, int T0,
-                                                         double* __restrict__ stats) {
+// Bandwidth-bound: a CTA stages its contiguous slice of the waveform (2048 windows = 10245 samples, 41 KB) in smem with
+// coalesced 128-bit loads - every sample is read from HBM exactly once, ~20 independent loads in flight per thread -
+// then each thread walks 16 windows out of smem (stride 5 floats: conflict-free) with the 65 running sums in fp32
+// registers.  The 128 per-thread partials of each statistic are summed through the (re-used) smem slice: 4 serial adds +
+// one 5-step shuffle tree per statistic and warp instead of a 65 x 5 fp64 shuffle butterfly in every warp.  Only the
+// cross-CTA accumulation (25 CTAs per utterance at L = 246000) is fp64.
+constexpr int STATS_THREADS = 128;
+constexpr int STATS_SEG = STATS_WIN_PER_BLOCK * C0_S + (C0_K - C0_S);   // samples a CTA touches
+
+__global__ void __launch_bounds__(STATS_THREADS) wave_stats_kernel(const float* __restrict__ wave, int L, int T0,
+                                                                   double* __restrict__ stats) {
+  extern __shared__ __align__(16) float seg[];   // max(STATS_SEG, 65 * 128) floats
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.y;
-  const float* x = wave + (size_t)b * L;
   const int w_begin = blockIdx.x * STATS_WIN_PER_BLOCK;
-  const int w_end = min(T0, w_begin + STATS_WIN_PER_BLOCK);
+  const int nwin = min(T0 - w_begin, STATS_WIN_PER_BLOCK);
+  const float* x = wave + (size_t)b * L + (size_t)w_begin * C0_S;
+  const int n = nwin * C0_S + (C0_K - C0_S);      // valid samples of this slice (all inside the utterance)
+  const int tid = threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) {
+    const int n4 = n >> 2;
+    for (int i = tid; i < n4; i += STATS_THREADS) reinterpret_cast<float4*>(seg)[i] = __ldg(reinterpret_cast<const float4*>(x) + i);
+    for (int i = 4 * n4 + tid; i < n; i += STATS_THREADS) seg[i] = __ldg(x + i);
+  } else {
+    for (int i = tid; i < n; i += STATS_THREADS) seg[i] = __ldg(x + i);
+  }
+  __syncthreads();
   float acc[C0_NSTAT];
 #pragma unroll
   for (int i = 0; i < C0_NSTAT; ++i) acc[i] = 0.0f;
-  for (int w = w_begin + threadIdx.x; w < w_end; w += 256) {
+  for (int w = tid; w < nwin; w += STATS_THREADS) {
     float v[C0_K];
 #pragma unroll
-    for (int j = 0; j < C0_K; ++j) v[j] = __ldg(x + (size_t)w * C0_S + j);
+    for (int j = 0; j < C0_K; ++j) v[j] = seg[w * C0_S + j];
     int q = C0_K;
 #pragma unroll
     for (int i = 0; i < C0_K; ++i) {
@@ -48,22 +68,15 @@ __global__ void __launch_bounds__(256) wave_stats_kernel(const float* __restrict
       }
     }
   }
-  // <= 8 windows per thread were summed in fp32; everything above that is fp64.
-  __shared__ double red[8][C0_NSTAT];
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  __syncthreads();                                  // the slice is dead: reuse it as red[65][128]
 #pragma unroll
-  for (int i = 0; i < C0_NSTAT; ++i) {
-    double d = (double)acc[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if (lane == 0) red[warp][i] = d;
-  }
+  for (int i = 0; i < C0_NSTAT; ++i) seg[i * STATS_THREADS + tid] = acc[i];
   __syncthreads();
-  if (threadIdx.x < C0_NSTAT) {
-    double d = 0.0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) d += red[w][threadIdx.x];
-    atomicAdd(stats + (size_t)b * C0_NSTAT + threadIdx.x, d);
+  const int lane = lane_id(), warp = tid >> 5;
+  for (int i = warp; i < C0_NSTAT; i += STATS_THREADS / 32) {
+    const float4 p = *reinterpret_cast<const float4*>(seg + i * STATS_THREADS + 4 * lane);
+    const float s = warp_sum((p.x + p.y) + (p.z + p.w));
+    if (lane == 0) atomicAdd(stats + (size_t)b * C0_NSTAT + i, (double)s);
   }
 }
 
@@ -283,7 +296,12 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       float y1 = fmaf((v[i].y - mean) * rstd, g.y, bt.y);
       float y2 = fmaf((v[i].z - mean) * rstd, g.z, bt.z);
       float y3 = fmaf((v[i].w - mean) * rstd, g.w, bt.w);
-      if (gelu) {
+      if (gelu == 2) {          // tf.nn.gelu(approximate=True): config.py:14
+        y0 = gelu_tanh_tf(y0);
+        y1 = gelu_tanh_tf(y1);
+        y2 = gelu_tanh_tf(y2);
+        y3 = gelu_tanh_tf(y3);
+      } else if (gelu) {
         gelu_erf_x2(y0, y1);
         gelu_erf_x2(y2, y3);
       }
@@ -366,7 +384,8 @@ extern "C" int w2v2_wave_stats(const float* wave, int batch, int num_samples, do
   const int T0 = 1 + (num_samples - C0_K) / C0_S;
   W2V2_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * C0_NSTAT * batch, s));
   dim3 grid((T0 + STATS_WIN_PER_BLOCK - 1) / STATS_WIN_PER_BLOCK, batch);
-  W2V2_CUDA(launch_pdl(wave_stats_kernel, grid, dim3(256), 0, s, 0, wave, num_samples, T0, stats));
+  constexpr size_t smem = sizeof(float) * (STATS_SEG > C0_NSTAT * STATS_THREADS ? STATS_SEG : C0_NSTAT * STATS_THREADS);
+  W2V2_CUDA(launch_pdl(wave_stats_kernel, grid, dim3(STATS_THREADS), smem, s, 0, wave, num_samples, T0, stats));
   return 0;
 }
 

@@ -384,6 +384,14 @@ __device__ __forceinline__ uint64_t gelu_tanh_p2(uint64_t v) {
   const uint64_t h = mul2(v, pack2(0.5f, 0.5f));
   return fma2(h, t, h);
 }
+// tf.nn.gelu(approximate=True) - the reference's `is_gelu_approx` switch (config.py:14, feature_extractor.py:58,
+// encoder.py:127): 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3), evaluated as x / (1 + exp(-2u)) with
+// ex2.approx (2^-22 relative) so that it is fp32-grade in every precision mode (MUFU.TANH alone is only 2^-11).
+__device__ __forceinline__ float gelu_tanh_tf(float x) {
+  const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+  const float e = ex2_approx(-2.8853900818f * u);   // exp(-2u)
+  return __fdividef(x, 1.0f + e);
+}
 template <bool FAST>
 __device__ __forceinline__ void gelu_x2(float& x0, float& x1) {
   if (FAST) {

@@ -15,6 +15,7 @@ CSRC_DIR = os.path.join(_ROOT, "csrc")
 
 GEMM_GELU = 1
 GEMM_MN_MAJOR = 2
+GEMM_GELU_TANH = 4
 
 
 class GemmArgs(C.Structure):
@@ -31,6 +32,8 @@ class GemmArgs(C.Structure):
         ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p),
         ("res_ln_stats", C.c_void_p), ("res_ln_gamma", C.c_void_p), ("res_ln_beta", C.c_void_p),
         ("w_row_stride", C.c_int64),
+        ("row_replace_mask", C.c_void_p), ("row_replace_value", C.c_void_p),
+        ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("drop_seed", C.c_uint64),
     ]
 
 
@@ -41,7 +44,7 @@ class PosconvArgs(C.Structure):
         ("bias", C.c_void_p), ("resid", C.c_void_p), ("out_f32", C.c_void_p),
         ("batch", C.c_int32), ("frames", C.c_int32), ("hidden", C.c_int32), ("groups", C.c_int32),
         ("ktaps", C.c_int32), ("passes", C.c_int32),
-        ("pre_out", C.c_void_p), ("shift", C.c_int32), ("linear", C.c_int32),
+        ("pre_out", C.c_void_p), ("shift", C.c_int32), ("linear", C.c_int32), ("gelu_approx", C.c_int32),
     ]
 
 
@@ -64,7 +67,7 @@ SIGNATURES = {
     "w2v2_wave_stats": [_P, _I, _I, _P, _P],
     "w2v2_conv0_fold": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
     "w2v2_conv0_im2col": [_P, _I, _I, _P, _P, _P],
-    "w2v2_conv0_gn_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _P],
+    "w2v2_conv0_gn_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P],
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows_stats": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _P],

@@ -22,7 +22,7 @@ _FIELD_TABLE = (
     ("num_heads", 12, "attention heads; the sm_100a attention kernels need hidden_size / num_heads == 64"),
     ("num_layers", 12, "transformer layers"),
     ("intermediate_size", 3072, "FFN width"),
-    ("is_gelu_approx", False, "tanh GELU switch of the reference; only the exact (erf) form is implemented"),
+    ("is_gelu_approx", False, "tf.nn.gelu(approximate=...) switch of the reference: False = erf form, True = tanh form"),
     ("layer_norm_eps", 1e-5, "epsilon of every LayerNormalization"),
     ("survival_prob", 1.0, "StochasticDepth on the FFN branch, training only (tensorflow_addons.py:374-394)"),
     ("pad_id", 0, "CTC blank / label padding (losses.py:32-41)"),

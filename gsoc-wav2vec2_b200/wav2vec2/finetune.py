@@ -26,16 +26,16 @@ Batches = Callable[[], Iterable[Tuple[torch.Tensor, torch.Tensor]]]
 
 @dataclass
 class FineTuneArgs:
-    """The training knobs of src/main.py:28-62 that the recipe itself uses."""
+    """The training knobs of src/main.py:28-62 that the recipe itself uses, with the reference's defaults."""
     stage1_lr: float = 1e-3
-    stage1_epochs: int = 3
+    stage1_epochs: int = 15
     stage2_lr1: float = 1e-4
     stage2_lr2: float = 5e-5
-    stage2_transition_epochs: int = 5
+    stage2_transition_epochs: int = 10
     stage2_epochs: int = 15
     logging_steps: int = 16
     ckpt_path: Optional[str] = None
-    seed: int = 0
+    seed: int = 42
 
 
 def stage2_learning_rate(epoch: int, args: FineTuneArgs) -> float:

@@ -99,7 +99,8 @@ def _init_variable(name, shape, gen):
 
 
 class _Arena:
-    """Named activation buffers, allocated once per shape and reused across calls and layers."""
+    """Named activation buffers reused across calls and layers; a buffer is reallocated when its shape changes (captured
+    CUDA graphs therefore never share an arena with the eager path, see ``_graphed``)."""
 
     def __init__(self, device):
         self.device = device
@@ -155,10 +156,31 @@ class _B200Model:
         v = self.variables[pc + "weight_v"]
         self.variables[pc + "weight_g"] = v.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()  # tensorflow_addons.py:45-48
         self.trainable = {k: True for k in self.variables}
+        self._graphs = {}
         self._packed = None
         self._arena = None
         self._use_graph = os.environ.get("W2V2_CUDA_GRAPH", "0") == "1"
-        self._graphs = {}
+
+    # Captured CUDA graphs hold raw device pointers to the packed weights and to ``self.variables``.  Anything that replaces
+    # those tensors (set_variables / load_hf_state_dict / init_random, the trainers' re-packing) goes through this setter or
+    # calls ``_invalidate_graphs()``, so a later eval call re-captures instead of replaying against freed memory.
+    @property
+    def _packed(self):
+        return self.__dict__.get("_packed_store")
+
+    @_packed.setter
+    def _packed(self, value):
+        self.__dict__["_packed_store"] = value
+        self._invalidate_graphs()
+
+    def _invalidate_graphs(self):
+        self.__dict__["_graphs"] = {}
+
+    def _on_device(self):
+        """Kernels launch on the CURRENT device's current stream (ops._stream): make the model's device current for the call,
+        so ``device="cuda:1"`` works without a global ``torch.cuda.set_device``."""
+        import contextlib
+        return torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
 
     @staticmethod
     def _check_supported(cfg):
@@ -175,8 +197,6 @@ class _B200Model:
             raise ValueError("positional conv: channels/group must be 16..64 (multiple of 16), taps <= 128 (multiple of 4)")
         if cfg.hidden_size % 64 or cfg.intermediate_size % 64 or fs[-1] % 64:
             raise ValueError("hidden_size, intermediate_size and the last filter size must be multiples of 64")
-        if cfg.is_gelu_approx:
-            raise ValueError("only the exact (erf) GELU of the reference default is implemented")
 
     # ---------------------------------------------------------------- weights
     def set_variables(self, values: Dict[str, torch.Tensor], strict=True):
@@ -190,7 +210,7 @@ class _B200Model:
                 if tuple(t.shape) != tuple(self.variables[k].shape):
                     raise ValueError(f"{k}: shape {tuple(t.shape)} != {tuple(self.variables[k].shape)}")
                 self.variables[k] = t.detach().to(self.device, torch.float32).contiguous()
-        self._packed = None
+        self._packed = None                      # also drops every captured graph
         return missing, extra
 
     def init_random(self, seed=0):
@@ -325,6 +345,8 @@ class _B200Model:
         fe = "wav2vec2/feature_extractor/conv_layers/"
         layer_norm_convs = cfg.feature_extractor_norm_type == "layer"
         nconv = len(cfg.filter_sizes)
+        approx = bool(cfg.is_gelu_approx)        # config.py:14: tf.nn.gelu(approximate=True) instead of the erf form
+        ln_gelu = 2 if approx else 1
 
         # ---- extractor layer 0 (feature_extractor.py:54-59)
         T0 = frames[0]
@@ -338,13 +360,13 @@ class _B200Model:
             ops.wave_stats(x, stats)
             ops.conv0_fold(P["conv0.w"], v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], stats, B, L, None, fb,
                            1e-5, scale=fs)
-            ops.conv0_gn_gelu(x, P["conv0.w"], fs, fb, act, passes)
+            ops.conv0_gn_gelu(x, P["conv0.w"], fs, fb, act, passes, gelu_approx=approx)
         else:
             raw_elems = max(B * t * c for t, c in zip(frames, cfg.filter_sizes))
             raw_flat = A.get("conv.raw", (raw_elems,), f32)   # pre-norm conv output, reused by every layer
             raw = raw_flat[: B * T0 * C0].view(B * T0, C0)
             ops.conv0(x, P["conv0.w"], 0, v.get(fe + "0/conv/bias") if cfg.conv_bias else None, 0, False, out_f32=raw, channels=C0)
-            ops.ln_rows(raw, v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], 1e-5, B * T0, C0, gelu=True,
+            ops.ln_rows(raw, v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], 1e-5, B * T0, C0, gelu=ln_gelu,
                         out_hi=act.hi, out_lo=act.lo)
         # ---- extractor layers 1.. as implicit GEMMs
         last_f32 = None
@@ -361,25 +383,25 @@ class _B200Model:
                 g_, b_ = v[fe + f"{i}/layer_norm/gamma"], v[fe + f"{i}/layer_norm/beta"]
                 if last:
                     last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
-                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=True, out_f32=last_f32)
+                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=ln_gelu, out_f32=last_f32)
                 else:
                     nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
-                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=True, out_hi=nxt.hi, out_lo=nxt.lo)
+                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=ln_gelu, out_hi=nxt.hi, out_lo=nxt.lo)
                     act = nxt
             elif last:
                 last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
-                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, out_f32=last_f32, **geo)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, gelu_approx=approx, out_f32=last_f32, **geo)
             else:
                 nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
-                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, out_hi=nxt.hi, out_lo=nxt.lo, **geo)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, gelu_approx=approx, out_hi=nxt.hi, out_lo=nxt.lo, **geo)
                 act = nxt
         return last_f32, B, frames[-1]
 
     def _encode(self, batch, attention_mask, training):
         cfg, v = self.config, self.variables
-        if training and cfg.dropout:
-            raise NotImplementedError("training-mode forward with dropout needs the base architecture without an attention mask "
-                                      "(see _training_forward); use dropout=0 here")
+        if training and (cfg.dropout or cfg.survival_prob < 1.0):
+            raise NotImplementedError("training-mode forward with dropout / StochasticDepth needs the base architecture without an "
+                                      "attention mask (see _training_forward); use dropout=0 and survival_prob=1 here")
         last_f32, B, T = self._features(batch)
         P, A = self._packed, self._arena
         passes = _PRECISIONS[self.precision]
@@ -397,28 +419,24 @@ class _B200Model:
         ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo)
         h_f32 = A.get("h.f32", (M, d), f32)
         h = A.pair("h", (M, d), lo)
-        spec = training and cfg.apply_spec_augment
+        row_replace = None
+        if training and cfg.apply_spec_augment:
+            # modeling.py:193-199 (training only): span starts from the host numpy RNG like the reference; the replacement of the
+            # masked frames by masked_spec_embed happens in the projection GEMM's epilogue (before the padded-frame zeroing)
+            from .spec_augment import _compute_mask_indices
+            mask = _compute_mask_indices((B, T), cfg.mask_time_prob, cfg.mask_time_length, min_masks=2)
+            row_replace = (torch.from_numpy(mask.astype("uint8")).to(self.device).reshape(M).contiguous(),
+                           v["wav2vec2/masked_spec_embed"])
         ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"],
-                 row_valid=None if spec else kv_len, out_f32=h_f32, out_hi=h.hi, out_lo=h.lo, passes=passes)
-        if spec:  # modeling.py:193-199 (training only; host-side RNG like the reference's numpy RNG)
-            from .spec_augment import apply_spec_augmentation
-            hv = apply_spec_augmentation(h_f32.view(B, T, d), v["wav2vec2/masked_spec_embed"], cfg.mask_time_prob,
-                                         cfg.mask_time_length)
-            if kv_len is not None:
-                keep = torch.arange(T, device=self.device)[None, :] < kv_len[:, None]
-                hv = torch.where(keep[:, :, None], hv, torch.zeros((), device=self.device))
-            h_f32.copy_(hv.reshape(M, d))
-            sp = ops.split_bf16(h_f32, lo)
-            h.hi.copy_(sp.hi)
-            if lo:
-                h.lo.copy_(sp.lo)
+                 row_valid=kv_len, row_replace=row_replace, out_f32=h_f32, out_hi=h.hi, out_lo=h.lo, passes=passes)
 
         # ---- encoder (encoder.py:251-276)
         enc = "wav2vec2/encoder/"
         pre = cfg.attention_norm_type == "prenorm"
         y = A.get("y.f32", (M, d), f32)
         ops.posconv(h, P["pos.w"], v[enc + "pos_conv_embed/conv/bias"], h_f32, y, B, T, d,
-                    cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes)
+                    cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes,
+                    gelu_approx=bool(cfg.is_gelu_approx))
         xs_f32 = A.get("x.f32", (M, d), f32)      # residual stream
         xs = A.pair("x", (M, d), lo)              # GEMM operand view of the (normalised) stream
         st = res_ln = None
@@ -460,8 +478,8 @@ class _B200Model:
                 ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st)
                 res_ln = (st, g1, b1)
             ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M,
-                     bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, out_hi=mid.hi, out_lo=mid.lo,
-                     passes=passes)
+                     bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, gelu_approx=bool(cfg.is_gelu_approx),
+                     out_hi=mid.hi, out_lo=mid.lo, passes=passes)
             if pre:
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
                          bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=xs_f32, passes=passes)
@@ -487,12 +505,14 @@ class _B200Model:
         path is captured as is; it matters for small batches, where launch latency dominates."""
         self._use_graph = bool(on)
         if not on:
-            self._graphs = {}
+            self._invalidate_graphs()
         return self
 
     def _graphed(self, fn, batch, attention_mask):
         """Run ``fn(static_batch, static_mask)`` through a cached CUDA graph keyed by the input shapes."""
         key = (tuple(batch.shape), attention_mask is not None, fn.__name__)
+        if self._packed is None:
+            self._pack()                                 # before the lookup: packing drops the graphs of the old weights
         entry = self._graphs.get(key)
         if entry is None:
             sx = torch.empty(tuple(batch.shape), dtype=torch.float32, device=self.device)
@@ -500,14 +520,20 @@ class _B200Model:
             sx.copy_(batch)
             if sm is not None:
                 sm.copy_(attention_mask)
-            fn(sx, sm)                                   # warm-up: packs weights, allocates the arena, sets attributes
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                outs = fn(sx, sm)
-            entry = (graph, sx, sm, outs)
+            # every graph owns its activation arena: the eager arena (and other shapes' graphs) may reallocate their
+            # buffers freely without this graph replaying into freed blocks
+            eager_arena, self._arena = self._arena, _Arena(self.device)
+            try:
+                fn(sx, sm)                               # warm-up: allocates the arena, sets function attributes
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    outs = fn(sx, sm)
+                entry = (graph, sx, sm, outs, self._arena)
+            finally:
+                self._arena = eager_arena
             self._graphs[key] = entry
-        graph, sx, sm, outs = entry
+        graph, sx, sm, outs, _ = entry
         sx.copy_(batch, non_blocking=True)
         if sm is not None:
             sm.copy_(attention_mask, non_blocking=True)
@@ -551,13 +577,14 @@ class Wav2Vec2Model(_B200Model):
     @torch.no_grad()
     def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
         self._warn_mask(attention_mask)
-        if self._use_graph and not training:
-            return self._graphed(self._hidden_eager, batch, attention_mask).clone()
-        if training and (self.config.dropout or self.config.survival_prob < 1.0) and attention_mask is None:
-            _, x_f32, (B, T, d) = self._training_forward(batch)
+        with self._on_device():
+            if self._use_graph and not training:
+                return self._graphed(self._hidden_eager, batch, attention_mask).clone()
+            if training and (self.config.dropout or self.config.survival_prob < 1.0) and attention_mask is None:
+                _, x_f32, (B, T, d) = self._training_forward(batch)
+                return x_f32.view(B, T, d).clone()
+            x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
             return x_f32.view(B, T, d).clone()
-        x_f32, _, (B, T, d) = self._encode(batch, attention_mask, training)
-        return x_f32.view(B, T, d).clone()
 
     call = __call__
 
@@ -579,10 +606,11 @@ class Wav2Vec2ForCTC(_B200Model):
     def forward_with_hidden(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
         """(logits [B,T',vocab], encoder output [B*T', hidden] fp32 - an arena view valid until the next call)."""
         self._warn_mask(attention_mask)
-        if self._use_graph and not training:
-            logits, hidden = self._graphed(self._ctc_eager, batch, attention_mask)
-            return logits.clone(), hidden
-        return self._forward_impl(batch, attention_mask, training)
+        with self._on_device():
+            if self._use_graph and not training:
+                logits, hidden = self._graphed(self._ctc_eager, batch, attention_mask)
+                return logits.clone(), hidden
+            return self._forward_impl(batch, attention_mask, training)
 
     def _forward_impl(self, batch, attention_mask, training):
         if training and (self.config.dropout or self.config.survival_prob < 1.0) and attention_mask is None:
@@ -610,3 +638,4 @@ class Wav2Vec2ForCTC(_B200Model):
         if Vp != V:
             w = torch.cat([w, torch.zeros(Vp - V, w.shape[1], device=self.device)], 0)
         self._packed["lm.w"] = _split(w, _PRECISIONS[self.precision] == 3)
+        self._invalidate_graphs()                # the captured lm_head launch points at the old tensor

@@ -59,10 +59,12 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
          row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
-         res_ln=None, mn_major=False, w_row_stride=0):
+         res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
     ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
-    ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride]."""
+    ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride].
+    ``gelu_approx``: the GELU is tf.nn.gelu(approximate=True) (config.is_gelu_approx).  ``row_replace = (mask uint8 [rows],
+    value fp32 [N])``: SpecAugment row replacement; ``drop = (rate, seed, site)``: dropout before the residual add."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
     args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if passes == 3 else None
@@ -74,7 +76,13 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.w_rows = w.hi.shape[0]
     args.K, args.N, args.rows_per_batch, args.batch = K, N, rows_per_batch, batch
     args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
-    args.flags = (_lib.GEMM_GELU if gelu else 0) | (_lib.GEMM_MN_MAJOR if mn_major else 0) | (debug << 8)
+    args.flags = (_lib.GEMM_GELU if gelu else 0) | (_lib.GEMM_MN_MAJOR if mn_major else 0) | (debug << 8) | \
+        (_lib.GEMM_GELU_TANH if (gelu and gelu_approx) else 0)
+    if row_replace is not None:
+        _need_cuda(*row_replace)
+        args.row_replace_mask, args.row_replace_value = _ptr(row_replace[0]), _ptr(row_replace[1])
+    if drop is not None and drop[0] > 0.0:
+        args.drop_p, args.drop_seed, args.drop_site = float(drop[0]), int(drop[1]), int(drop[2])
     args.w_row_stride = w_row_stride
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
@@ -103,12 +111,13 @@ def conv0_im2col(wave, a: Pair):
     _count(); _lib.check(_lib.load().w2v2_conv0_im2col(_ptr(wave), B, L, _ptr(a.hi), _ptr(a.lo), _stream()), "w2v2_conv0_im2col")
 
 
-def conv0_gn_gelu(wave, kernel, scale, shift, out: Pair, passes=1):
+def conv0_gn_gelu(wave, kernel, scale, shift, out: Pair, passes=1, gelu_approx=False):
     """Fused extractor layer 0: conv (tensor cores, no im2col) + folded GroupNorm + GELU, written once."""
     _need_cuda(wave, kernel, scale, shift, out.hi, out.lo)
     B, L = wave.shape
     _count(); _lib.check(_lib.load().w2v2_conv0_gn_gelu(_ptr(wave), B, L, kernel.shape[-1], _ptr(kernel), _ptr(scale),
-                                              _ptr(shift), _ptr(out.hi), _ptr(out.lo), passes, _stream()),
+                                              _ptr(shift), _ptr(out.hi), _ptr(out.lo), passes, 1 if gelu_approx else 0,
+                                              _stream()),
                          "w2v2_conv0_gn_gelu")
 
 
@@ -135,7 +144,7 @@ def normalize_utterances(wave, lengths=None, eps=1e-5, out=None):
 def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None, stats=None):
     """``stats`` [rows, 2] fp32 (optional) receives (mean, rstd) per row for ``gemm(..., res_ln=(stats, gamma, beta))``."""
     _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo, stats)
-    _count(); _lib.check(_lib.load().w2v2_ln_rows_stats(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, 1 if gelu else 0,
+    _count(); _lib.check(_lib.load().w2v2_ln_rows_stats(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, int(gelu),
                                               _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(stats), _stream()), "w2v2_ln_rows")
 
 
@@ -146,13 +155,14 @@ def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1):
                                          _stream()), "w2v2_attn_fwd")
 
 
-def posconv(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps, passes=1):
+def posconv(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps, passes=1, gelu_approx=False):
     _need_cuda(x.hi, w.hi, bias, resid, out_f32)
     args = _lib.PosconvArgs()
     args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if passes == 3 else None
     args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
     args.bias, args.resid, args.out_f32 = _ptr(bias), _ptr(resid), _ptr(out_f32)
     args.batch, args.frames, args.hidden, args.groups, args.ktaps, args.passes = B, T, d, groups, ktaps, passes
+    args.gelu_approx = 1 if gelu_approx else 0
     _count(); _lib.check(_lib.load().w2v2_posconv(C.byref(args), _stream()), "w2v2_posconv")
 
 

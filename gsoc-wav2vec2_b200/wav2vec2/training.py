@@ -8,8 +8,11 @@ main.py:141-156) -> Adam.  Here every arithmetic step is a kernel behind the C A
 forward (all the inference kernels), ``w2v2_ctc_loss`` (loss + d loss / d logits), ``w2v2_lm_head_wgrad``, ONE
 ``torch.distributed.all_reduce`` over the flat gradient buffer (NCCL on GPUs), ``w2v2_adam``.
 
-Not covered yet (stage 2, main.py:234-250): gradients through the encoder.  Dropout RNG is not implemented, so the step
-requires ``config.dropout == 0`` (SpecAugment, main.py/modeling.py:193-199, is applied when enabled).
+Stage 2 (main.py:234-250: ``freeze_feature_extractor()``, everything else trains) is ``Stage2Trainer`` below: the full
+backward through the encoder on the same kernels, dropout at the reference's six sites from a stateless counter-based
+generator, SpecAugment and StochasticDepth.  Limits (both trainers): the training forward with dropout / StochasticDepth
+covers the base architecture (group-norm extractor, post-norm encoder) without an attention mask - which is what
+main.py:128-133 fine-tunes; other combinations raise ``NotImplementedError`` instead of silently skipping a regulariser.
 """
 import os
 
@@ -39,6 +42,7 @@ class Stage1Trainer:
         self.v = torch.zeros_like(self.flat_w)
         for name in model.trainable:
             model.trainable[name] = name.startswith("lm_head/")
+        model._invalidate_graphs()          # lm_head variables were re-bound to views of flat_w
 
     @torch.no_grad()
     def step(self, speech, labels, attention_mask=None):
@@ -141,13 +145,15 @@ class Stage2Trainer:
 
     @staticmethod
     def supports(cfg):
-        return cfg.attention_norm_type == "postnorm" and cfg.feature_extractor_norm_type == "group"
+        return cfg.attention_norm_type == "postnorm" and cfg.feature_extractor_norm_type == "group" and not cfg.is_gelu_approx
 
     def __init__(self, model: Wav2Vec2ForCTC, loss_fn: CTCLoss, learning_rate=5e-5, beta_1=0.9, beta_2=0.999,
                  epsilon=1e-7, seed=0):
         cfg = model.config
         if cfg.attention_norm_type != "postnorm" or cfg.feature_extractor_norm_type != "group":
             raise NotImplementedError("Stage2Trainer covers the base architecture (group-norm extractor, post-norm encoder)")
+        if cfg.is_gelu_approx:
+            raise NotImplementedError("Stage2Trainer differentiates the erf GELU (config.is_gelu_approx=False, the reference default)")
         self.model, self.loss_fn = model, loss_fn
         self.seed = int(seed)
         self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon
@@ -283,8 +289,6 @@ class Stage2Trainer:
         ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo)
         h_f32 = A.get("h.f32", (M, d), f32)
         h = A.pair("h", (M, d), lo)
-        ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"], out_f32=h_f32,
-                 out_hi=h.hi, out_lo=h.lo, passes=passes)
         p_drop = float(cfg.dropout)
         S["dropout"] = p_drop
 
@@ -293,19 +297,20 @@ class Stage2Trainer:
             pair.hi.copy_(sp.hi)
             if lo:
                 pair.lo.copy_(sp.lo)
-        if p_drop:                                          # feature_extractor.py:95
-            ops.dropout_rows(h_f32, self._drop(self.SITE_PROJ), out_f32=h_f32)
-            resplit(h_f32, h)
-        S["spec_mask"] = None
-        if cfg.apply_spec_augment:                         # modeling.py:193-199 (host RNG like the reference's numpy RNG)
+        # dropout after the projection (feature_extractor.py:95) and the SpecAugment replacement of masked frames by
+        # masked_spec_embed (modeling.py:193-199; span starts from the host numpy RNG like the reference) both happen in the
+        # projection GEMM's epilogue: no extra pass over h
+        S["spec_mask"], row_replace = None, None
+        if cfg.apply_spec_augment:
             if spec_mask is None:
                 from .spec_augment import _compute_mask_indices
                 spec_mask = _compute_mask_indices((B, T), cfg.mask_time_prob, cfg.mask_time_length, min_masks=2)
-            mask = torch.as_tensor(spec_mask).to(model.device).bool()
-            hv = torch.where(mask[:, :, None], v["wav2vec2/masked_spec_embed"], h_f32.view(B, T, d))
-            h_f32.copy_(hv.reshape(M, d))
-            resplit(h_f32, h)
-            S["spec_mask"] = mask.reshape(M)
+            mask = torch.as_tensor(spec_mask).to(model.device).bool().reshape(M)
+            S["spec_mask"] = mask
+            row_replace = (mask.to(torch.uint8).contiguous(), v["wav2vec2/masked_spec_embed"])
+        ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"], out_f32=h_f32,
+                 out_hi=h.hi, out_lo=h.lo, passes=passes, row_replace=row_replace,
+                 drop=self._drop(self.SITE_PROJ) if p_drop else None)
         S["pn"], S["h"] = pn, h
         enc = "wav2vec2/encoder/"
         y0 = A.get("t.y0", (M, d), f32)

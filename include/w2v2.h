@@ -46,6 +46,9 @@ const char* w2v2_last_error_string(void);
 #define W2V2_GEMM_GELU 1u /* GELU after bias (feature_extractor.py:58, encoder.py:127): erf-exact in 3-pass (parity) mode;
                              single-pass mode uses the bf16-grade tanh form (|err| < 5e-4) */
 
+#define W2V2_GEMM_GELU_TANH 4u /* GELU after bias in tf.nn.gelu(approximate=True) form - the reference's `is_gelu_approx` switch
+                                  (config.py:14); fp32-grade in every precision mode */
+
 typedef struct w2v2_gemm_args {
   /* A operand: bf16 planes, logical shape [batch][a_rows][a_row_len], element strides given. */
   const void* a_hi;
@@ -86,6 +89,16 @@ typedef struct w2v2_gemm_args {
   const float* res_ln_gamma;  /* [N] */
   const float* res_ln_beta;   /* [N] */
   int64_t w_row_stride;       /* W2V2_GEMM_MN_MAJOR only: leading dimension (elements) of Y */
+  /* optional epilogue steps of the TRAINING forward, applied in this order after bias / GELU:
+   *   dropout (feature_extractor.py:95, encoder.py:118,128): the stateless stream of w2v2_dropout_rows for (drop_seed, drop_site)
+   *     over the flat output element index, survivors x 1/(1-p); then the residual is added;
+   *   SpecAugment (modeling.py:193-199, spec_augment.py:119-128): rows whose row_replace_mask byte is non-zero are written as
+   *     row_replace_value[0:N] (masked_spec_embed) instead; then row_valid zeroing. */
+  const uint8_t* row_replace_mask; /* [batch*rows_per_batch] or NULL */
+  const float* row_replace_value;  /* [N] */
+  float drop_p;                    /* 0 = off */
+  uint32_t drop_site;
+  uint64_t drop_seed;
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
@@ -116,12 +129,14 @@ int w2v2_conv0_im2col(const float* wave, int batch, int num_samples, void* a_hi,
  * shared-memory copy of the waveform slice: no im2col tensor, the activation is written once. */
 int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples, int channels, const float* kernel /*[10][C]*/,
                        const float* scale /*[batch][C]*/, const float* shift /*[batch][C]*/, void* out_hi,
-                       void* out_lo /*NULL unless passes == 3*/, int passes, void* stream);
+                       void* out_lo /*NULL unless passes == 3*/, int passes,
+                       int gelu_approx /*0: erf GELU (config.py:14 default); 1: tf.nn.gelu(approximate=True)*/, void* stream);
 int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, const float* weights,
                int weights_batch_stride, const float* bias /*or NULL*/, int bias_batch_stride, int gelu,
                float* out_f32, void* out_hi, void* out_lo, void* stream);
 
-/* LayerNormalization over the last axis (biased variance) with optional GELU; fp32 in, outputs
+/* LayerNormalization over the last axis (biased variance) with optional GELU (gelu: 0 none, 1 erf-exact, 2 tf-approximate
+ * tanh form = is_gelu_approx, config.py:14); fp32 in, outputs
  * fp32 and/or bf16 hi(/lo).  Replaces tf.keras.layers.LayerNormalization at encoder.py:96-108,
  * 116,121,126,132,232-234,268,275 and feature_extractor.py:50,86-88,93. */
 int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
@@ -168,6 +183,7 @@ typedef struct w2v2_posconv_args {
   int32_t shift;         /* the tap window starts at frame t - ktaps/2 + shift */
   int32_t linear;        /* 1: out = resid + conv(x) (no bias, no GELU) - with flipped / transposed taps and shift = 1
                             this is the input gradient of the convolution */
+  int32_t gelu_approx;   /* 1: tf.nn.gelu(approximate=True) instead of the erf form (config.py:14, encoder.py:181) */
 } w2v2_posconv_args;
 
 int w2v2_posconv(const w2v2_posconv_args* args, void* stream);

@@ -52,6 +52,14 @@ def gelu_erf(x):
     return 0.5 * x * (1.0 + torch.erf(x * (1.0 / math.sqrt(2.0))))
 
 
+def gelu(x, cfg):
+    """``tf.nn.gelu(batch, approximate=self.is_gelu_approx)`` (config.py:14; feature_extractor.py:58; encoder.py:127):
+    erf form by default, 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) when ``is_gelu_approx``."""
+    if getattr(cfg, "is_gelu_approx", False):
+        return 0.5 * x * (1.0 + torch.tanh(math.sqrt(2.0 / math.pi) * (x + 0.044715 * x ** 3)))
+    return gelu_erf(x)
+
+
 def layer_norm(x, gamma, beta, eps):
     """Keras LayerNormalization over the last axis, biased variance."""
     mu = x.mean(-1, keepdim=True)
@@ -95,7 +103,7 @@ def feature_extractor_layer(x, p: Params, cfg, i: int, prefix="wav2vec2/"):
             y = group_norm_per_channel(y, p[base + "layer_norm/gamma"], p[base + "layer_norm/beta"], 1e-5)
     else:
         y = layer_norm(y, p[base + "layer_norm/gamma"], p[base + "layer_norm/beta"], 1e-5)
-    return gelu_erf(y)
+    return gelu(y, cfg)
 
 
 def _drop(x, drop, key):
@@ -123,7 +131,7 @@ def positional_conv_embedding(x, p: Params, cfg, prefix="wav2vec2/"):
     y = conv1d_valid(xp, kernel, p[base + "bias"], stride=1, groups=cfg.num_conv_pos_embedding_groups)
     if k % 2 == 0:
         y = y[:, :-1, :]  # encoder.py:175,179-180
-    return gelu_erf(y)
+    return gelu(y, cfg)
 
 
 def attention(x, p: Params, cfg, base: str, additive_mask=None, drop=None, layer=0):
@@ -160,8 +168,8 @@ def transformer_layer(x, p: Params, cfg, i: int, additive_mask=None, prefix="wav
     res = x
     if pre:
         x = layer_norm(x, p[base + "final_layer_norm/gamma"], p[base + "final_layer_norm/beta"], eps)
-    h = _drop(gelu_erf(dense(x, p[base + "feed_forward/intermediate_dense/kernel"],
-                             p[base + "feed_forward/intermediate_dense/bias"])), drop, f"ffn_mid.{i}")             # :127-128
+    h = _drop(gelu(dense(x, p[base + "feed_forward/intermediate_dense/kernel"],
+                             p[base + "feed_forward/intermediate_dense/bias"]), cfg), drop, f"ffn_mid.{i}")             # :127-128
     branch = dense(h, p[base + "feed_forward/output_dense/kernel"], p[base + "feed_forward/output_dense/bias"])
     # StochasticDepth (tensorflow_addons.py:374-394): eval = plain add; training = shortcut + b * residual with ONE Bernoulli
     # draw b per layer call (explicit here: drop["stochastic_depth.<i>"] in {0, 1})

@@ -35,11 +35,25 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.w2v2_version() >= 100
 
 
-def test_struct_layouts_match_header():
-    # 64-bit pointers / int64 first, then int32 fields: sizes are what the C struct has on LP64
-    assert C.sizeof(_lib.GemmArgs) == 8 * 8 + 11 * 4 + 4 + 8 * 8 + 3 * 8 + 8
-    assert C.sizeof(_lib.PackJob) == 2 * 8 + 8 * 4
-    assert C.sizeof(_lib.PosconvArgs) == 7 * 8 + 6 * 4 + 8 + 2 * 4
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every argument struct, as gcc lays out include/w2v2.h, equal the ctypes mirrors field by field."""
+    import subprocess
+    structs = {"w2v2_gemm_args": _lib.GemmArgs, "w2v2_posconv_args": _lib.PosconvArgs, "w2v2_pack_job": _lib.PackJob}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void) {']
+    for cname, ct in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == C.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
 
 
 def test_argument_errors_are_reported_not_crashed(lib):

@@ -77,8 +77,9 @@ def test_model_constructor_and_errors():
         Wav2Vec2Model({"hidden_size": 768})
     with pytest.raises(ValueError):
         Wav2Vec2ForCTC("not a config")
+    Wav2Vec2Model(Wav2Vec2Config(is_gelu_approx=True, **SMALL), device="cpu")      # both GELU forms of config.py:14 are accepted
     with pytest.raises(ValueError):
-        Wav2Vec2Model(Wav2Vec2Config(is_gelu_approx=True), device="cpu")
+        Wav2Vec2Model(Wav2Vec2Config(hidden_size=96, num_heads=2), device="cpu")   # head_size 48: not built
     m = Wav2Vec2ForCTC(Wav2Vec2Config(**SMALL), input_shape=(1, 2048), device="cpu")
     assert set(m.variables) == set(variable_shapes(m.config, True))
     g = m.variables["wav2vec2/encoder/pos_conv_embed/conv/weight_g"]

@@ -186,3 +186,78 @@ def test_too_short_input_raises():
     m, _ = _build(Wav2Vec2ForCTC, cfg, "bf16")
     with pytest.raises(ValueError):
         m(torch.randn(1, 399).cuda())
+
+
+def test_cuda_graphs_follow_weight_updates_and_shape_changes():
+    """a captured graph must never replay against replaced weights or a reallocated arena.
+    (1) set_variables after capture -> the next call equals a fresh eager model with the new weights;
+    (2) shape A graph, shape B call, shape A again -> still equals eager A (every graph owns its arena)."""
+    cfg = Wav2Vec2Config(num_layers=2)
+    m, params = _build(Wav2Vec2ForCTC, cfg, "bf16")
+    g = torch.Generator().manual_seed(11)
+    xa, xb = torch.randn(2, 16000, generator=g).cuda(), torch.randn(3, 9000, generator=g).cuda()
+    ea, eb = m(xa), m(xb)
+    m.enable_cuda_graph(True)
+    assert torch.equal(m(xa), ea)
+    assert torch.equal(m(xb), eb)
+    keep = m(xa)                                      # a user-held result while other shapes run
+    assert torch.equal(m(xb), eb) and torch.equal(m(xa), ea) and torch.equal(keep, ea)
+    params2 = O.random_params(cfg, seed=9)
+    m.set_variables(params2)
+    assert len(m._graphs) == 0                        # the captured graphs pointed at the old packed weights
+    fresh = Wav2Vec2ForCTC(cfg, precision="bf16")
+    fresh.set_variables(params2)
+    assert torch.equal(m(xa), fresh(xa))
+
+
+@pytest.mark.parametrize("arch", ["base", "robust"])
+def test_tf_approximate_gelu_switch(arch):
+    """config.is_gelu_approx=True (config.py:14): tf.nn.gelu(approximate=True) at the extractor, positional-conv and FFN
+    sites (feature_extractor.py:58, encoder.py:127,181) - parity mode vs the oracle with the same switch."""
+    kw = dict(num_layers=2, is_gelu_approx=True)
+    cfg = Wav2Vec2Config(**kw) if arch == "base" else RobustWav2Vec2Config(**kw)
+    m, params = _build(Wav2Vec2ForCTC, cfg, "bf16x3")
+    x = torch.randn(2, 12000, generator=torch.Generator().manual_seed(5))
+    got = m(x.cuda()).cpu()
+    ref = O.wav2vec2_for_ctc(x, params, cfg)
+    exact = O.wav2vec2_for_ctc(x, params, Wav2Vec2Config(num_layers=2) if arch == "base" else RobustWav2Vec2Config(num_layers=2))
+    err = (got - ref).abs().max().item()
+    print(f"{arch} is_gelu_approx: max-abs err {err:.3e}; approx-vs-erf oracle difference {(ref - exact).abs().max():.3e}")
+    assert err < 1e-3
+    fast = Wav2Vec2ForCTC(cfg, precision="bf16")
+    fast.set_variables(params)
+    assert (fast(x.cuda()).cpu() - ref).abs().max().item() < 1e-1
+
+
+def test_utterance_without_valid_frames_stays_finite():
+    """An attention mask shorter than the receptive field gives ZERO valid frames: the reference's additive -10000 on every key
+    cancels in the softmax (encoder.py:256-263), so it attends over all keys and stays finite - no NaN from exp(-inf + inf)."""
+    cfg = RobustWav2Vec2Config(num_layers=2)
+    m, params = _build(Wav2Vec2ForCTC, cfg, "bf16x3")
+    x = torch.randn(2, 8000, generator=torch.Generator().manual_seed(6))
+    am = torch.ones(2, 8000, dtype=torch.int32)
+    am[1, 300:] = 0                                   # 300 samples < 400: no frame survives
+    x = x * am
+    got = m(x.cuda(), attention_mask=am.cuda()).cpu()
+    ref = O.wav2vec2_for_ctc(x, params, cfg, attention_mask=am)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 1e-3
+
+
+def test_training_call_applies_spec_augment_in_the_projection_epilogue():
+    """model(x, training=True) with dropout 0: the SpecAugment replacement (modeling.py:193-199) happens inside the projection
+    GEMM; with the mask the call sampled (same numpy seed) the oracle gives the same hidden states, also with an attention mask."""
+    from wav2vec2.spec_augment import _compute_mask_indices
+    cfg = RobustWav2Vec2Config(num_layers=2, dropout=0.0, apply_spec_augment=True)
+    m, params = _build(Wav2Vec2Model, cfg, "bf16x3")
+    x = torch.randn(2, 20000, generator=torch.Generator().manual_seed(8))
+    am = torch.ones(2, 20000, dtype=torch.int32)
+    am[0, -4000:] = 0
+    T = cfg.num_frames(20000)
+    np.random.seed(123)
+    got = m(x.cuda(), attention_mask=am.cuda(), training=True).cpu()
+    np.random.seed(123)
+    mask = _compute_mask_indices((2, T), cfg.mask_time_prob, cfg.mask_time_length, min_masks=2)
+    ref = O.wav2vec2_model(x, params, cfg, attention_mask=am, spec_mask=torch.from_numpy(mask).bool())
+    assert mask.sum() > 0
+    assert (got - ref).abs().max().item() < 1e-3
