@@ -282,7 +282,7 @@ def main():
     ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="infer: BASELINE configs[1] (default, the headline); train: configs[2], the stage-2 fine-tune step")
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default 32 for infer, 8 for train)")
     ap.add_argument("--seq", type=int, default=246000)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp16", "fp16f8"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--headline-only", action="store_true", help="skip the bf16x3 / large / train sub-records of the default line")
     ap.add_argument("--no-graph", action="store_true", help="launch the ~100 kernels of a forward eagerly instead of replaying one CUDA graph")
@@ -395,13 +395,14 @@ def main():
 
     # ---------------- the parity-green mode, timed on the same workload: precision="bf16x3" (the drop-in default)
     sub = {}
-    if args.precision == "bf16" and not args.headline_only:
-        par = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision="bf16x3", device=dev)
+    other_modes = [m for m in ("bf16x3", "fp16f8", "fp16") if m != args.precision] if not args.headline_only else []
+    for prec in other_modes:
+        par = Wav2Vec2ForCTC(cfg, input_shape=(B, L), precision=prec, device=dev)
         par.set_variables(model.variables)
         ms3, logits3, _, _ = timed_forward(par, x, K)
         par.enable_cuda_graph(False)
         bd3, ffn1_3 = profile_classes(par, x, cfg, steps=min(K, 3))
-        sub["bf16x3"] = (ms3, logits3[:CPU_SAMPLE_BATCH].float().cpu(), bd3, ffn1_3)
+        sub[prec] = (ms3, logits3[:CPU_SAMPLE_BATCH].float().cpu(), bd3, ffn1_3)
         del par, logits3
         torch.cuda.empty_cache()
     # ---------------- BASELINE configs[3]: wav2vec2-large (robust, 24 layers, d = 1024) inference, batch 16 x 246000
@@ -421,11 +422,11 @@ def main():
     # ---------------- BASELINE configs[2]: the stage-2 CTC fine-tune step, 8 utterances per GPU, ONE NCCL all-reduce per step
     if (B, L) == (32, 246000) and not args.headline_only:
         sub["train"] = train_subrecord(cfg, dev, rank, world, L, W, min(K, 10), barrier)
-    t = torch.tensor([sub["bf16x3"][0] if "bf16x3" in sub else 0.0, sub["large"][0] if "large" in sub else 0.0],
-                     device=dev, dtype=torch.float64)
+    t = torch.tensor([sub["large"][0] if "large" in sub else 0.0] + [sub[m][0] for m in other_modes], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms3_max, msl_max = t.tolist()
+    msl_max, mode_ms = t.tolist()[0], dict(zip(other_modes, t.tolist()[1:]))
+    ms3_max = mode_ms.get("bf16x3", 0.0)
 
     if rank != 0:
         if world > 1:
@@ -440,10 +441,12 @@ def main():
     fl = flops_forward(cfg, L)
     ffn1_flops = 2.0 * B * T * cfg.hidden_size * cfg.intermediate_size
     achieved = ffn1_flops / (gemm_ffn1 * 1e-3) / 1e12 if gemm_ffn1 else None
+    breakdown = breakdown_eager               # conv0 / FFN1 rooflines use the event-timed launches themselves
     result = {
         "metric": "audio-sec/s", "value": value, "unit": "audio-sec/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32-equivalent operands)",
+        "dtype": {"bf16": "bf16", "bf16x3": "bf16x3 (split-bf16, fp32-equivalent operands)", "fp16": "fp16",
+                  "fp16f8": "fp16f8 (fp16 products + e4m3 cross terms)"}[args.precision],
         "data": "synthetic",
         "config": {"workload": f"wav2vec2-base inference (Wav2Vec2ForCTC forward), batch={B}/GPU, seq={L} -> {T} frames",
                    "global_batch": B * world, "seq_len": L, "parallelism": f"dp{world} (batch sharded, no collective)",
@@ -477,6 +480,16 @@ def main():
                                      "frac": (ach3 / peaks["bf16_tflops"]) if ach3 else None,
                                      "note": "ALGORITHMIC flops (2MKN counted once); the tensor pipe executes 3x that"}
         result["breakdown_ms_bf16x3"] = scale_breakdown(bd3, ms3_max / K)
+    # every precision mode on the SAME workload: step time, throughput, cost relative to the headline mode, FFN1 roofline on
+    # algorithmic flops (logits errors vs the CPU oracle are added by the cpu_baseline leg)
+    result["modes"] = {args.precision: {"ms_per_step": ms / K, "value": value, "rel_step": 1.0}}
+    for m in other_modes:
+        _, _, bdm, f1 = sub[m]
+        am = ffn1_flops / (f1 * 1e-3) / 1e12 if f1 else None
+        result["modes"][m] = {"ms_per_step": mode_ms[m] / K, "value": audio_s / (mode_ms[m] / K / 1e3),
+                              "rel_step": mode_ms[m] / ms, "ffn1_algorithmic_tflops": am,
+                              "ffn1_frac_of_bf16_peak": (am / peaks["bf16_tflops"]) if am else None,
+                              "breakdown_ms": scale_breakdown(bdm, mode_ms[m] / K)}
     if "large" in sub:
         _, lcfg, bd_l, ffn1_l = sub["large"]
         lfl = flops_forward(lcfg, L)
@@ -496,11 +509,15 @@ def main():
     if breakdown.get("conv0"):
         by = B * (4.0 * L + 2.0 * 512 * fl["frames"][0])
         gbs = by / (breakdown["conv0"] * 1e-3) / 1e9
+        with_stats = by / ((breakdown["conv0"] + breakdown.get("conv0 stats+fold", 0.0)) * 1e-3) / 1e9
         result["roofline_conv0"] = {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                     "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": by,
+                                    "frac_incl_stats_pass": with_stats / peaks["hbm_gbs"],
                                     "traffic": traffic.get("conv0_bytes_per_launch") if (B, L) == (32, 246000) else None}
     if not args.no_cpu_baseline:
-        result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args, sub.get("bf16x3")))
+        result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args, {m: sub[m][1] for m in other_modes}))
+        for m in result.get("modes", {}):
+            result["modes"][m]["logits_max_abs_err"] = result.get(f"logits_max_abs_err_{m}")
     print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
@@ -662,7 +679,7 @@ def profile_classes(model, x, cfg, steps):
     return {k: round(v, 4) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}, ffn1
 
 
-def cpu_baseline_and_error(model, cfg, x_host, logits, args, par_run=None):
+def cpu_baseline_and_error(model, cfg, x_host, logits, args, mode_logits=None):
     """cpu_baseline leg: the oracle port timed on the host cores on a bounded sample of the same workload, and the
     logits error of the GPU path against it on those utterances (checker use of oracle/ only)."""
     from oracle import w2v2_oracle as O
@@ -686,10 +703,10 @@ def cpu_baseline_and_error(model, cfg, x_host, logits, args, par_run=None):
                             "sample": f"oracle port (torch CPU fp32, stand-in for the reference's TF-2 CPU path) on "
                                       f"{nb} x {args.seq} samples, best of 3"},
            f"logits_max_abs_err_{args.precision}": err_fast, "logits_max_abs": ref.abs().max().item()}
+    for m, lg in (mode_logits or {}).items():     # logits of the TIMED runs of the other precision modes (same batch, utterances 0..nb-1)
+        out[f"logits_max_abs_err_{m}"] = (lg[:nb] - ref).abs().max().item()
     if args.precision == "bf16":
-        if par_run is not None:              # logits of the TIMED bf16x3 run (same batch, utterances 0..nb-1)
-            out["logits_max_abs_err_bf16x3"] = (par_run[1][:nb] - ref).abs().max().item()
-        else:
+        if "bf16x3" not in (mode_logits or {}):
             par = Wav2Vec2ForCTC(cfg, input_shape=tuple(xs.shape), precision="bf16x3", device=model.device)
             par.set_variables(model.variables)
             out["logits_max_abs_err_bf16x3"] = (par(xs.to(model.device)).float().cpu() - ref).abs().max().item()

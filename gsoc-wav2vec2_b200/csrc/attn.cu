@@ -60,9 +60,11 @@ struct AttnParams {
   __nv_bfloat16* out_lo;
   DropSpec drop;       // attention-probability dropout of the training forward (encoder.py:42); thr16 == 0: off
   int H;
+  int out_format;      // W2V2_OUT_*: 0 bf16 hi(/lo), 1 fp16 hi(/lo) of value * 2^4, 2 fp16 hi + e4m3 pair plane [rows][2 d]
 };
 
-template <int PASSES>
+// FP16: q / k / v are fp16 planes of value * 2^4 (modes 17 / 19): S comes out at 2^8, O at 2^4; P is packed as fp16.
+template <int PASSES, bool FP16>
 __global__ void __launch_bounds__(AT_THREADS, (PASSES == 1) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                 const AttnParams p) {
@@ -70,7 +72,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   constexpr int KV_STAGES = S::KV_STAGES;
   constexpr int TMEM_COLS = 256;  // S: columns [0,128), O: columns [128,192), P (single-pass mode): columns [192,256)
   constexpr bool P_IN_TMEM = (PASSES == 1) && AT_P_IN_TMEM;
-  constexpr float LOG2E = 1.4426950408889634f;
+  constexpr float LOG2E = FP16 ? 1.4426950408889634f / (ACT_SCALE * ACT_SCALE) : 1.4426950408889634f;   // of the SCALED score
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
@@ -155,8 +157,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   } else if (warp == 5) {
     // ---------------------------------------------------------------- MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_s = idesc_bf16(AT_BM, AT_BN, 0, 0);   // S = Q K^T : A, B K-major
-      constexpr uint32_t idesc_pv = idesc_bf16(AT_BM, AT_DH, 0, 1);  // PV: A = P K-major, B = V MN-major
+      constexpr uint32_t idesc_s = idesc_16bit(FP16, AT_BM, AT_BN, 0, 0);   // S = Q K^T : A, B K-major
+      constexpr uint32_t idesc_pv = idesc_16bit(FP16, AT_BM, AT_DH, 0, 1);  // PV: A = P K-major, B = V MN-major
       const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
       const uint32_t p_addr = smem_u32(smem + S::P_OFF);
       mbar_wait(q_full, 0);
@@ -340,7 +342,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         uint32_t pk[2][32];
 #pragma unroll
         for (int c = 0; c < 64; ++c)
-          pk[c >> 5][c & 31] = pack_bf16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]));
+          pk[c >> 5][c & 31] = FP16 ? pack_f16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]))
+                                    : pack_bf16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]));
         tmem_st_32x32b_x32(tmem_p + lane_sel, pk[0]);
         tmem_st_32x32b_x32(tmem_p + lane_sel + 32, pk[1]);
         tmem_st_wait();
@@ -354,7 +357,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
             uint32_t hi[4], lo[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              hi[e] = split_bf16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e]);
+              hi[e] = FP16 ? split_f16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e])
+                           : split_bf16x2(__uint_as_float(sr[pc][8 * q + 2 * e]), __uint_as_float(sr[pc][8 * q + 2 * e + 1]), lo[e]);
             const uint32_t chunk = (uint32_t)((pc & 1) * 4 + q);
             const uint32_t off = half_off + ((chunk ^ swz) << 4);
             *reinterpret_cast<uint4*>(p_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
@@ -371,7 +375,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     mbar_wait(pv_done, (nchunks - 1) & 1);
     tc_fence_after();
     const int t = q0 + r;
-    const float inv = 1.0f / l_run;
+    // O sits at the scale of v (2^4 in the fp16 modes); the fp16 output planes want value * 2^4 again
+    const float inv = (1.0f / l_run) * ((FP16 ? 1.0f / ACT_SCALE : 1.0f) * (p.out_format != 0 ? ACT_SCALE : 1.0f));
     const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
 #pragma unroll
     for (int piece = 0; piece < 2; ++piece) {
@@ -379,15 +384,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       tmem_ld_32x32b_x32(o_addr + piece * 32, rr);
       tmem_ld_wait();
       if (t < p.T) {
+        if (p.out_format == 2) {
+          // fp16 plane + e4m3 pair plane: this head's 64 columns are one 128-byte group of the byte plane [rows][2 d]
+          uint8_t* p8 = reinterpret_cast<uint8_t*>(p.out_lo) + ((size_t)b * p.T + t) * p.d * 2 + (size_t)h * 128 + piece * 32;
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {       // 16 columns per iteration
+            uint32_t hi[8];
+            uint16_t l8[8], h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              hi[e] = split_f16_f8x2(__uint_as_float(rr[16 * q + 2 * e]) * inv, __uint_as_float(rr[16 * q + 2 * e + 1]) * inv, l8[e], h8[e]);
+            *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 16 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 16 * q + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+            *reinterpret_cast<uint4*>(p8 + 16 * q) = make_uint4(l8[0] | ((uint32_t)l8[1] << 16), l8[2] | ((uint32_t)l8[3] << 16),
+                                                                l8[4] | ((uint32_t)l8[5] << 16), l8[6] | ((uint32_t)l8[7] << 16));
+            *reinterpret_cast<uint4*>(p8 + 64 + 16 * q) = make_uint4(h8[0] | ((uint32_t)h8[1] << 16), h8[2] | ((uint32_t)h8[3] << 16),
+                                                                     h8[4] | ((uint32_t)h8[5] << 16), h8[6] | ((uint32_t)h8[7] << 16));
+          }
+        } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            hi[e] = split_bf16x2(__uint_as_float(rr[8 * q + 2 * e]) * inv, __uint_as_float(rr[8 * q + 2 * e + 1]) * inv, lo[e]);
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(rr[8 * q + 2 * e]) * inv, v1 = __uint_as_float(rr[8 * q + 2 * e + 1]) * inv;
+            hi[e] = (p.out_format == 0) ? split_bf16x2(v0, v1, lo[e]) : split_f16x2(v0, v1, lo[e]);
+          }
           *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 8 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          if (PASSES == 3)
+          if (p.out_lo != nullptr)
             *reinterpret_cast<uint4*>(p.out_lo + off + piece * 32 + 8 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
         }
       }
     }
@@ -400,9 +426,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-template <int PASSES>
+template <int PASSES, bool FP16>
 static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int H, const int* kv_len, void* out_hi,
-                       void* out_lo, DropSpec drop, cudaStream_t stream) {
+                       void* out_lo, int out_format, DropSpec drop, cudaStream_t stream) {
   using S = AttnSmem<PASSES>;
   const int d = H * AT_DH;
   CUtensorMap tm_hi, tm_lo;
@@ -424,7 +450,8 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
   p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   p.drop = drop;
   p.H = H;
-  auto kern = attn_fwd_kernel<PASSES>;
+  p.out_format = out_format;
+  auto kern = attn_fwd_kernel<PASSES, FP16>;
   static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
   W2V2_CUDA(ensure_dyn_smem(kern, S::TOTAL, smem_attr_done));
   dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
@@ -435,23 +462,35 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
 }  // namespace w2v2
 
 static int attn_fwd_impl(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
-                         const int32_t* kv_len, void* out_hi, void* out_lo, int passes, w2v2::DropSpec drop, void* stream) {
+                         const int32_t* kv_len, void* out_hi, void* out_lo, int passes, int out_format, w2v2::DropSpec drop,
+                         void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(qkv_hi && out_hi, "null pointer");
   W2V2_CHECK_ARG(head_size == AT_DH, "only head_size == 64 is implemented (base: 768/12, large: 1024/16)");
-  W2V2_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
-  W2V2_CHECK_ARG(passes == 1 || (qkv_lo && out_lo), "3-pass mode needs the lo planes");
+  W2V2_CHECK_ARG(passes == 1 || passes == 3 || passes == 17 || passes == 19, "passes must be 1, 3 (bf16) or 17, 19 (fp16)");
+  const int np = mode_passes(passes);
+  W2V2_CHECK_ARG(np == 1 || qkv_lo, "3-pass modes need the lo planes of q / k / v");
+  W2V2_CHECK_ARG(out_format >= 0 && out_format <= 2 && (out_format != 2 || out_lo), "out_format must be 0, 1 or 2 (2 writes out_lo)");
   W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (passes == 1) return launch_attn<1>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, drop, s);
-  return launch_attn<3>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, drop, s);
+  if (passes == 1) return launch_attn<1, false>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
+  if (passes == 3) return launch_attn<3, false>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
+  if (passes == 17) return launch_attn<1, true>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
+  return launch_attn<3, true>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
+}
+
+extern "C" int w2v2_attn_fwd_ex(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
+                                int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes, int out_format,
+                                void* stream) {
+  return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes, out_format,
+                       w2v2::make_drop(0.0f, 0, 0), stream);
 }
 
 extern "C" int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
                              int head_size, const int32_t* kv_len, void* out_hi, void* out_lo, int passes,
                              void* stream) {
   return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes,
-                       w2v2::make_drop(0.0f, 0, 0), stream);
+                       (passes & 16) ? 1 : 0, w2v2::make_drop(0.0f, 0, 0), stream);
 }
 
 extern "C" int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads,
@@ -459,5 +498,5 @@ extern "C" int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int b
                                    float drop_p, uint64_t seed, uint32_t site, void* stream) {
   if (!(drop_p >= 0.0f && drop_p < 1.0f)) return w2v2::fail(-1, "%s: drop_p must be in [0, 1)", __func__);
   return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes,
-                       w2v2::make_drop(drop_p, seed, site), stream);
+                       (passes & 16) ? 1 : 0, w2v2::make_drop(drop_p, seed, site), stream);
 }

@@ -4,8 +4,14 @@
 // gradient dO, both [b][t][d] bf16.  Output dqkv[b][t][0:3d] in the same packed layout (the q part multiplied by `q_scale`,
 // so that every downstream product uses the UNSCALED projection kernels).
 //
-//     P = softmax(S), S = Q K^T;  D_i = sum_c dO_ic O_ic;  dV = P^T dO;  dP = dO V^T;  dS = P o (dP - D);
+//     P = softmax(S), S = Q K^T;  dV = P^T dO;  dP = dO V^T;  D_i = sum_j P_ij dP_ij;  dS = P o (dP - D);
 //     dQ = dS K;  dK = dS^T Q
+// D is NOT taken from the stored context as sum_c dO_ic O_ic (the FlashAttention shortcut): O was rounded to bf16 by the forward
+// and formed from bf16-rounded probabilities, so that D misses sum_j P_ij dP_ij of THIS pass by ~2^-9 |dO||O|, a per-row error
+// eps_i that leaks into dQ_i as eps_i * (P-weighted mean key) and into dK.  With near-uniform attention over 768 keys the true dS
+// is a small difference of large terms and that leak was 5 - 27 x the true dq / dk weight gradients of the upper layers
+// (tests/test_full_size_gpu.py).  Sweep 1 therefore also forms dP and accumulates sum_j P_ij dP_ij online: the row sum of dS is
+// then zero to fp32 rounding, like the exact softmax Jacobian.
 //
 // Two kernels, no atomics, deterministic:
 //   attn_bwd_dq   : CTA = 64 queries of one (b, h).  Sweep 1 over the key blocks rebuilds the softmax statistics
@@ -135,25 +141,8 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     load_a(aq[ks], sQ, m0, 16 * ks, g, q);
     load_a(ado[ks], sdO, m0, 16 * ks, g, q);
   }
-  // D_i = sum_c dO_ic O_ic for rows m0 + g and m0 + g + 8
-  float dsum[2] = {0.0f, 0.0f};
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int t = t0 + m0 + g + 8 * r;
-    if (t < T) {
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {   // this lane's 16 columns: [16 q, 16 q + 16) as two 16-byte pieces
-        const uint4 ov = __ldg(reinterpret_cast<const uint4*>(op + (size_t)t * d + 16 * q + 8 * c));
-        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(dop + (size_t)t * d + 16 * q + 8 * c));
-        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          dsum[r] += bf16_lo_to_f32(ow[e]) * bf16_lo_to_f32(gw[e]) + bf16_hi_to_f32(ow[e]) * bf16_hi_to_f32(gw[e]);
-      }
-    }
-    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 1);
-    dsum[r] += __shfl_xor_sync(0xffffffffu, dsum[r], 2);
-  }
+  (void)op;   // the stored context is not needed: D comes from this pass's own P and dP (see the header)
+  float dsum[2] = {0.0f, 0.0f};   // running sum_j exp2(s_ij - mx_i) dP_ij, normalised after sweep 1
 
   const int nkb = (klen + AB_BLK - 1) / AB_BLK;
   // K / V tiles stream through a 2-deep cp.async pipeline over the 2 * nkb stages of both sweeps (sweep 1 needs K only);
@@ -164,28 +153,38 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
   auto issue = [&](int stage) {
     const int kb2 = (stage >= nkb) ? stage - nkb : stage;
     load_tile_async(bufK[stage & 1], kp, kb2 * AB_BLK, klen, ld3, tid, 128);
-    if (stage >= nkb) load_tile_async(bufV[stage & 1], vp, kb2 * AB_BLK, klen, ld3, tid, 128);
+    load_tile_async(bufV[stage & 1], vp, kb2 * AB_BLK, klen, ld3, tid, 128);
     cp_async_commit();
   };
   issue(0);
   float mx[2] = {-INFINITY, -INFINITY}, sum[2] = {0.0f, 0.0f};
-  // ---- sweep 1: softmax statistics (log2 domain)
+  __shared__ uint8_t s_keep[2][AB_BLK][16];    // dropout keep bits of the current / next tile
+  if (dr.thr16) {
+    fill_keep_tile(s_keep[0], dr, bh, t0, 0, T, tid);
+    __syncthreads();
+  }
+  // ---- sweep 1: softmax statistics (log2 domain) and D_i = sum_j P_ij dP_ij
   for (int kb = 0; kb < nkb; ++kb) {
     issue(kb + 1);                 // stage nkb (first of sweep 2) always exists
     cp_async_wait<1>();
     __syncthreads();
     const __nv_bfloat16* sK = bufK[kb & 1];
-    float s[8][4];
+    const __nv_bfloat16* sV = bufV[kb & 1];
+    if (dr.thr16) fill_keep_tile(s_keep[(kb + 1) & 1], dr, bh, t0, ((kb + 1 < nkb) ? kb + 1 : 0) * AB_BLK, T, tid);   // next tile (or sweep 2's first)
+    float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.0f;
-      s[j + 1][0] = s[j + 1][1] = s[j + 1][2] = s[j + 1][3] = 0.0f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[j][e] = s[j + 1][e] = dp[j][e] = dp[j + 1][e] = 0.0f;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         uint32_t bb[4];
         load_b_nk_x4(bb, sK, 8 * j, 16 * ks, lane);
         mma16816(s[j], aq[ks], bb[0], bb[1]);
         mma16816(s[j + 1], aq[ks], bb[2], bb[3]);
+        load_b_nk_x4(bb, sV, 8 * j, 16 * ks, lane);
+        mma16816(dp[j], ado[ks], bb[0], bb[1]);
+        mma16816(dp[j + 1], ado[ks], bb[2], bb[3]);
       }
     }
 #pragma unroll
@@ -205,12 +204,28 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 1));
       bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, 2));
       const float nm = fmaxf(mx[r], bm);
-      float ps = 0.0f;
+      float ps = 0.0f, pd = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) ps += ex2_approx(s[j][2 * r] - nm) + ex2_approx(s[j][2 * r + 1] - nm);
+      for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float pe = ex2_approx(s[j][2 * r + e] - nm);     // 0 for masked keys (s = -inf)
+          float dpv = dp[j][2 * r + e];
+          if (dr.thr16) {   // the same dropped-and-rescaled dP as sweep 2 uses
+            const uint32_t kb4 = s_keep[kb & 1][m0 + g + 8 * r][2 * j + (q >> 1)];
+            dpv = ((kb4 >> (2 * (q & 1) + e)) & 1u) ? dpv * dr.scale : 0.0f;
+          }
+          ps += pe;
+          pd = fmaf(pe, dpv, pd);
+        }
+      }
       ps += __shfl_xor_sync(0xffffffffu, ps, 1);
       ps += __shfl_xor_sync(0xffffffffu, ps, 2);
-      sum[r] = sum[r] * exp2f(mx[r] - nm) + ps;
+      pd += __shfl_xor_sync(0xffffffffu, pd, 1);
+      pd += __shfl_xor_sync(0xffffffffu, pd, 2);
+      const float resc = exp2f(mx[r] - nm);
+      sum[r] = sum[r] * resc + ps;
+      dsum[r] = dsum[r] * resc + pd;
       mx[r] = nm;
     }
     __syncthreads();               // every warp is done with this buffer before the stage after next refills it
@@ -219,6 +234,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     lse2[r] = mx[r] + log2f(sum[r]);
+    dsum[r] = dsum[r] / sum[r];
     const int t = t0 + m0 + g + 8 * r;
     if (q == 0 && t < T) {
       lse2_out[(size_t)bh * T + t] = lse2[r];
@@ -226,12 +242,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     }
   }
 
-  // ---- sweep 2: dQ += (P o (dO V^T - D)) K
-  __shared__ uint8_t s_keep[2][AB_BLK][16];    // dropout keep bits of the current / next tile
-  if (dr.thr16) {
-    fill_keep_tile(s_keep[0], dr, bh, t0, 0, T, tid);
-    __syncthreads();
-  }
+  // ---- sweep 2: dQ += (P o (dO V^T - D)) K      (keep bits of its first tile were filled by sweep 1's last iteration)
   float dq[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) dq[j][0] = dq[j][1] = dq[j][2] = dq[j][3] = 0.0f;
@@ -246,7 +257,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __syncthreads();
     const __nv_bfloat16* sK = bufK[stage & 1];
     const __nv_bfloat16* sV = bufV[stage & 1];
-    if (dr.thr16 && kb + 1 < nkb) fill_keep_tile(s_keep[(kb + 1) & 1], dr, bh, t0, (kb + 1) * AB_BLK, T, tid);   // visible after the loop's closing barrier
+    if (dr.thr16 && kb + 1 < nkb) fill_keep_tile(s_keep[(stage + 1) & 1], dr, bh, t0, (kb + 1) * AB_BLK, T, tid);   // visible after the loop's closing barrier
     float s[8][4], dp[8][4];
 #pragma unroll
     for (int j = 0; j < 8; j += 2) {
@@ -276,7 +287,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
           const float p = (key < klen) ? ex2_approx(s[j][2 * r + e] * AB_LOG2E - lse2[r]) : 0.0f;
           float dpv = dp[j][2 * r + e];
           if (dr.thr16) {   // dP = dP_dropped o mask / (1 - p_drop)
-            const uint32_t kb4 = s_keep[kb & 1][m0 + g + 8 * r][2 * j + (q >> 1)];
+            const uint32_t kb4 = s_keep[stage & 1][m0 + g + 8 * r][2 * j + (q >> 1)];
             dpv = ((kb4 >> (2 * (q & 1) + e)) & 1u) ? dpv * dr.scale : 0.0f;
           }
           ds[2 * r + e] = p * (dpv - dsum[r]);

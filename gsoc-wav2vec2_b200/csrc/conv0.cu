@@ -31,7 +31,10 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int PASSES, bool TF_APPROX = false>   // TF_APPROX: tf.nn.gelu(approximate=True), the reference's is_gelu_approx switch
+// TF_APPROX: tf.nn.gelu(approximate=True), the reference's is_gelu_approx switch.  OUT_FMT (w2v2.h W2V2_OUT_*): 0 = bf16 hi
+// (+ lo when PASSES == 3), 1 = fp16 plane of value * 2^4, 2 = fp16 plane + e4m3 pair plane (fp16f8 mode); formats 1 / 2 always
+// run the 3-MMA window product (the kernel is HBM-bound, the extra MMAs are free) and the erf-exact GELU.
+template <int PASSES, bool TF_APPROX = false, int OUT_FMT = 0>
 __global__ void __launch_bounds__(256, 2)
 conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __restrict__ kernel /*[10][512]*/,
                  const float* __restrict__ scale /*[B][512]*/, const float* __restrict__ shift /*[B][512]*/,
@@ -135,7 +138,22 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
       for (int r = 0; r < 2; ++r) {
         uint64_t v = fma2(pack2(acc[i][2 * r], acc[i][2 * r + 1]), sc[i], sh[i]);
         float v0, v1;
-        if (TF_APPROX) {
+        if (OUT_FMT != 0) {
+          unpack2(v, v0, v1);
+          if (TF_APPROX) {
+            v0 = gelu_tanh_tf(v0);
+            v1 = gelu_tanh_tf(v1);
+          } else {
+            gelu_erf_x2(v0, v1);
+          }
+          if (OUT_FMT == 1) {
+            oh[r][i] = pack_f16x2(v0 * ACT_SCALE, v1 * ACT_SCALE);
+          } else {
+            uint16_t l8, h8;
+            oh[r][i] = split_f16_f8x2(v0 * ACT_SCALE, v1 * ACT_SCALE, l8, h8);
+            ol[r][i] = l8 | ((uint32_t)h8 << 16);
+          }
+        } else if (TF_APPROX) {
           unpack2(v, v0, v1);
           v0 = gelu_tanh_tf(v0);
           v1 = gelu_tanh_tf(v1);
@@ -159,7 +177,17 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
         __nv_bfloat16* p = out_hi + out_base + (size_t)t * CM_C;
         *reinterpret_cast<uint4*>(p) = make_uint4(oh[r][0], oh[r][1], oh[r][2], oh[r][3]);
         *reinterpret_cast<uint4*>(p + 32) = make_uint4(oh[r][4], oh[r][5], oh[r][6], oh[r][7]);
-        if (PASSES == 3) {
+        if (OUT_FMT == 2) {
+          // e4m3 pair plane [B*T0][2 * 512] bytes: the warp's 64 channels are one 128-byte group; this lane holds channels
+          // 8q..8q+7 (n-tiles 0-3) and 32+8q.. (n-tiles 4-7): 8 lo bytes each, the hi bytes 64 further
+          uint8_t* p8 = reinterpret_cast<uint8_t*>(out_lo) + ((size_t)b * T0 + t) * (2 * CM_C) + warp * 128 + 8 * q;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const uint32_t* o4 = &ol[r][4 * hb];
+            *reinterpret_cast<uint2*>(p8 + 32 * hb) = make_uint2((o4[0] & 0xFFFFu) | (o4[1] << 16), (o4[2] & 0xFFFFu) | (o4[3] << 16));
+            *reinterpret_cast<uint2*>(p8 + 32 * hb + 64) = make_uint2((o4[0] >> 16) | (o4[1] & 0xFFFF0000u), (o4[2] >> 16) | (o4[3] & 0xFFFF0000u));
+          }
+        } else if (PASSES == 3 && OUT_FMT == 0) {
           __nv_bfloat16* pl = out_lo + out_base + (size_t)t * CM_C;
           *reinterpret_cast<uint4*>(pl) = make_uint4(ol[r][0], ol[r][1], ol[r][2], ol[r][3]);
           *reinterpret_cast<uint4*>(pl + 32) = make_uint4(ol[r][4], ol[r][5], ol[r][6], ol[r][7]);
@@ -179,14 +207,18 @@ extern "C" int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples,
   W2V2_CHECK_ARG(wave && kernel && scale && shift && out_hi, "null pointer");
   W2V2_CHECK_ARG(channels == CM_C, "extractor layer 0 is built for 512 output channels");
   W2V2_CHECK_ARG(batch > 0 && num_samples >= 10, "need batch > 0 and at least 10 samples");
-  W2V2_CHECK_ARG(passes == 1 || passes == 3, "passes must be 1 or 3");
-  W2V2_CHECK_ARG((passes == 3) == (out_lo != nullptr), "out_lo is written exactly in 3-pass mode");
+  W2V2_CHECK_ARG(passes == 1 || passes == 3 || passes == 17 || passes == 25, "passes must be 1, 3, 17 (fp16) or 25 (fp16f8)");
+  W2V2_CHECK_ARG((passes == 3 || passes == 25) == (out_lo != nullptr), "out_lo is written exactly in the two-plane modes (3, 25)");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int T0 = 1 + (num_samples - 10) / 5;
   dim3 grid((T0 + CM_TT - 1) / CM_TT, batch);
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  if (gelu_approx) {
+  if (passes == 17 || passes == 25) {
+    auto kern = passes == 17 ? (gelu_approx ? conv0_mma_kernel<3, true, 1> : conv0_mma_kernel<3, false, 1>)
+                             : (gelu_approx ? conv0_mma_kernel<3, true, 2> : conv0_mma_kernel<3, false, 2>);
+    W2V2_CUDA(launch_pdl(kern, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+  } else if (gelu_approx) {
     if (passes == 1)
       W2V2_CUDA(launch_pdl(conv0_mma_kernel<1, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
     else

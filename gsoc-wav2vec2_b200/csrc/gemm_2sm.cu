@@ -125,10 +125,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         if (f_ln) rr = ln_of_residual(rr, ln_mean, ln_rstd, p.ln_gamma, p.ln_beta, n0 + c0 + 4 * j);
         const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
         float4 o;
-        o.x = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x + rr.x;
-        o.y = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y + rr.y;
-        o.z = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z + rr.z;
-        o.w = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w + rr.w;
+        o.x = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), p.acc_scale, bb.x) + rr.x;   // fmaf(a, 1, b) == a + b
+        o.y = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), p.acc_scale, bb.y) + rr.y;
+        o.z = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), p.acc_scale, bb.z) + rr.z;
+        o.w = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), p.acc_scale, bb.w) + rr.w;
         if (zero_row) o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         *reinterpret_cast<float4*>(bslot(j)) = o;
       }
@@ -190,10 +190,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), sc.z, bb.z);
         v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), sc.w, bb.w);
       } else {
-        v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
-        v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
-        v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
-        v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+        v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), p.acc_scale, bb.x);   // fmaf(a, 1, b) == a + b
+        v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), p.acc_scale, bb.y);
+        v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), p.acc_scale, bb.z);
+        v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), p.acc_scale, bb.w);
       }
     }
     if (f_gelu) {
@@ -241,9 +241,31 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
     }
   }
   if (f_hi) {
+    const int fmt = p.out_format;   // 0: bf16 hi(/lo); 1: fp16 hi(/lo) of value * 2^4; 2: fp16 hi + e4m3 pair plane
 #pragma unroll
     for (int plane = 0; plane < 2; ++plane) {
       if (plane == 1 && !f_lo) continue;
+      if (fmt == 2 && plane == 1) {
+        // e4m3 pair plane [rows][2 N] bytes: this warp's 64 columns are ONE 128-byte group = slab 0: e4m3((v - hi) 2^6) of the
+        // 64 columns, slab 1: e4m3(hi 2^-6); each slab is a 64-byte-row staging block and one bulk store
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          stage_acquire();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {      // 16 columns -> 16 bytes
+            uint16_t l8[8], h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              split_f16_f8x2(__uint_as_float(r[j >> 1][16 * (j & 1) + 2 * e]) * ACT_SCALE,
+                             __uint_as_float(r[j >> 1][16 * (j & 1) + 2 * e + 1]) * ACT_SCALE, l8[e], h8[e]);
+            const uint16_t* s8 = half == 0 ? l8 : h8;
+            *reinterpret_cast<uint4*>(slot(lane, j)) = make_uint4(s8[0] | ((uint32_t)s8[1] << 16), s8[2] | ((uint32_t)s8[3] << 16),
+                                                                  s8[4] | ((uint32_t)s8[5] << 16), s8[6] | ((uint32_t)s8[7] << 16));
+          }
+          stage_store(&om.lo, 2 * n + 64 * half);
+        }
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
         if (n + 32 * i >= p.N) continue;
@@ -252,8 +274,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         for (int j = 0; j < 4; ++j) {
           uint32_t h[4], l[4];
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            h[e] = split_bf16x2(__uint_as_float(r[i][8 * j + 2 * e]), __uint_as_float(r[i][8 * j + 2 * e + 1]), l[e]);
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(r[i][8 * j + 2 * e]), v1 = __uint_as_float(r[i][8 * j + 2 * e + 1]);
+            h[e] = (fmt == 0) ? split_bf16x2(v0, v1, l[e]) : split_f16x2(v0 * ACT_SCALE, v1 * ACT_SCALE, l[e]);
+          }
           *reinterpret_cast<uint4*>(slot(lane, j)) = plane == 0 ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(l[0], l[1], l[2], l[3]);
         }
         stage_store(plane == 0 ? &om.hi : &om.lo, n + 32 * i);
@@ -298,7 +322,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB_hi);
-    if (PASSES == 3) {
+    if (PASSES != 1) {
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
     }
@@ -342,11 +366,15 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
           for (int it = 0; it < total_kb; ++it) {
             const int pass = (PASSES == 1) ? 0 : it / p.num_kb;
             const int kb = it - pass * p.num_kb;
+            // PASSES == 2 (fp16f8): pass 0 = fp16 planes, pass 1 = the e4m3 pair planes of BOTH operands - byte tensors whose
+            // 128-byte k-block holds [lo8 x 64 | hi8 x 64] (A) / [hi8 x 64 | lo8 x 64] (W), i.e. the two cross terms as ONE K = 128 product
+            const bool f8pass = (PASSES == 2) && pass == 1;
             const CUtensorMap* ma = (pass == 1) ? &tmA_lo : &tmA_hi;
-            const CUtensorMap* mb = (pass == 2) ? &tmB_lo : &tmB_hi;
-            int kc = kb * GEMM_BLOCK_K, trow = t0;
+            const CUtensorMap* mb = (pass == 2 || f8pass) ? &tmB_lo : &tmB_hi;
+            const int kw = f8pass ? 2 * GEMM_BLOCK_K : GEMM_BLOCK_K;     // k-block width in elements of that plane
+            int kc = kb * kw, trow = t0;
             if (kb >= p.kb_split) {
-              kc = (kb - p.kb_split) * GEMM_BLOCK_K;
+              kc = (kb - p.kb_split) * kw;
               trow = t0 + 1;
             }
             mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -355,7 +383,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             const uint32_t lead_full = mapa_cluster(smem_u32(&full_bar[stage]), 0);
             if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * S::STAGE_BYTES);  // both CTAs' TMA bytes land here
             tma_load_3d_2sm(sa, ma, lead_full, kc, trow, b);
-            tma_load_2d_2sm(sb, mb, lead_full, kb * GEMM_BLOCK_K, n0);
+            tma_load_2d_2sm(sb, mb, lead_full, kb * kw, n0);
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -366,7 +394,8 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
     } else if (warp == 1) {
       // ---------------------------------------------------------------- MMA issuer (leader CTA only)
       if (leader && elect_one()) {
-        constexpr uint32_t idesc = idesc_bf16(2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);
+        const uint32_t idesc = idesc_16bit(p.fp16 != 0, 2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);
+        constexpr uint32_t idesc8 = idesc_fmt0(2 * GEMM_BLOCK_M, BLOCK_N, 0, 0);     // e4m3 x e4m3 under kind::f8f6f4
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -381,8 +410,14 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
             const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
             const uint64_t da = desc_kmajor_sw128(sa);
             const uint64_t db = desc_kmajor_sw128(sa + S::A_BYTES);
+            if (PASSES == 2 && it >= p.num_kb) {
+              // 128 e4m3 per 128-byte swizzle row: 4 MMAs of K = 32 (32 bytes per step, like 16 fp16)
 #pragma unroll
-            for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+              for (int k = 0; k < 4; ++k) umma_f8_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc8, 1);
+            } else {
+#pragma unroll
+              for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) umma_f16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (it | k) != 0);
+            }
             umma_commit_2sm_mcast(&empty_bar[stage], 3);  // slot free in both CTAs once these MMAs retire
             if (++stage == STAGES) {
               stage = 0;
@@ -494,6 +529,15 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
   if (rc) return rc;
   tmB_lo = tmB_hi;
   if (PASSES == 3 && (rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if (PASSES == 2) {
+    // e4m3 pair planes: two bytes per element, so the SAME byte strides as the 16-bit planes; 128-byte k-blocks
+    const uint64_t a8_dims[3] = {(uint64_t)a->a_row_len * 2, (uint64_t)a->a_rows, (uint64_t)a->batch};
+    const uint32_t a8_box[3] = {2 * GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+    if ((rc = make_tmap(&tmA_lo, a->a_lo, 3, a8_dims, a_strides, a8_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_UINT8))) return rc;
+    const uint64_t b8_dims[2] = {(uint64_t)a->K * 2, (uint64_t)a->w_rows};
+    const uint32_t b8_box[2] = {2 * GEMM_BLOCK_K, (uint32_t)(GEMM2_BLOCK_N / 2)};
+    if ((rc = make_tmap(&tmB_lo, a->w_lo, 2, b8_dims, b_strides, b8_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_UINT8))) return rc;
+  }
   GemmParams p = make_gemm_params(a, GEMM2_BLOCK_N);
   // output tensor maps {N, rows_per_batch, batch}: rows past an utterance are clipped by the TMA store
   Gemm2OutMaps om;
@@ -508,7 +552,11 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
     if (S::TMA_RES && (rc = make_tmap(&om.res, a->residual, 3, c_dims, s32, box32, CU_TENSOR_MAP_SWIZZLE_64B,
                                       CU_TENSOR_MAP_DATA_TYPE_FLOAT32))) return rc;
     if (a->out_hi && (rc = make_tmap(&om.hi, a->out_hi, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
-    if (a->out_lo && (rc = make_tmap(&om.lo, a->out_lo, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if (a->out_lo && a->out_format == 2) {   // byte plane [rows][2 N]: 64-byte slabs
+      const uint64_t c8_dims[3] = {(uint64_t)a->N * 2, (uint64_t)a->rows_per_batch, (uint64_t)a->batch};
+      const uint32_t box8[3] = {64, 32, 1};
+      if ((rc = make_tmap(&om.lo, a->out_lo, 3, c8_dims, s16, box8, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_DATA_TYPE_UINT8))) return rc;
+    } else if (a->out_lo && (rc = make_tmap(&om.lo, a->out_lo, 3, c_dims, s16, box16, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   auto kern = gemm_bf16_2sm_kernel<PASSES, EPI>;
   static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
@@ -528,20 +576,21 @@ static int launch_gemm_2sm_t(const w2v2_gemm_args* a, cudaStream_t stream) {
 
 // Picks the compile-time epilogue recipe matching the call (the combinations the Wav2Vec2 forward uses);
 // anything else runs the generic run-time-flag instance.
-template <int PASSES>
+template <int PASSES, bool FASTG>
 static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
   const bool gelu = (a->flags & W2V2_GEMM_GELU) != 0, res = a->residual != nullptr, sc = a->scale != nullptr;
   const bool f32 = a->out_f32 != nullptr, hi = a->out_hi != nullptr, lo = a->out_lo != nullptr;
-  constexpr int LO = (PASSES == 3) ? EPI_LO : 0;     // the model writes hi+lo planes exactly in 3-pass mode
-  constexpr int G = EPI_GELU | ((PASSES == 1) ? EPI_FASTGELU : 0);   // single-pass mode: bf16-grade tanh-form GELU
+  constexpr int LO = (PASSES != 1) ? EPI_LO : 0;     // the model writes two planes exactly in the multi-plane modes
+  // bf16 single-pass mode: bf16-grade tanh-form GELU; every mode that is more precise than that keeps the erf-exact form
+  constexpr int G = EPI_GELU | (FASTG ? EPI_FASTGELU : 0);
   // the rarely used epilogue options (tf-approximate GELU, dropout, SpecAugment row replacement) only exist in the run-time instance
   if ((a->flags & W2V2_GEMM_GELU_TANH) || a->row_replace_mask != nullptr || a->drop_p > 0.0f)
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
   if (sc) {
-    if (gelu && !res && !f32 && hi && lo == (PASSES == 3)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | G | EPI_HI | LO>(a, s);
+    if (gelu && !res && !f32 && hi && lo == (PASSES != 1)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | G | EPI_HI | LO>(a, s);
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
   }
-  if (lo == (PASSES == 3) || !hi) {
+  if (lo == (PASSES != 1) || !hi) {
     if (gelu && !res && !f32 && hi) return launch_gemm_2sm_t<PASSES, G | EPI_HI | LO>(a, s);
     if (gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, G | EPI_F32>(a, s);
     if (!gelu && !res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_F32>(a, s);
@@ -557,7 +606,9 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
 }
 
 int launch_gemm_2sm(const w2v2_gemm_args* a, cudaStream_t stream) {
-  return a->passes == 1 ? dispatch_2sm<1>(a, stream) : dispatch_2sm<3>(a, stream);
+  if (mode_f8(a->passes)) return dispatch_2sm<2, false>(a, stream);
+  if (mode_passes(a->passes) == 3) return dispatch_2sm<3, false>(a, stream);
+  return mode_fp16(a->passes) ? dispatch_2sm<1, false>(a, stream) : dispatch_2sm<1, true>(a, stream);
 }
 
 }  // namespace w2v2

@@ -45,6 +45,9 @@ struct GemmParams {
   const uint8_t* row_replace;  // [batch*rows_per_batch] or null: rows with a non-zero byte are written as row_value[0:N] (SpecAugment)
   const float* row_value;      // [N]
   DropSpec drop;               // dropout on the activation (after bias / GELU, before the residual); thr16 == 0: off
+  int fp16;               // 1: the 16-bit operand planes are fp16 (idesc format 0) instead of bf16
+  float acc_scale;        // accumulator -> value: 1, or 2^-15 for the scaled fp16 operand planes (ACT_SCALE * WGT_SCALE)
+  int out_format;         // bf16/16-bit outputs: 0 = bf16 hi(/lo), 1 = fp16 hi(/lo) of value * 2^4, 2 = fp16 hi + e4m3 pair plane
   float* out_f32;         // optional outputs, all [batch*rows_per_batch, N] row-major
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
@@ -221,10 +224,11 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), sc.z, bb.z);
           v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), sc.w, bb.w);
         } else {
-          v[4 * j + 0] = __uint_as_float(r[i][16 * hf + 4 * j + 0]) + bb.x;
-          v[4 * j + 1] = __uint_as_float(r[i][16 * hf + 4 * j + 1]) + bb.y;
-          v[4 * j + 2] = __uint_as_float(r[i][16 * hf + 4 * j + 2]) + bb.z;
-          v[4 * j + 3] = __uint_as_float(r[i][16 * hf + 4 * j + 3]) + bb.w;
+          // fmaf(acc, 1, b) == acc + b bit for bit; the fp16 modes un-scale their 2^15 accumulators here for free
+          v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), p.acc_scale, bb.x);
+          v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), p.acc_scale, bb.y);
+          v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), p.acc_scale, bb.z);
+          v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), p.acc_scale, bb.w);
         }
       }
       if (f_gelu) {
@@ -275,10 +279,15 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
             if (p.atomic_f32) atomicAdd(p.out_f32 + orow * p.N + n + j, v);
             else p.out_f32[orow * p.N + n + j] = v;
           }
-          if (f_hi) {
+          if (f_hi && p.out_format == 0) {
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             p.out_hi[orow * p.N + n + j] = h;
             if (f_lo) p.out_lo[orow * p.N + n + j] = __float2bfloat16_rn(v - __bfloat162float(h));
+          } else if (f_hi) {   // fp16 planes (format 2 needs N % 64 == 0 and never gets here)
+            uint32_t l;
+            const uint32_t h = split_f16x2(v * ACT_SCALE, 0.0f, l);
+            reinterpret_cast<uint16_t*>(p.out_hi)[orow * p.N + n + j] = (uint16_t)(h & 0xFFFFu);
+            if (f_lo) reinterpret_cast<uint16_t*>(p.out_lo)[orow * p.N + n + j] = (uint16_t)(l & 0xFFFFu);
           }
         }
       }
@@ -294,11 +303,32 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       const bool pair_lo = (i & 1) == 0 && (i + 1 < NMINE) && (chunk_of(i + 1) < NCH) && (n + 64 <= p.N);
       const bool pair_hi = (i & 1) == 1 && (n0 + chunk_of(i - 1) * 32 + 64 <= p.N);
       if (pair_hi) continue;  // already written together with chunk i-1
+      const int fmt = p.out_format;
 #pragma unroll
       for (int plane = 0; plane < 2; ++plane) {
         if (plane == 1 && !f_lo) continue;
         __nv_bfloat16* dst = plane == 0 ? p.out_hi : p.out_lo;
         const int nch = pair_lo ? 2 : 1;
+        if (fmt == 2 && plane == 1) {
+          // e4m3 pair plane [rows][2 N] bytes: per 64-column group 64 bytes of e4m3((v - hi) 2^6) then 64 bytes of e4m3(hi 2^-6)
+          // (N % 64 == 0 is checked by the launcher, so chunks always come in pairs here)
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int iu = (i + u < NMINE) ? i + u : i;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {        // 16 columns per 16-byte piece
+              uint16_t l8[8], h8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                split_f16_f8x2(__uint_as_float(r[iu][16 * j + 2 * e]) * ACT_SCALE, __uint_as_float(r[iu][16 * j + 2 * e + 1]) * ACT_SCALE,
+                               l8[e], h8[e]);
+              put(2 * u + j, make_uint4(l8[0] | (l8[1] << 16), l8[2] | (l8[3] << 16), l8[4] | (l8[5] << 16), l8[6] | (l8[7] << 16)));
+              put(4 + 2 * u + j, make_uint4(h8[0] | (h8[1] << 16), h8[2] | (h8[3] << 16), h8[4] | (h8[5] << 16), h8[6] | (h8[7] << 16)));
+            }
+          }
+          flush(reinterpret_cast<uint8_t*>(p.out_lo) + (orow0 * p.N + n) * 2, (size_t)p.N * 2, 8);
+          continue;
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           if (u >= nch) continue;
@@ -307,8 +337,10 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           for (int j = 0; j < 4; ++j) {
             uint32_t h[4], l[4];
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              h[e] = split_bf16x2(__uint_as_float(r[iu][8 * j + 2 * e]), __uint_as_float(r[iu][8 * j + 2 * e + 1]), l[e]);
+            for (int e = 0; e < 4; ++e) {
+              const float v0 = __uint_as_float(r[iu][8 * j + 2 * e]), v1 = __uint_as_float(r[iu][8 * j + 2 * e + 1]);
+              h[e] = (fmt == 0) ? split_bf16x2(v0, v1, l[e]) : split_f16x2(v0 * ACT_SCALE, v1 * ACT_SCALE, l[e]);
+            }
             put(4 * u + j, plane == 0 ? make_uint4(h[0], h[1], h[2], h[3]) : make_uint4(l[0], l[1], l[2], l[3]));
           }
         }

@@ -68,7 +68,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tmA_hi);
     tma_prefetch_desc(&tmB_hi);
-    if (PASSES == 3) {
+    if (PASSES != 1) {
       tma_prefetch_desc(&tmA_lo);
       tma_prefetch_desc(&tmB_lo);
     }
@@ -108,11 +108,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
         for (int it = 0; it < total_kb; ++it) {
           const int pass = (PASSES == 1) ? 0 : it / p.num_kb;
           const int kb = it - pass * p.num_kb;
+          // PASSES == 2 (fp16f8): pass 1 reads the e4m3 pair planes of both operands (128-byte k-blocks), see gemm_2sm.cu
+          const bool f8pass = (PASSES == 2) && pass == 1;
           const CUtensorMap* ma = (pass == 1) ? &tmA_lo : &tmA_hi;
-          const CUtensorMap* mb = (pass == 2) ? &tmB_lo : &tmB_hi;
-          int kc = kb * GEMM_BLOCK_K, trow = t0;
+          const CUtensorMap* mb = (pass == 2 || f8pass) ? &tmB_lo : &tmB_hi;
+          const int kw = f8pass ? 2 * GEMM_BLOCK_K : GEMM_BLOCK_K;
+          int kc = kb * kw, trow = t0;
           if (kb >= p.kb_split) {
-            kc = (kb - p.kb_split) * GEMM_BLOCK_K;
+            kc = (kb - p.kb_split) * kw;
             trow = t0 + 1;
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -130,9 +133,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
           } else {
           tma_load_3d(sa, ma, &full_bar[stage], kc, trow, b);
           if (CLUSTER == 1)
-            tma_load_2d(sb, mb, &full_bar[stage], kb * GEMM_BLOCK_K, n0);
+            tma_load_2d(sb, mb, &full_bar[stage], kb * kw, n0);
           else  // my slice of the weight tile, delivered to every CTA of the cluster
-            tma_load_2d_mcast(sb + crank * (B_SLICE_ROWS * 128), mb, &full_bar[stage], kb * GEMM_BLOCK_K,
+            tma_load_2d_mcast(sb + crank * (B_SLICE_ROWS * 128), mb, &full_bar[stage], kb * kw,
                               n0 + crank * B_SLICE_ROWS, kMask);
           }
           if (++stage == S::STAGES) {
@@ -145,10 +148,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc_k = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 0, 0);
-      constexpr uint32_t idesc_mn = idesc_bf16(GEMM_BLOCK_M, BLOCK_N, 1, 1);
       const bool mn = (CLUSTER == 1) && p.mn_major;
-      const uint32_t idesc = mn ? idesc_mn : idesc_k;
+      const uint32_t idesc = idesc_16bit(p.fp16 != 0, GEMM_BLOCK_M, BLOCK_N, mn ? 1 : 0, mn ? 1 : 0);
+      constexpr uint32_t idesc8 = idesc_fmt0(GEMM_BLOCK_M, BLOCK_N, 0, 0);     // e4m3 x e4m3 under kind::f8f6f4
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -170,6 +172,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
             for (int k = 0; k < GEMM_BLOCK_K / 16; ++k)
               umma_f16(d_tmem, desc_mnmajor_sw128(sa + k * 2048, 8192, 1024), desc_mnmajor_sw128(sa + S::A_BYTES + k * 2048, 8192, 1024),
                        idesc, (it | k) != 0);
+          } else if (PASSES == 2 && it >= p.num_kb) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f8(d_tmem, da + 2 * k, db + 2 * k, idesc8, 1);   // K = 32 e4m3 = 32 bytes per step
           } else {
 #pragma unroll
           for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
@@ -293,7 +298,10 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.batch = a->batch;
   p.n_tiles = (a->N + block_n - 1) / block_n;
   p.N = a->N;
-  p.gelu = (a->flags & W2V2_GEMM_GELU_TANH) ? 3 : (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form fit (single-pass mode)
+  p.gelu = (a->flags & W2V2_GEMM_GELU_TANH) ? 3 : (a->flags & W2V2_GEMM_GELU) ? (a->passes == 1 ? 2 : 1) : 0;   // 2 = tanh-form fit (bf16 single-pass mode only)
+  p.fp16 = mode_fp16(a->passes) ? 1 : 0;
+  p.acc_scale = mode_fp16(a->passes) ? ACC_UNSCALE : 1.0f;
+  p.out_format = a->out_format;
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.mn_major = (a->flags & W2V2_GEMM_MN_MAJOR) ? 1 : 0;
@@ -351,6 +359,14 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
     rc = make_tmap(&tmB_lo, a->w_lo, 2, b_dims, b_strides, b_box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
   }
+  if (PASSES == 2) {   // e4m3 pair planes: same byte strides as the 16-bit planes, 128-byte k-blocks
+    const uint64_t a8_dims[3] = {(uint64_t)a->a_row_len * 2, (uint64_t)a->a_rows, (uint64_t)a->batch};
+    const uint32_t a8_box[3] = {2 * GEMM_BLOCK_K, GEMM_BLOCK_M, 1};
+    if ((rc = make_tmap(&tmA_lo, a->a_lo, 3, a8_dims, a_strides, a8_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_UINT8))) return rc;
+    const uint64_t b8_dims[2] = {(uint64_t)a->K * 2, (uint64_t)a->w_rows};
+    const uint32_t b8_box[2] = {2 * GEMM_BLOCK_K, (uint32_t)(BLOCK_N / CLUSTER)};
+    if ((rc = make_tmap(&tmB_lo, a->w_lo, 2, b8_dims, b_strides, b8_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_UINT8))) return rc;
+  }
   }
   GemmParams p = make_gemm_params(a, BLOCK_N);
   auto kern = gemm_bf16_tcgen05_kernel<BLOCK_N, PASSES, CLUSTER>;
@@ -376,8 +392,13 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(a != nullptr, "args is null");
   W2V2_CHECK_ARG(a->a_hi && a->w_hi, "A / W pointers must be non-null");
-  W2V2_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3");
-  W2V2_CHECK_ARG(a->passes == 1 || (a->a_lo && a->w_lo), "3-pass mode needs the lo planes");
+  const int np = mode_passes(a->passes);
+  W2V2_CHECK_ARG((np == 1 || np == 3) && (a->passes & ~(3 | MODE_FP16 | MODE_F8)) == 0 && (!mode_f8(a->passes) || (np == 1 && mode_fp16(a->passes))),
+                 "passes must be 1 (bf16), 3 (bf16x3), 17 (fp16), 19 (fp16x3) or 25 (fp16 + e4m3 cross terms)");
+  W2V2_CHECK_ARG((np == 1 && !mode_f8(a->passes)) || (a->a_lo && a->w_lo), "multi-plane modes need the second planes");
+  W2V2_CHECK_ARG(a->out_format >= 0 && a->out_format <= 2, "out_format must be 0 (bf16), 1 (fp16) or 2 (fp16 + e4m3 pairs)");
+  W2V2_CHECK_ARG(a->out_format != 2 || (a->out_hi && a->out_lo && a->N % 64 == 0), "out_format 2 writes both planes and needs N % 64 == 0");
+  W2V2_CHECK_ARG(!mode_fp16(a->passes) || a->scale == nullptr, "per-column scale is not combined with the scaled fp16 planes");
   W2V2_CHECK_ARG(a->K > 0 && a->K % GEMM_BLOCK_K == 0, "K must be a positive multiple of 64");
   W2V2_CHECK_ARG(a->N > 0 && a->rows_per_batch > 0 && a->batch > 0, "N, rows_per_batch, batch must be positive");
   W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements (16 B)");
@@ -393,7 +414,7 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   int bn = a->block_n;
   if (a->flags & W2V2_GEMM_MN_MAJOR) {
     // D[m][n] = sum_r X[r][m] Y[r][n]  (weight gradients: X = layer input, Y = output gradient, both row-major as stored)
-    W2V2_CHECK_ARG(a->passes == 1 && a->kb_split == 0, "MN-major mode: single pass");
+    W2V2_CHECK_ARG(a->passes == 1 && a->kb_split == 0 && a->out_format == 0, "MN-major mode: single bf16 pass");
     W2V2_CHECK_ARG(a->batch == 1 || (a->out_f32 && !a->out_hi && !a->bias && !a->residual),
                    "MN-major split-K (batch > 1): only out_f32 (accumulated atomically into a zeroed buffer), no bias / residual");
     W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->w_row_stride % 8 == 0 && a->w_row_stride >= a->N && a->a_row_stride >= a->rows_per_batch,
@@ -410,7 +431,15 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   const long m_tiles = (long)a->batch * ((a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
   const bool pair = (bn >= 128) && m_tiles >= 2 && a->cluster != 1;
   const bool can_2sm = (a->N % 8 == 0);
-  if (a->passes == 1) {
+  W2V2_CHECK_ARG(a->out_format != 2 || bn >= 64, "out_format 2 needs block_n >= 64");
+  if (mode_f8(a->passes)) {
+    switch (bn) {
+      case 256: return pair ? (a->cluster == 3 || !can_2sm ? launch_gemm<256, 2, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 2, 1>(a, s);
+      case 128: return pair ? launch_gemm<128, 2, 2>(a, s) : launch_gemm<128, 2, 1>(a, s);
+      case 64: return launch_gemm<64, 2, 1>(a, s);
+      case 32: return launch_gemm<32, 2, 1>(a, s);
+    }
+  } else if (np == 1) {
     switch (bn) {
       case 256: return pair ? (a->cluster == 3 || !can_2sm ? launch_gemm<256, 1, 2>(a, s) : launch_gemm_2sm(a, s)) : launch_gemm<256, 1, 1>(a, s);
       case 128: return pair ? launch_gemm<128, 1, 2>(a, s) : launch_gemm<128, 1, 1>(a, s);

@@ -28,6 +28,8 @@ struct PosconvParams {
   int shift;              // window starts at frame tf0 - ktaps/2 + shift (0 = forward; +1 = transposed conv of the backward)
   int linear;             // 1: out = resid + acc (no bias, no GELU): the dgrad of the conv
   int gelu_approx;        // 1: tf.nn.gelu(approximate=True) (config.py:14, encoder.py:181)
+  int fp16;               // 1: x / w planes are fp16 (x * 2^4, w * 2^11): accumulators are un-scaled by acc_scale
+  float acc_scale;
   float* pre_out;         // optional fp32 [B, T, d]: bias + conv (pre-activation kept for the backward)
   const float* bias;      // [d]
   const float* resid;     // fp32 [B, T, d]
@@ -120,7 +122,7 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = idesc_bf16(128, p.cpg, 0, 0);
+      const uint32_t idesc = idesc_16bit(p.fp16 != 0, 128, p.cpg, 0, 0);
       const uint32_t b_lbo = (uint32_t)p.cpg * 16;
       const int ksteps = p.cpg / 16;
       mbar_wait(a_full, 0);
@@ -173,15 +175,15 @@ posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant_
           float v[16];
           if (p.linear) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.acc_scale;
           } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n) + i);
-              v[4 * i + 0] = __uint_as_float(r[4 * i + 0]) + bb.x;
-              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
-              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z;
-              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+              v[4 * i + 0] = fmaf(__uint_as_float(r[4 * i + 0]), p.acc_scale, bb.x);   // fmaf(a, 1, b) == a + b
+              v[4 * i + 1] = fmaf(__uint_as_float(r[4 * i + 1]), p.acc_scale, bb.y);
+              v[4 * i + 2] = fmaf(__uint_as_float(r[4 * i + 2]), p.acc_scale, bb.z);
+              v[4 * i + 3] = fmaf(__uint_as_float(r[4 * i + 3]), p.acc_scale, bb.w);
             }
             if (p.pre_out != nullptr) {
 #pragma unroll
@@ -239,6 +241,8 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
   p.shift = a->shift;
   p.linear = a->linear;
   p.gelu_approx = a->gelu_approx;
+  p.fp16 = mode_fp16(a->passes) ? 1 : 0;
+  p.acc_scale = mode_fp16(a->passes) ? ACC_UNSCALE : 1.0f;
   p.pre_out = a->pre_out;
   p.bias = a->bias;
   p.resid = a->resid;
@@ -265,8 +269,8 @@ extern "C" int w2v2_posconv(const w2v2_posconv_args* a, void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(a != nullptr, "args is null");
   W2V2_CHECK_ARG(a->x_hi && a->w_hi && (a->bias || a->linear) && a->resid && a->out_f32, "null pointer");
-  W2V2_CHECK_ARG(a->passes == 1 || a->passes == 3, "passes must be 1 or 3");
-  W2V2_CHECK_ARG(a->passes == 1 || (a->x_lo && a->w_lo), "3-pass mode needs the lo planes");
+  W2V2_CHECK_ARG(a->passes == 1 || a->passes == 3 || a->passes == 17 || a->passes == 19, "passes must be 1, 3 (bf16) or 17, 19 (fp16)");
+  W2V2_CHECK_ARG(mode_passes(a->passes) == 1 || (a->x_lo && a->w_lo), "3-pass modes need the lo planes");
   W2V2_CHECK_ARG(a->groups > 0 && a->hidden % a->groups == 0, "hidden must be divisible by groups");
   const int cpg = a->hidden / a->groups;
   W2V2_CHECK_ARG(cpg % 16 == 0 && cpg >= 16 && cpg <= 64, "channels per group must be 16, 32, 48 or 64");
@@ -274,6 +278,6 @@ extern "C" int w2v2_posconv(const w2v2_posconv_args* a, void* stream) {
                  "ktaps must be even, a multiple of 4 and at most 128");
   W2V2_CHECK_ARG(a->batch > 0 && a->frames > 0, "batch and frames must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (a->passes == 1) return launch_posconv<1>(a, s);
+  if (mode_passes(a->passes) == 1) return launch_posconv<1>(a, s);
   return launch_posconv<3>(a, s);
 }

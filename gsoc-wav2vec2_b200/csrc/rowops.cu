@@ -255,7 +255,7 @@ template <int MAXV, bool EXACT = false>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                int rows, int d, int gelu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-               __nv_bfloat16* __restrict__ out_lo, float* __restrict__ stats) {
+               __nv_bfloat16* __restrict__ out_lo, float* __restrict__ stats, int out_format) {
   pdl_trigger();
   pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -307,11 +307,25 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       }
       const size_t o = (size_t)row * d + 4 * (size_t)idx;
       if (out_f32 != nullptr) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(y0, y1, y2, y3);
-      if (out_hi != nullptr) {
+      if (out_hi != nullptr && out_format == 0) {
         uint32_t l0, l1;
         const uint32_t h0 = split_bf16x2(y0, y1, l0), h1 = split_bf16x2(y2, y3, l1);
         *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
         if (out_lo != nullptr) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l0, l1);
+      } else if (out_hi != nullptr && out_format == 1) {     // fp16 planes of y * 2^4
+        uint32_t l0, l1;
+        const uint32_t h0 = split_f16x2(y0 * ACT_SCALE, y1 * ACT_SCALE, l0), h1 = split_f16x2(y2 * ACT_SCALE, y3 * ACT_SCALE, l1);
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
+        if (out_lo != nullptr) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(l0, l1);
+      } else if (out_hi != nullptr) {                        // fp16 hi + e4m3 pair plane [rows][2 d] (d % 64 == 0)
+        uint16_t la, lb, ha, hb;
+        const uint32_t h0 = split_f16_f8x2(y0 * ACT_SCALE, y1 * ACT_SCALE, la, ha);
+        const uint32_t h1 = split_f16_f8x2(y2 * ACT_SCALE, y3 * ACT_SCALE, lb, hb);
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(h0, h1);
+        const int c = 4 * idx;
+        uint8_t* p8 = reinterpret_cast<uint8_t*>(out_lo) + (size_t)row * d * 2 + (size_t)(c >> 6) * 128 + (c & 63);
+        *reinterpret_cast<uint32_t*>(p8) = la | ((uint32_t)lb << 16);
+        *reinterpret_cast<uint32_t*>(p8 + 64) = ha | ((uint32_t)hb << 16);
       }
     }
   }
@@ -450,7 +464,15 @@ extern "C" int w2v2_ln_rows(const float* x, const float* gamma, const float* bet
 
 extern "C" int w2v2_ln_rows_stats(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
                                   int gelu, float* out_f32, void* out_hi, void* out_lo, float* stats, void* stream) {
+  return w2v2_ln_rows_ex(x, gamma, beta, eps, rows, d, gelu, out_f32, out_hi, out_lo, stats, 0, stream);
+}
+
+extern "C" int w2v2_ln_rows_ex(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d,
+                               int gelu, float* out_f32, void* out_hi, void* out_lo, float* stats, int out_format,
+                               void* stream) {
   W2V2_CHECK_ARG(x && gamma && beta, "null pointer");
+  W2V2_CHECK_ARG(out_format >= 0 && out_format <= 2, "out_format must be 0 (bf16), 1 (fp16) or 2 (fp16 + e4m3 pairs)");
+  W2V2_CHECK_ARG(out_format != 2 || (out_hi && out_lo && d % 64 == 0), "out_format 2 writes both planes and needs d % 64 == 0");
   W2V2_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 2048, "d must be a multiple of 4, at most 2048");
   W2V2_CHECK_ARG(out_f32 || out_hi || stats, "at least one output");
   W2V2_CHECK_ARG(out_lo == nullptr || out_hi != nullptr, "out_lo requires out_hi");
@@ -460,15 +482,15 @@ extern "C" int w2v2_ln_rows_stats(const float* x, const float* gamma, const floa
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
   if (d == 512)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<4, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<4, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   else if (d == 768)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<6, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<6, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   else if (d == 1024)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<8, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<8, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   else if (d <= 1024)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   else
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats));
+    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   return 0;
 }
 

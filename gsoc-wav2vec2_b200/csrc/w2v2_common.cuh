@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -170,6 +171,15 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t desc_a, u
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void umma_f8_2sm(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -198,6 +208,16 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// e4m3 x e4m3 -> fp32 (K = 32 per instruction), one CTA
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -288,6 +308,27 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, 
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// Same with the operand format fields cleared: fp16 x fp16 -> fp32 under kind::f16, and e4m3 x e4m3 -> fp32 under
+// kind::f8f6f4 (format code 0 is F16 in the first table and E4M3 in the second).
+__host__ __device__ constexpr uint32_t idesc_fmt0(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t idesc_16bit(bool fp16, int M, int N, int a_mn_major, int b_mn_major) {
+  return fp16 ? idesc_fmt0(M, N, a_mn_major, b_mn_major) : idesc_bf16(M, N, a_mn_major, b_mn_major);
+}
+
+// ---- precision modes (the `passes` argument of the C ABI, see include/w2v2.h) ----
+//   1 = bf16, 3 = bf16x3 (hi*hi + lo*hi + hi*lo), | 16 = fp16 operands (activations stored x 2^4, weights x 2^11),
+//   | 8 = fp16 main product + the two cross terms as e4m3 MMAs ("fp16f8", planes: fp16 + interleaved e4m3 pairs)
+constexpr int MODE_FP16 = 16, MODE_F8 = 8;
+__host__ __device__ constexpr int mode_passes(int mode) { return mode & 3; }
+__host__ __device__ constexpr bool mode_fp16(int mode) { return (mode & MODE_FP16) != 0; }
+__host__ __device__ constexpr bool mode_f8(int mode) { return (mode & MODE_F8) != 0; }
+constexpr float ACT_SCALE = 16.0f;          // fp16 activation planes hold x * 2^4 ...
+constexpr float WGT_SCALE = 2048.0f;        // ... fp16 weight planes w * 2^11: accumulators are at 2^15
+constexpr float ACC_UNSCALE = 1.0f / 32768.0f;
+constexpr float F8_UP = 64.0f, F8_DOWN = 1.0f / 64.0f;   // e4m3 cross-term operands: lo * 2^6, hi * 2^-6
 
 // --------------------------------------------------------------------------- math
 // erf-GELU without erff():  gelu(x) = max(x,0) - 0.5*|x|*erfc(|x|/sqrt2),
@@ -456,6 +497,40 @@ __device__ __forceinline__ float bf16_hi_to_f32(uint32_t packed) { return __uint
 __device__ __forceinline__ uint32_t split_bf16x2(float v0, float v1, uint32_t& lo_pair) {
   const uint32_t hi = pack_bf16x2(v0, v1);
   lo_pair = pack_bf16x2(v0 - bf16_lo_to_f32(hi), v1 - bf16_hi_to_f32(hi));
+  return hi;
+}
+
+// ---- fp16 / e4m3 operand planes (fp16 and fp16f8 modes) ----
+// h = fp16(sat(x)) pair; x is ALREADY multiplied by the plane scale (ACT_SCALE for activations)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));   // first source -> upper half
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t packed) {
+  return __half2float(__ushort_as_half((unsigned short)(packed & 0xFFFFu)));
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t packed) {
+  return __half2float(__ushort_as_half((unsigned short)(packed >> 16)));
+}
+// Returns the packed fp16 hi pair of (v0, v1); lo_pair = packed fp16 residuals (fp16x3 mode)
+__device__ __forceinline__ uint32_t split_f16x2(float v0, float v1, uint32_t& lo_pair) {
+  const uint32_t hi = pack_f16x2(v0, v1);
+  lo_pair = pack_f16x2(v0 - f16_lo_to_f32(hi), v1 - f16_hi_to_f32(hi));
+  return hi;
+}
+// two e4m3 bytes (v0 -> low byte)
+__device__ __forceinline__ uint16_t pack_e4m3x2(float v0, float v1) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(v1), "f"(v0));   // first source -> upper byte
+  return r;
+}
+// fp16f8 planes of a value pair: returns the packed fp16 hi pair; l8 = e4m3((v - hi) * 2^6) pair, h8 = e4m3(hi * 2^-6) pair
+__device__ __forceinline__ uint32_t split_f16_f8x2(float v0, float v1, uint16_t& l8, uint16_t& h8) {
+  const uint32_t hi = pack_f16x2(v0, v1);
+  const float h0 = f16_lo_to_f32(hi), h1 = f16_hi_to_f32(hi);
+  l8 = pack_e4m3x2((v0 - h0) * F8_UP, (v1 - h1) * F8_UP);
+  h8 = pack_e4m3x2(h0 * F8_DOWN, h1 * F8_DOWN);
   return hi;
 }
 

@@ -16,6 +16,8 @@ CSRC_DIR = os.path.join(_ROOT, "csrc")
 GEMM_GELU = 1
 GEMM_MN_MAJOR = 2
 GEMM_GELU_TANH = 4
+MODE_BF16, MODE_BF16X3, MODE_FP16, MODE_FP16X3, MODE_FP16F8 = 1, 3, 17, 19, 25      # W2V2_MODE_*
+OUT_BF16, OUT_FP16, OUT_FP16F8 = 0, 1, 2                                              # W2V2_OUT_*
 
 
 class GemmArgs(C.Structure):
@@ -34,6 +36,7 @@ class GemmArgs(C.Structure):
         ("w_row_stride", C.c_int64),
         ("row_replace_mask", C.c_void_p), ("row_replace_value", C.c_void_p),
         ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("drop_seed", C.c_uint64),
+        ("out_format", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -71,9 +74,11 @@ SIGNATURES = {
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows_stats": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _P],
+    "w2v2_ln_rows_ex": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _I, _P],
     "w2v2_normalize_utterances": [_P, _P, _I, _I, _F, _P, _P],
     "w2v2_split_bf16": [_P, _L, _P, _P, _P],
     "w2v2_attn_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],
+    "w2v2_attn_fwd_ex": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _I, _P],
     "w2v2_posconv": [C.POINTER(PosconvArgs), _P],
     "w2v2_ctc_loss": [_P, _P, _I, _I, _I, _I, _I, _F, _P, _P, _P, _P, _P],
     "w2v2_ctc_workspace_bytes": [_I, _I, _I],

@@ -28,7 +28,29 @@ from .weights import hf_to_reference, reference_to_hf
 
 logger = logging.getLogger(__name__)
 
-_PRECISIONS = {"bf16": 1, "bf16x3": 3}
+# precision -> W2V2_MODE_* of the GEMMs / convs (include/w2v2.h).  "fp16f8": fp16 main product + both cross terms as e4m3 MMAs.
+_PRECISIONS = {"bf16": 1, "bf16x3": 3, "fp16": 17, "fp16f8": 25}
+
+# operand-plane kinds: name -> (dtype of hi, kind of lo, W2V2_OUT_* the producer is asked for)
+_KINDS = {"bf16": (torch.bfloat16, None, 0), "bf16x2": (torch.bfloat16, "same", 0),
+          "fp16": (torch.float16, None, 1), "fp16x2": (torch.float16, "same", 1), "fp16f8": (torch.float16, "pairs", 2)}
+
+
+class _Modes:
+    """What each kernel class runs in for a model precision.  ``gemm``: Dense layers and convs; ``attn`` / ``pos``: the attention
+    and positional-conv kernels have no e4m3 path - under "fp16f8" attention is a single fp16 pass and so is the positional
+    conv (tests/precision_study.py: the logits stay within ~2e-4, the same as with split-fp16 in those two kernels); ``act`` / ``qkv`` / ``pos_in``: plane kinds of the
+    activations feeding the GEMMs, the attention kernel and the positional conv."""
+
+    def __init__(self, precision):
+        g = _PRECISIONS[precision]
+        self.gemm = g
+        self.attn = {1: 1, 3: 3, 17: 17, 25: 17}[g]
+        self.pos = {1: 1, 3: 3, 17: 17, 25: 17}[g]
+        self.act = {1: "bf16", 3: "bf16x2", 17: "fp16", 25: "fp16f8"}[g]
+        self.qkv = {1: "bf16", 3: "bf16x2", 17: "fp16", 25: "fp16"}[g]
+        self.pos_in = {1: "bf16", 3: "bf16x2", 17: "fp16", 25: "fp16"}[g]
+        self.lo = g == 3                      # legacy flag of the bf16 modes: a second bf16 plane exists
 
 
 def _default_precision():
@@ -117,12 +139,39 @@ class _Arena:
     def pair(self, key, shape, lo):
         return Pair(self.get(key + ".hi", shape, torch.bfloat16), self.get(key + ".lo", shape, torch.bfloat16) if lo else None)
 
+    def planes(self, key, shape, kind):
+        """Operand planes of one activation [..., C] in the layout ``kind`` (see ``_KINDS``)."""
+        hi_dt, lo_kind, _ = _KINDS[kind]
+        hi = self.get(key + ".hi", shape, hi_dt)
+        if lo_kind is None:
+            return Pair(hi, None)
+        if lo_kind == "same":
+            return Pair(hi, self.get(key + ".lo", shape, hi_dt))
+        return Pair(hi, self.get(key + ".c8", tuple(shape[:-1]) + (2 * shape[-1],), torch.uint8))
 
-def _split(t: torch.Tensor, lo: bool) -> Pair:
-    """Weight packing helper (load time, not on the hot path): fp32 -> bf16 hi (+ lo)."""
+
+def _split(t: torch.Tensor, lo) -> Pair:
+    """Weight packing helper (load time, not on the hot path).  ``lo`` False / True: fp32 -> bf16 hi (+ lo), the bf16 modes;
+    or a W2V2_MODE_* int: 17 -> fp16(w * 2^11); 19 -> that + the fp16 residual; 25 -> that + the e4m3 pair plane [rows][2 K]
+    holding per 64-wide k-block 64 x e4m3(hi * 2^-6) then 64 x e4m3((w 2^11 - hi) * 2^6) (K % 64 == 0)."""
     t = t.contiguous().float()
-    hi = t.to(torch.bfloat16)
-    return Pair(hi, (t - hi.float()).to(torch.bfloat16) if lo else None)
+    mode = (3 if lo else 1) if isinstance(lo, bool) else int(lo)
+    if mode in (1, 3):
+        hi = t.to(torch.bfloat16)
+        return Pair(hi, (t - hi.float()).to(torch.bfloat16) if mode == 3 else None)
+    lo = mode
+    w = torch.clamp(t * 2048.0, -65504.0, 65504.0)
+    hi = w.to(torch.float16)
+    if lo == 17:
+        return Pair(hi, None)
+    res = w - hi.float()
+    if lo == 19:
+        return Pair(hi, res.to(torch.float16))
+    assert lo == 25 and t.shape[-1] % 64 == 0, "fp16f8 weight planes need K % 64 == 0"
+    rows, K = t.reshape(-1, t.shape[-1]).shape
+    h8 = torch.clamp(hi.float() / 64.0, -448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8).reshape(rows, K // 64, 1, 64)
+    l8 = torch.clamp(res * 64.0, -448.0, 448.0).to(torch.float8_e4m3fn).view(torch.uint8).reshape(rows, K // 64, 1, 64)
+    return Pair(hi, torch.cat([h8, l8], dim=2).reshape(tuple(t.shape[:-1]) + (2 * K,)).contiguous())
 
 
 def pack_posconv_kernel(kern: torch.Tensor, groups: int) -> torch.Tensor:
@@ -144,6 +193,7 @@ class _B200Model:
         self.precision = precision or _default_precision()
         if self.precision not in _PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self._modes = _Modes(self.precision)
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
         self.device = torch.device(device)
@@ -275,7 +325,8 @@ class _B200Model:
 
     # ---------------------------------------------------------------- packing (kernel layouts)
     def _pack(self):
-        cfg, v, lo = self.config, self.variables, _PRECISIONS[self.precision] == 3
+        cfg, v = self.config, self.variables
+        lo = self._modes.gemm          # plane layout of every Dense / conv weight (see _split)
         dev = self.device
         P = {}
         # conv 0: TF [10,1,C] -> [10][C] fp32
@@ -292,7 +343,7 @@ class _B200Model:
         kern = wv * torch.rsqrt(torch.clamp(ss, min=1e-12)) * wg                     # [k, cpg, d]
         k, cpg, d = kern.shape
         G = d // cpg
-        P["pos.w"] = _split(pack_posconv_kernel(kern, G), lo)
+        P["pos.w"] = _split(pack_posconv_kernel(kern, G), self._modes.pos)
         dh = cfg.head_size
         scale = dh ** (-0.5)                                                         # encoder.py:28, folded
         for i in range(cfg.num_layers):
@@ -332,8 +383,8 @@ class _B200Model:
         if self._arena is None:
             self._arena = _Arena(self.device)
         A = self._arena
-        passes = _PRECISIONS[self.precision]
-        lo = passes == 3
+        md = self._modes
+        passes, kind, ofmt = md.gemm, md.act, _KINDS[md.act][2]
         x = batch.to(self.device, torch.float32).contiguous()
         if x.dim() != 2:
             raise ValueError("batch must have shape (batch_size, seqlen)")
@@ -350,7 +401,7 @@ class _B200Model:
 
         # ---- extractor layer 0 (feature_extractor.py:54-59)
         T0 = frames[0]
-        act = A.pair("c0", (B, T0, C0), lo)
+        act = A.planes("c0", (B, T0, C0), kind)
         if not layer_norm_convs:
             # GroupNorm statistics from the waveform alone, folded to a per-(b, c) scale / shift; conv + scale/shift + GELU
             # in one kernel (window products on the tensor cores from an smem copy of the waveform, no im2col tensor)
@@ -367,7 +418,7 @@ class _B200Model:
             raw = raw_flat[: B * T0 * C0].view(B * T0, C0)
             ops.conv0(x, P["conv0.w"], 0, v.get(fe + "0/conv/bias") if cfg.conv_bias else None, 0, False, out_f32=raw, channels=C0)
             ops.ln_rows(raw, v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], 1e-5, B * T0, C0, gelu=ln_gelu,
-                        out_hi=act.hi, out_lo=act.lo)
+                        out_hi=act.hi, out_lo=act.lo, out_format=ofmt)
         # ---- extractor layers 1.. as implicit GEMMs
         last_f32 = None
         for i in range(1, nconv):
@@ -385,15 +436,16 @@ class _B200Model:
                     last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
                     ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=ln_gelu, out_f32=last_f32)
                 else:
-                    nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
-                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=ln_gelu, out_hi=nxt.hi, out_lo=nxt.lo)
+                    nxt = A.planes(f"c{i}", (B, Tout, cout), kind)
+                    ops.ln_rows(raw, g_, b_, 1e-5, B * Tout, cout, gelu=ln_gelu, out_hi=nxt.hi, out_lo=nxt.lo, out_format=ofmt)
                     act = nxt
             elif last:
                 last_f32 = A.get("c_last.f32", (B * Tout, cout), f32)
                 ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, gelu_approx=approx, out_f32=last_f32, **geo)
             else:
-                nxt = A.pair(f"c{i}", (B, Tout, cout), lo)
-                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, gelu_approx=approx, out_hi=nxt.hi, out_lo=nxt.lo, **geo)
+                nxt = A.planes(f"c{i}", (B, Tout, cout), kind)
+                ops.gemm(act, P[f"conv{i}.w"], bias=bias, gelu=True, gelu_approx=approx, out_hi=nxt.hi, out_lo=nxt.lo,
+                         out_format=ofmt, **geo)
                 act = nxt
         return last_f32, B, frames[-1]
 
@@ -404,8 +456,8 @@ class _B200Model:
                                       "attention mask (see _training_forward); use dropout=0 and survival_prob=1 here")
         last_f32, B, T = self._features(batch)
         P, A = self._packed, self._arena
-        passes = _PRECISIONS[self.precision]
-        lo = passes == 3
+        md = self._modes
+        passes, kind, ofmt = md.gemm, md.act, _KINDS[md.act][2]
         f32, eps = torch.float32, cfg.layer_norm_eps
         Cl, d = cfg.filter_sizes[-1], cfg.hidden_size
         M = B * T
@@ -415,10 +467,11 @@ class _B200Model:
         if attention_mask is not None:
             kv_len = self._frame_lengths(attention_mask, T)
         fp = "wav2vec2/feature_projection/"
-        pn = A.pair("proj.in", (M, Cl), lo)
-        ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo)
+        pn = A.planes("proj.in", (M, Cl), kind)
+        ops.ln_rows(last_f32, v[fp + "layer_norm/gamma"], v[fp + "layer_norm/beta"], eps, M, Cl, out_hi=pn.hi, out_lo=pn.lo,
+                    out_format=ofmt)
         h_f32 = A.get("h.f32", (M, d), f32)
-        h = A.pair("h", (M, d), lo)
+        h = A.planes("h", (M, d), md.pos_in)          # consumed by the positional conv only
         row_replace = None
         if training and cfg.apply_spec_augment:
             # modeling.py:193-199 (training only): span starts from the host numpy RNG like the reference; the replacement of the
@@ -428,17 +481,18 @@ class _B200Model:
             row_replace = (torch.from_numpy(mask.astype("uint8")).to(self.device).reshape(M).contiguous(),
                            v["wav2vec2/masked_spec_embed"])
         ops.gemm(pn, P["proj.w"], K=Cl, N=d, rows_per_batch=T, batch=B, bias=v[fp + "projection/bias"],
-                 row_valid=kv_len, row_replace=row_replace, out_f32=h_f32, out_hi=h.hi, out_lo=h.lo, passes=passes)
+                 row_valid=kv_len, row_replace=row_replace, out_f32=h_f32, out_hi=h.hi, out_lo=h.lo, passes=passes,
+                 out_format=_KINDS[md.pos_in][2])
 
         # ---- encoder (encoder.py:251-276)
         enc = "wav2vec2/encoder/"
         pre = cfg.attention_norm_type == "prenorm"
         y = A.get("y.f32", (M, d), f32)
         ops.posconv(h, P["pos.w"], v[enc + "pos_conv_embed/conv/bias"], h_f32, y, B, T, d,
-                    cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, passes,
+                    cfg.num_conv_pos_embedding_groups, cfg.num_conv_pos_embeddings, md.pos,
                     gelu_approx=bool(cfg.is_gelu_approx))
         xs_f32 = A.get("x.f32", (M, d), f32)      # residual stream
-        xs = A.pair("x", (M, d), lo)              # GEMM operand view of the (normalised) stream
+        xs = A.planes("x", (M, d), kind)          # GEMM operand view of the (normalised) stream
         st = res_ln = None
         if pre:
             xs_f32, y = y, xs_f32                 # stream = h + posconv(h); LN happens inside the layers
@@ -448,11 +502,11 @@ class _B200Model:
             # pre-norm sum `y` in its epilogue (bit-identical arithmetic) and overwrites `y` in place with the new sum.
             st = A.get("ln.stats", (M, 2), f32)
             g0, b0 = v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"]
-            ops.ln_rows(y, g0, b0, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st)
+            ops.ln_rows(y, g0, b0, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st, out_format=ofmt)
             res_ln = (st, g0, b0)
-        qkv = A.pair("qkv", (M, 3 * d), lo)
-        ctx = A.pair("ctx", (M, d), lo)
-        mid = A.pair("mid", (M, cfg.intermediate_size), lo)
+        qkv = A.planes("qkv", (M, 3 * d), md.qkv)
+        ctx = A.planes("ctx", (M, d), kind)
+        mid = A.planes("mid", (M, cfg.intermediate_size), kind)
         x1_f32 = A.get("x1.f32", (M, d), f32) if pre else None
         H, dh, ffn = cfg.num_heads, cfg.head_size, cfg.intermediate_size
         if not pre and cfg.num_layers == 0:
@@ -462,24 +516,24 @@ class _B200Model:
             g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
             g2, b2 = v[lb + "final_layer_norm/gamma"], v[lb + "final_layer_norm/beta"]
             if pre:
-                ops.ln_rows(xs_f32, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo)
+                ops.ln_rows(xs_f32, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
             ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi,
-                     out_lo=qkv.lo, passes=passes)
-            ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, passes)
+                     out_lo=qkv.lo, passes=passes, out_format=_KINDS[md.qkv][2])
+            ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, md.attn, out_format=ofmt)
             if pre:
                 # x1 = x + out_proj(ctx)
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
                          residual=xs_f32, out_f32=x1_f32, passes=passes)
-                ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo)
+                ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
             else:
                 # y <- LN(y) + out_proj(ctx);  x1 = LN1(y) as bf16 operand + row statistics
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
                          residual=y, res_ln=res_ln, out_f32=y, passes=passes)
-                ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st)
+                ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st, out_format=ofmt)
                 res_ln = (st, g1, b1)
             ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M,
                      bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, gelu_approx=bool(cfg.is_gelu_approx),
-                     out_hi=mid.hi, out_lo=mid.lo, passes=passes)
+                     out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt)
             if pre:
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
                          bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=xs_f32, passes=passes)
@@ -489,12 +543,12 @@ class _B200Model:
                          bias=v[lb + "feed_forward/output_dense/bias"], residual=y, res_ln=res_ln, out_f32=y, passes=passes)
                 last = i == cfg.num_layers - 1
                 ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32 if last else None, out_hi=xs.hi, out_lo=xs.lo,
-                            stats=None if last else st)
+                            stats=None if last else st, out_format=ofmt)
                 res_ln = (st, g2, b2)
         if pre:
             out_f32 = A.get("enc.out", (M, d), f32)
             ops.ln_rows(xs_f32, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=out_f32,
-                        out_hi=xs.hi, out_lo=xs.lo)
+                        out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
             xs_f32 = out_f32
         return xs_f32, xs, (B, T, d)
 
@@ -544,7 +598,7 @@ class _B200Model:
         """``training=True`` with dropout: the training forward of ``training.Stage2Trainer`` (dropout at the reference's
         six sites from a per-call mask stream, SpecAugment).  Returns (logits or None, hidden fp32 [B*T', d], (B, T', d))."""
         from .training import Stage2Trainer
-        if not Stage2Trainer.supports(self.config):
+        if not Stage2Trainer.supports(self.config) or self.precision not in ("bf16", "bf16x3"):
             raise NotImplementedError("training-mode forward with dropout covers the base architecture (group-norm extractor, "
                                       "post-norm encoder) without an attention mask; use dropout=0 otherwise")
         if getattr(self, "_train_fwd", None) is None:
@@ -620,7 +674,7 @@ class Wav2Vec2ForCTC(_B200Model):
         V = self.config.vocab_size
         logits = torch.empty((B, T, V), dtype=torch.float32, device=self.device)
         ops.gemm(xs, self._packed["lm.w"], K=d, N=V, rows_per_batch=B * T, bias=self.variables["lm_head/bias"],
-                 out_f32=logits, passes=_PRECISIONS[self.precision], block_n=32)
+                 out_f32=logits, passes=self._modes.gemm, block_n=32)
         return logits, hidden
 
     def __call__(self, batch, attention_mask: Optional[torch.Tensor] = None, training=False):
@@ -637,5 +691,5 @@ class Wav2Vec2ForCTC(_B200Model):
         Vp = ((V + 31) // 32) * 32
         if Vp != V:
             w = torch.cat([w, torch.zeros(Vp - V, w.shape[1], device=self.device)], 0)
-        self._packed["lm.w"] = _split(w, _PRECISIONS[self.precision] == 3)
+        self._packed["lm.w"] = _split(w, self._modes.gemm)
         self._invalidate_graphs()                # the captured lm_head launch points at the old tensor

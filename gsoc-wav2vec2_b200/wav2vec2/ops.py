@@ -12,6 +12,7 @@ import torch
 from . import _lib
 
 BF16 = torch.bfloat16
+TWO_PLANE_MODES = (_lib.MODE_BF16X3, _lib.MODE_FP16X3, _lib.MODE_FP16F8)   # precision modes whose operands have a second plane
 LAUNCHES = 0   # kernels launched through this module (bench.py reports it as gpu_launches)
 
 
@@ -35,7 +36,8 @@ def _need_cuda(*ts):
 
 
 class Pair:
-    """A bf16 activation as hi (+ optional lo) planes; value ~= hi + lo."""
+    """An activation / weight as operand planes: hi (+ optional lo).  bf16 modes: value ~= hi + lo (bf16 each); fp16 modes: hi (+ lo)
+    = fp16 planes of value * 2^4 (weights: * 2^11); fp16f8: lo is the uint8 e4m3 pair plane [rows][2 K] (include/w2v2.h)."""
     __slots__ = ("hi", "lo")
 
     def __init__(self, hi, lo=None):
@@ -59,7 +61,7 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
          row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
-         res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None):
+         res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None, out_format=0):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
     ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
     ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride].
@@ -67,12 +69,13 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     value fp32 [N])``: SpecAugment row replacement; ``drop = (rate, seed, site)``: dropout before the residual add."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
     args = _lib.GemmArgs()
-    args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if passes == 3 else None
+    two = passes in TWO_PLANE_MODES
+    args.a_hi, args.a_lo = _ptr(a.hi), _ptr(a.lo) if two else None
     args.a_row_len = K if a_row_len is None else a_row_len
     args.a_rows = rows_per_batch if a_rows is None else a_rows
     args.a_row_stride = K if a_row_stride is None else a_row_stride
     args.a_batch_stride = (args.a_rows * args.a_row_stride) if a_batch_stride is None else a_batch_stride
-    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
+    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if two else None
     args.w_rows = w.hi.shape[0]
     args.K, args.N, args.rows_per_batch, args.batch = K, N, rows_per_batch, batch
     args.passes, args.kb_split, args.block_n, args.max_ctas, args.cluster = passes, kb_split, block_n, max_ctas, cluster
@@ -87,6 +90,7 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.bias, args.residual, args.row_valid = _ptr(bias), _ptr(residual), _ptr(row_valid)
     args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
+    args.out_format = out_format
     if res_ln is not None:
         _need_cuda(*res_ln)
         args.res_ln_stats, args.res_ln_gamma, args.res_ln_beta = (_ptr(t) for t in res_ln)
@@ -115,8 +119,9 @@ def conv0_gn_gelu(wave, kernel, scale, shift, out: Pair, passes=1, gelu_approx=F
     """Fused extractor layer 0: conv (tensor cores, no im2col) + folded GroupNorm + GELU, written once."""
     _need_cuda(wave, kernel, scale, shift, out.hi, out.lo)
     B, L = wave.shape
+    lo = out.lo if passes in TWO_PLANE_MODES else None
     _count(); _lib.check(_lib.load().w2v2_conv0_gn_gelu(_ptr(wave), B, L, kernel.shape[-1], _ptr(kernel), _ptr(scale),
-                                              _ptr(shift), _ptr(out.hi), _ptr(out.lo), passes, 1 if gelu_approx else 0,
+                                              _ptr(shift), _ptr(out.hi), _ptr(lo), passes, 1 if gelu_approx else 0,
                                               _stream()),
                          "w2v2_conv0_gn_gelu")
 
@@ -141,25 +146,33 @@ def normalize_utterances(wave, lengths=None, eps=1e-5, out=None):
     return out
 
 
-def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None, stats=None):
+def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None, out_lo=None, stats=None, out_format=0):
     """``stats`` [rows, 2] fp32 (optional) receives (mean, rstd) per row for ``gemm(..., res_ln=(stats, gamma, beta))``."""
     _need_cuda(x, gamma, beta, out_f32, out_hi, out_lo, stats)
-    _count(); _lib.check(_lib.load().w2v2_ln_rows_stats(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, int(gelu),
-                                              _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(stats), _stream()), "w2v2_ln_rows")
+    _count(); _lib.check(_lib.load().w2v2_ln_rows_ex(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, int(gelu),
+                                           _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(stats), out_format, _stream()),
+                         "w2v2_ln_rows")
 
 
-def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1):
+def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1, out_format=None):
+    """``passes``: 1 / 3 (bf16 planes) or 17 / 19 (fp16 planes of q, k, v * 2^4).  ``out_format`` (default: bf16 planes for the
+    bf16 modes, fp16 for the fp16 modes; 2 = fp16 + e4m3 pair plane for a mode-25 output projection); ``out.lo`` is written when
+    the mode has three passes (second 16-bit plane) or the format requires it (2)."""
     _need_cuda(qkv.hi, out.hi, kv_len)
-    _count(); _lib.check(_lib.load().w2v2_attn_fwd(_ptr(qkv.hi), _ptr(qkv.lo) if passes == 3 else None, B, T, H, dh,
-                                         _ptr(kv_len), _ptr(out.hi), _ptr(out.lo) if passes == 3 else None, passes,
-                                         _stream()), "w2v2_attn_fwd")
+    if out_format is None:
+        out_format = 1 if passes & 16 else 0
+    three = (passes & 3) == 3
+    out_lo = out.lo if (three or out_format == 2) else None
+    _count(); _lib.check(_lib.load().w2v2_attn_fwd_ex(_ptr(qkv.hi), _ptr(qkv.lo) if three else None, B, T, H, dh,
+                                            _ptr(kv_len), _ptr(out.hi), _ptr(out_lo), passes, out_format,
+                                            _stream()), "w2v2_attn_fwd")
 
 
 def posconv(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps, passes=1, gelu_approx=False):
     _need_cuda(x.hi, w.hi, bias, resid, out_f32)
     args = _lib.PosconvArgs()
-    args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if passes == 3 else None
-    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
+    args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if (passes & 3) == 3 else None
+    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if (passes & 3) == 3 else None
     args.bias, args.resid, args.out_f32 = _ptr(bias), _ptr(resid), _ptr(out_f32)
     args.batch, args.frames, args.hidden, args.groups, args.ktaps, args.passes = B, T, d, groups, ktaps, passes
     args.gelu_approx = 1 if gelu_approx else 0
@@ -285,8 +298,8 @@ def posconv_train(x: Pair, w: Pair, bias, resid, out_f32, B, T, d, groups, ktaps
     """w2v2_posconv with the training options: pre-activation output / transposed-conv (input gradient) mode."""
     _need_cuda(x.hi, w.hi, bias, resid, out_f32, pre_out)
     args = _lib.PosconvArgs()
-    args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if passes == 3 else None
-    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if passes == 3 else None
+    args.x_hi, args.x_lo = _ptr(x.hi), _ptr(x.lo) if (passes & 3) == 3 else None
+    args.w_hi, args.w_lo = _ptr(w.hi), _ptr(w.lo) if (passes & 3) == 3 else None
     args.bias, args.resid, args.out_f32 = _ptr(bias), _ptr(resid), _ptr(out_f32)
     args.batch, args.frames, args.hidden, args.groups, args.ktaps, args.passes = B, T, d, groups, ktaps, passes
     args.pre_out, args.shift, args.linear = _ptr(pre_out), shift, 1 if linear else 0

@@ -154,6 +154,8 @@ class Stage2Trainer:
             raise NotImplementedError("Stage2Trainer covers the base architecture (group-norm extractor, post-norm encoder)")
         if cfg.is_gelu_approx:
             raise NotImplementedError("Stage2Trainer differentiates the erf GELU (config.is_gelu_approx=False, the reference default)")
+        if model.precision not in ("bf16", "bf16x3"):
+            raise NotImplementedError("Stage2Trainer runs its forward in precision 'bf16' or 'bf16x3' (backward products are bf16)")
         self.model, self.loss_fn = model, loss_fn
         self.seed = int(seed)
         self.lr, self.b1, self.b2, self.eps = learning_rate, beta_1, beta_2, epsilon

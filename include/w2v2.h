@@ -46,6 +46,24 @@ const char* w2v2_last_error_string(void);
 #define W2V2_GEMM_GELU 1u /* GELU after bias (feature_extractor.py:58, encoder.py:127): erf-exact in 3-pass (parity) mode;
                              single-pass mode uses the bf16-grade tanh form (|err| < 5e-4) */
 
+/* Precision modes - the `passes` argument of every tensor-core entry point:
+ *    1  bf16     one MMA per product on bf16 operands                                   (throughput mode, ~3e-2 on the logits)
+ *    3  bf16x3   split-bf16: hi*hi + lo*hi + hi*lo, planes bf16 hi + bf16 lo              (parity mode, ~1.4e-4)
+ *   17  fp16     one MMA on fp16 operands; planes hold activation * 2^4, weight * 2^11    (~3e-3, the reference's own 4e-3 logits bar)
+ *   19  fp16x3   split-fp16, planes fp16 hi + fp16 lo (same scaling)
+ *   25  fp16f8   fp16 main product + BOTH cross terms as e4m3 MMAs (kind::f8f6f4, twice the bf16 rate): planes = fp16 hi and a
+ *                byte plane [rows][2 K] holding, per 64-element k-block, 64 x e4m3((v - hi) * 2^6) then 64 x e4m3(hi * 2^-6)
+ *                (weights: the two halves swapped), so the two cross terms are ONE K = 128 e4m3 product       (~2e-4, 2 MMA units)
+ * All fp16 modes accumulate at scale 2^15 in fp32 and un-scale in the epilogue. */
+#define W2V2_MODE_BF16 1
+#define W2V2_MODE_BF16X3 3
+#define W2V2_MODE_FP16 17
+#define W2V2_MODE_FP16X3 19
+#define W2V2_MODE_FP16F8 25
+#define W2V2_OUT_BF16 0   /* out_hi (/ out_lo): bf16 planes of the value */
+#define W2V2_OUT_FP16 1   /* fp16 planes of value * 2^4 (hi, optional lo = residual) */
+#define W2V2_OUT_FP16F8 2 /* out_hi = fp16(value * 2^4), out_lo = e4m3 pair plane [rows][2 N] bytes (N % 64 == 0) */
+
 #define W2V2_GEMM_GELU_TANH 4u /* GELU after bias in tf.nn.gelu(approximate=True) form - the reference's `is_gelu_approx` switch
                                   (config.py:14); fp32-grade in every precision mode */
 
@@ -65,7 +83,7 @@ typedef struct w2v2_gemm_args {
   int32_t N;               /* output columns; leading dimension of residual and outputs */
   int32_t rows_per_batch;  /* output rows per batch entry */
   int32_t batch;
-  int32_t passes;          /* 1 = bf16 operands; 3 = split-bf16 (hi*hi + lo*hi + hi*lo) */
+  int32_t passes;          /* precision mode W2V2_MODE_*: 1 = bf16 operands; 3 = split-bf16 (hi*hi + lo*hi + hi*lo); 17 / 19 / 25 */
   int32_t kb_split;        /* 0, or: 64-wide k-blocks >= kb_split come from (k - 64*kb_split, row+1) */
   int32_t block_n;         /* 0 = auto (256/128/64/32) */
   int32_t max_ctas;        /* 0 = one persistent CTA per SM */
@@ -99,6 +117,8 @@ typedef struct w2v2_gemm_args {
   float drop_p;                    /* 0 = off */
   uint32_t drop_site;
   uint64_t drop_seed;
+  int32_t out_format;              /* layout of out_hi / out_lo: W2V2_OUT_BF16 (0), W2V2_OUT_FP16 (1), W2V2_OUT_FP16F8 (2) */
+  int32_t reserved0;
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
@@ -145,6 +165,10 @@ int w2v2_ln_rows(const float* x, const float* gamma, const float* beta, float ep
 int w2v2_ln_rows_stats(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
                        float* out_f32, void* out_hi, void* out_lo, float* stats, void* stream);
 
+/* same, with the layout of out_hi / out_lo chosen by out_format (W2V2_OUT_BF16 / W2V2_OUT_FP16 / W2V2_OUT_FP16F8) */
+int w2v2_ln_rows_ex(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
+                    float* out_f32, void* out_hi, void* out_lo, float* stats, int out_format, void* stream);
+
 /* Wav2Vec2Processor._normalize (processor.py:101-106) on the device: per utterance (x - mean) / sqrt(var + eps) with the
  * biased variance over its lengths[b] real samples (NULL: all num_samples); the padded tail is written as 0
  * (normalise BEFORE padding, data_utils.py:233,63).  In place (out == wave) is allowed. */
@@ -162,6 +186,10 @@ int w2v2_split_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream)
  * ------------------------------------------------------------------------------------------- */
 int w2v2_attn_fwd(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
                   const int32_t* kv_len, void* out_hi, void* out_lo, int passes, void* stream);
+/* same with the precision modes 17 / 19 (fp16 planes of q / k / v * 2^4) and the layout of out_hi / out_lo chosen by out_format
+ * (W2V2_OUT_*; W2V2_OUT_FP16F8 feeds an output projection running in mode 25) */
+int w2v2_attn_fwd_ex(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
+                     const int32_t* kv_len, void* out_hi, void* out_lo, int passes, int out_format, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Positional convolution + GELU + residual: out = resid + gelu(bias + grouped_conv_k(x)).

@@ -34,7 +34,7 @@ def site_mode():
 
 
 # static power-of-two scales of the e4m3 cross terms per site kind: (a_lo, b_hi, a_hi, b_lo), a_lo + b_hi = a_hi + b_lo = 15
-F8_SCALES = {"dense": (8, 7, -3, 18), "conv": (8, 7, -3, 18), "qk": (12, 3, 3, 12), "pv": (11, 4, 8, 7)}
+F8_SCALES = {"dense": (8, 7, -3, 18), "conv": (8, 7, -3, 18), "pos": (8, 7, -3, 18), "qk": (12, 3, 3, 12), "pv": (11, 4, 8, 7)}
 
 
 def _r(x, dt):
@@ -73,14 +73,14 @@ def terms(a, b):
         # the recipe as the kernels would implement it: operands pre-scaled (activation x 2^4, weight x 2^11; both x 2^4 when the
         # "weight" is an activation too), fp16 main product, e4m3 cross terms at 2^+-6, everything at scale 2^15 (2^8) in ONE
         # fp32 accumulator, un-scaled by the epilogue
-        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv") else 2.0 ** 4)
+        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv", "pos") else 2.0 ** 4)
         a2, b2 = (a * sa).clamp(-65504, 65504), (b * sb).clamp(-65504, 65504)
         ah, bh = _r(a2, torch.float16), _r(b2, torch.float16)
         al, bl = a2 - ah, b2 - bh
         s = 1.0 / (sa * sb)
         return [(ah, bh, s), (_e4m3(al * 64.0), _e4m3(bh / 64.0), s), (_e4m3(ah / 64.0), _e4m3(bl * 64.0), s)]
     if m == "f16s":
-        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv") else 2.0 ** 4)
+        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv", "pos") else 2.0 ** 4)
         a2, b2 = (a * sa).clamp(-65504, 65504), (b * sb).clamp(-65504, 65504)
         return [(_r(a2, torch.float16), _r(b2, torch.float16), 1.0 / (sa * sb))]
     raise ValueError(m)
@@ -92,7 +92,7 @@ def q_dense(x, kernel, bias):
 
 
 def q_conv(x, kernel, bias=None, stride=1, groups=1):
-    SITE["cur"] = "conv"
+    SITE["cur"] = "conv" if groups == 1 else "pos"      # the grouped conv is the positional embedding
     y = 0.0
     for a, b, s in terms(x, kernel):
         y = y + s * F.conv1d(a.transpose(1, 2), b.permute(2, 1, 0).contiguous(), stride=stride, groups=groups)

@@ -46,7 +46,7 @@ def test_full_length_logits_match_oracle(arch):
     with torch.no_grad():
         ref = O.wav2vec2_for_ctc(x, params, cfg, attention_mask=mask)
     assert ref.shape == (2, 768, cfg.vocab_size)
-    for precision, tol in (("bf16x3", 1e-3), ("bf16", 1e-1)):
+    for precision, tol in (("bf16x3", 1e-3), ("fp16f8", 1e-3), ("fp16", 6e-3), ("bf16", 1e-1)):
         m = Wav2Vec2ForCTC(cfg, input_shape=(2, L), precision=precision)
         m.set_variables(params)
         got = m(x.cuda(), attention_mask=None if mask is None else mask.cuda()).cpu()
@@ -54,7 +54,7 @@ def test_full_length_logits_match_oracle(arch):
         agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
         print(f"{arch} 2x{L} {precision}: logits max-abs err {err:.3e} (max |logit| {ref.abs().max():.2f}), argmax agreement {agree:.4f}")
         assert err < tol
-        if precision == "bf16x3":
+        if precision in ("bf16x3", "fp16f8"):
             assert agree == 1.0
         del m
         torch.cuda.empty_cache()
@@ -78,8 +78,7 @@ def test_bench_batch_spot_check():
 
 def test_stage2_gradients_full_depth_full_length():
     """configs[2] at its real depth and length: 12 layers x 246000 samples (B = 1), loss and all trainable gradients of the
-    stage-2 step against the oracle's autograd (fp32 here: an fp64 run of this size takes minutes), dropout 0, SpecAugment
-    mask fixed.  Tolerances as in tests/test_backward_gpu.py (relative L2 per tensor)."""
+    stage-2 step against the oracle's fp64 autograd, dropout 0, SpecAugment mask fixed.  Tolerances as in tests/test_backward_gpu.py (relative L2 per tensor)."""
     import numpy as np
     from wav2vec2.training import Stage2Trainer
     cfg = Wav2Vec2Config(dropout=0.0)
@@ -92,8 +91,8 @@ def test_stage2_gradients_full_depth_full_length():
     spec[0, 100:110] = 1
     spec[0, 400:410] = 1
     names = [k for k in params if "/feature_extractor/" not in k]
-    p = {k: (t.clone().requires_grad_(True) if k in names else t) for k, t in params.items()}
-    logits = O.wav2vec2_for_ctc(x, p, cfg, spec_mask=torch.from_numpy(spec).bool())
+    p = {k: (t.double().clone().requires_grad_(True) if k in names else t.double()) for k, t in params.items()}
+    logits = O.wav2vec2_for_ctc(x.double(), p, cfg, spec_mask=torch.from_numpy(spec).bool())
     lp = torch.log_softmax(logits.double(), -1).transpose(0, 1)
     loss_ref = torch.nn.functional.ctc_loss(lp, labels.long(), torch.full((1,), T), (labels != cfg.pad_id).sum(-1),
                                             blank=cfg.pad_id, reduction="sum")
@@ -104,17 +103,14 @@ def test_stage2_gradients_full_depth_full_length():
     loss = tr.loss_and_gradients(x.cuda(), labels.cuda(), spec_mask=spec)
     print(f"stage-2 12 layers x {L}: loss {float(loss):.4f} vs oracle {float(loss_ref):.4f}")
     assert abs(float(loss) - float(loss_ref)) < 2e-3 * max(1.0, abs(float(loss_ref)))
-    worst = ("", 0.0)
+    table = []
     for k in names:
         g_ref = p[k].grad
-        if g_ref is None:
+        if g_ref is None or k.endswith("k_proj/bias"):   # k_proj/bias: exact gradient 0 (softmax shift invariance)
             continue
-        g = tr.G[k].cpu()
-        den = g_ref.norm().item()
-        if den < 1e-6:                       # k_proj/bias: exact gradient 0 (softmax shift invariance)
-            continue
-        rel = (g - g_ref).norm().item() / den
-        if rel > worst[1]:
-            worst = (k, rel)
-    print(f"worst gradient relative L2: {worst[1]:.3e} ({worst[0]})")
-    assert worst[1] < 5e-2
+        g = tr.G[k].cpu().double()
+        table.append(((g - g_ref).norm().item() / max(g_ref.norm().item(), 1e-30), k, g_ref.norm().item(), g.norm().item()))
+    table.sort(reverse=True)
+    for rel, k, nr, ng in table[:12]:
+        print(f"  rel L2 {rel:.3e}  |ref| {nr:.3e}  |got| {ng:.3e}  {k}")
+    assert table[0][0] < 5e-2
