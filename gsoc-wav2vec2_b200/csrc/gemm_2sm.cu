@@ -23,7 +23,8 @@ constexpr int GEMM2_REGS_CONTROL = 32, GEMM2_REGS_EPILOGUE = 112;
 // staging blocks (two per warp, double-buffered) instead of per-lane row loads; it trades one ring stage for them.
 template <int EPI>
 struct Gemm2Smem {
-  static constexpr bool TMA_RES = (EPI == (EPI_RESID | EPI_F32 | EPI_TMARES));
+  // (+ EPI_HI [| EPI_LO]: the same recipe also writes the operand planes and row statistics of the sum - LayerNorm-fold producer)
+  static constexpr bool TMA_RES = (EPI >= 0) && ((EPI & ~(EPI_HI | EPI_LO)) == (EPI_RESID | EPI_F32 | EPI_TMARES));
   static constexpr int STAGES = GEMM2_STAGES;
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;           // 16 KB
   static constexpr int B_BYTES = (GEMM2_BLOCK_N / 2) * GEMM_BLOCK_K * 2;     // 16 KB: this CTA's half of the n-tile
@@ -67,7 +68,7 @@ struct Gemm2OutMaps {
 // erf-GELU, fp32 residual (coalesced block load through the staging block) and row masking run in registers.
 // Every output leaves through a 2 KB staging block (32 rows x 64 B, 64-byte swizzle) and a TMA bulk store per
 // 64-byte column slab (32 bf16 or 16 fp32 columns); rows past the utterance are clipped by the tensor map.
-template <int EPI>
+template <int EPI, int PASSES>
 __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const Gemm2OutMaps& om, uint32_t taddr, int cg,
                                                     int n0, int t_warp0, int b, int rows_valid, bool zero_row,
                                                     const float* sb, uint8_t* stage, uint64_t* res_bar,
@@ -80,6 +81,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
   const bool f_lo = (EPI >= 0) ? bool(EPI & EPI_LO) : (p.out_lo != nullptr);
   const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
+  const bool f_fold = (EPI >= 0) ? bool(EPI & EPI_LNFOLD) : (p.ln_fold_stats != nullptr);
   const int lane = lane_id();
   const int c_base = 64 * cg;       // first column of this warp inside the tile
   const int n = n0 + c_base;        // ... and in the output
@@ -103,9 +105,16 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   const bool f_ln = f_res && p.ln_stats != nullptr;
   float ln_mean = 0.0f, ln_rstd = 0.0f;
   if (f_ln && lane < rows_valid) {
-    const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow0 + lane);
+    const float2 st = (p.res_ln_parts > 0) ? mean_rstd_from_parts(p.ln_stats, orow0 + lane, p.res_ln_parts, 1.0f / (float)p.N, p.ln_eps)
+                                           : __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow0 + lane);
     ln_mean = st.x;
     ln_rstd = st.y;
+  }
+  float fold_rs = p.acc_scale, fold_nm = 0.0f;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
+  if (f_fold && lane < rows_valid) {
+    const float2 st = mean_rstd_from_parts(p.ln_fold_stats, orow0 + lane, p.ln_fold_parts, p.ln_fold_inv_dim, p.ln_eps);
+    fold_rs = st.y * p.acc_scale;
+    fold_nm = -st.y * st.x;
   }
 
   if constexpr (Gemm2Smem<EPI>::TMA_RES) {
@@ -131,6 +140,10 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         o.w = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), p.acc_scale, bb.w) + rr.w;
         if (zero_row) o = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         *reinterpret_cast<float4*>(bslot(j)) = o;
+        r[i][16 * hf + 4 * j + 0] = __float_as_uint(o.x);   // kept for the row statistics / operand planes below
+        r[i][16 * hf + 4 * j + 1] = __float_as_uint(o.y);
+        r[i][16 * hf + 4 * j + 2] = __float_as_uint(o.z);
+        r[i][16 * hf + 4 * j + 3] = __float_as_uint(o.w);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -141,6 +154,74 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
           bulk_wait_read0();
           mbar_arrive_expect_tx(&res_bar[q & 1], Gemm2Smem<EPI>::EPI_BLOCK_BYTES);
           tma_load_3d(blk, &om.res, &res_bar[q & 1], n + 16 * (q + 2), t_warp0, b);
+        }
+      }
+      __syncwarp();
+    }
+    if (p.row_stats_out != nullptr && lane < rows_valid) {
+      // (sum, sum of squares) of this row over the warp's 64 columns: the LayerNorm statistics of the NEXT GEMM's folded LayerNorm
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(r[i][j]);
+          s1 += x;
+          s2 = fmaf(x, x, s2);
+        }
+      }
+      reinterpret_cast<float2*>(p.row_stats_out)[(orow0 + lane) * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
+    }
+    if constexpr ((EPI & EPI_HI) != 0) {
+      // operand planes of the SUM (the un-normalised LayerNorm input the next GEMM consumes): the two staging blocks are free
+      // once the four fp32 slab stores have read them.  PASSES == 2 (fp16f8): fp16 + e4m3 pair plane; else bf16 or fp16 (out_format)
+      const int fmt = (PASSES == 2) ? 2 : p.out_format;
+      auto pslot = [&](int blk_i, int piece) { return stage + blk_i * Gemm2Smem<EPI>::EPI_BLOCK_BYTES + lane * 64 + ((piece ^ ((lane >> 1) & 3)) << 4); };
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float v0 = __uint_as_float(r[i][8 * j + 2 * e]), v1 = __uint_as_float(r[i][8 * j + 2 * e + 1]);
+            h[e] = (fmt == 0) ? split_bf16x2(v0, v1, l[e]) : split_f16x2(v0 * ACT_SCALE, v1 * ACT_SCALE, l[e]);
+          }
+          *reinterpret_cast<uint4*>(pslot(i, j)) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&om.hi, stage, n, t_warp0, b);
+        tma_store_3d(&om.hi, stage + Gemm2Smem<EPI>::EPI_BLOCK_BYTES, n + 32, t_warp0, b);
+        bulk_commit();
+      }
+      if constexpr (PASSES == 2 && (EPI & EPI_LO) != 0) {
+        if (lane == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {      // 16 columns -> 16 bytes
+            uint16_t l8[8], h8[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              split_f16_f8x2(__uint_as_float(r[j >> 1][16 * (j & 1) + 2 * e]) * ACT_SCALE,
+                             __uint_as_float(r[j >> 1][16 * (j & 1) + 2 * e + 1]) * ACT_SCALE, l8[e], h8[e]);
+            const uint16_t* s8 = half == 0 ? l8 : h8;
+            *reinterpret_cast<uint4*>(pslot(half, j)) = make_uint4(s8[0] | ((uint32_t)s8[1] << 16), s8[2] | ((uint32_t)s8[3] << 16),
+                                                                   s8[4] | ((uint32_t)s8[5] << 16), s8[6] | ((uint32_t)s8[7] << 16));
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&om.lo, stage, 2 * n, t_warp0, b);
+          tma_store_3d(&om.lo, stage + Gemm2Smem<EPI>::EPI_BLOCK_BYTES, 2 * n + 64, t_warp0, b);
+          bulk_commit();
         }
       }
       __syncwarp();
@@ -183,7 +264,13 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
-      if (f_scale) {
+      if (f_fold) {
+        const float4 cs = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 4 * j);
+        v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), fold_rs, fmaf(fold_nm, cs.x, bb.x));
+        v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), fold_rs, fmaf(fold_nm, cs.y, bb.y));
+        v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), fold_rs, fmaf(fold_nm, cs.z, bb.z));
+        v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), fold_rs, fmaf(fold_nm, cs.w, bb.w));
+      } else if (f_scale) {
         const float4 sc = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 4 * j);
         v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), sc.x, bb.x);
         v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), sc.y, bb.y);
@@ -224,6 +311,20 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
+  }
+
+  if (EPI < 0 && p.row_stats_out != nullptr && lane < rows_valid) {
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float x = __uint_as_float(r[i][j]);
+        s1 += x;
+        s2 = fmaf(x, x, s2);
+      }
+    }
+    reinterpret_cast<float2*>(p.row_stats_out)[(orow0 + lane) * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
   }
 
   // ---- pass B: outputs, one 64-byte column slab per bulk store
@@ -493,7 +594,7 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
-      gemm2_epilogue_warp<EPI>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage, res_bar,
+      gemm2_epilogue_warp<EPI, PASSES>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage, res_bar,
                                mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
       park_bias(acc ^ 1, next_bias);
       asm volatile("bar.sync 1, 512;" ::: "memory");   // every warp is done with this tile's slice; the next one is visible
@@ -586,6 +687,13 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
   // the rarely used epilogue options (tf-approximate GELU, dropout, SpecAugment row replacement) only exist in the run-time instance
   if ((a->flags & W2V2_GEMM_GELU_TANH) || a->row_replace_mask != nullptr || a->drop_p > 0.0f)
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
+  if (a->ln_fold_stats != nullptr) {   // LayerNorm folded into the GEMM (QKV, FFN1): the scale slot carries the column sums
+    if (!res && !f32 && hi && lo == (PASSES != 1) && a->row_stats_out == nullptr) {
+      if (gelu) return launch_gemm_2sm_t<PASSES, EPI_LNFOLD | EPI_SCALE | G | EPI_HI | LO>(a, s);
+      return launch_gemm_2sm_t<PASSES, EPI_LNFOLD | EPI_SCALE | EPI_HI | LO>(a, s);
+    }
+    return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
+  }
   if (sc) {
     if (gelu && !res && !f32 && hi && lo == (PASSES != 1)) return launch_gemm_2sm_t<PASSES, EPI_SCALE | G | EPI_HI | LO>(a, s);
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
@@ -600,6 +708,12 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
     static const int maxk = [] { const char* e = getenv("W2V2_RES_TMA_MAXK"); return e ? atoi(e) : (1 << 30); }();
     if (!gelu && res && f32 && !hi && a->N % 64 == 0 && a->K * PASSES <= maxk)
       return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32 | EPI_TMARES>(a, s);
+  }
+  // fp32 sum + its operand planes + row statistics (the producer side of a folded LayerNorm): same recipe, planes written last
+  if (PASSES != 3 && !gelu && res && f32 && hi && lo == (PASSES == 2) && a->N % 64 == 0 && (PASSES != 2 || a->out_format == 2)) {
+    return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32 | EPI_TMARES | EPI_HI | ((PASSES == 2) ? EPI_LO : 0)>(a, s);
+  }
+  if (lo == (PASSES != 1) || !hi) {
     if (!gelu && res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32>(a, s);
   }
   return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);

@@ -18,7 +18,9 @@ constexpr int GEMM_REGS_EPILOGUE = 224;
 // epilogue recipe bits (template parameter EPI of the kernels; EPI < 0 = decide from GemmParams at run time)
 constexpr int EPI_GELU = 1, EPI_RESID = 2, EPI_F32 = 4, EPI_HI = 8, EPI_LO = 16, EPI_SCALE = 32,
               EPI_FASTGELU = 64,     // tanh-form GELU (single-pass mode only; see gelu_tanh_p2)
-              EPI_TMARES = 128;    // 2-SM kernel: residual slabs fetched by TMA into the staging blocks
+              EPI_TMARES = 128,    // 2-SM kernel: residual slabs fetched by TMA into the staging blocks
+              EPI_LNFOLD = 256;    // the A operand is the UN-normalised LayerNorm input: the epilogue applies mean / rstd per row
+                                   // (needs EPI_SCALE: the scale slot then carries colsum(gamma o W) instead of a multiplier)
 constexpr int EPI_RUNTIME = -1;
 
 struct GemmParams {
@@ -45,6 +47,14 @@ struct GemmParams {
   const uint8_t* row_replace;  // [batch*rows_per_batch] or null: rows with a non-zero byte are written as row_value[0:N] (SpecAugment)
   const float* row_value;      // [N]
   DropSpec drop;               // dropout on the activation (after bias / GELU, before the residual); thr16 == 0: off
+  // LayerNorm folded into this GEMM (w2v2.h ln_fold_*): out = rstd_r * acc - rstd_r * mean_r * colsum[n] + bias[n]; (mean, rstd) of
+  // row r come from partial (sum, sum of squares) pairs over 64-column groups of the K input columns
+  const float* ln_fold_stats;  // [rows][ln_fold_parts][2] or null
+  int ln_fold_parts;
+  float ln_fold_inv_dim;       // 1 / K
+  float ln_eps;
+  float* row_stats_out;        // optional [rows][N / 64][2]: (sum, sum of squares) of the fp32 output per 64-column group
+  int res_ln_parts;            // 0: ln_stats holds (mean, rstd) per row; > 0: partial sums over N columns in that many groups
   int fp16;               // 1: the 16-bit operand planes are fp16 (idesc format 0) instead of bf16
   float acc_scale;        // accumulator -> value: 1, or 2^-15 for the scaled fp16 operand planes (ACT_SCALE * WGT_SCALE)
   int out_format;         // bf16/16-bit outputs: 0 = bf16 hi(/lo), 1 = fp16 hi(/lo) of value * 2^4, 2 = fp16 hi + e4m3 pair plane
@@ -52,6 +62,20 @@ struct GemmParams {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
 };
+
+// (mean, rstd) of one row from its partial sums: `parts` (sum, sum of squares) pairs, added in index order (deterministic)
+__device__ __forceinline__ float2 mean_rstd_from_parts(const float* stats, size_t row, int parts, float inv_dim, float eps) {
+  const float2* p2 = reinterpret_cast<const float2*>(stats) + row * parts;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = __ldg(p2 + i);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const float mean = s1 * inv_dim;
+  const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.0f);
+  return make_float2(mean, rsqrtf(var + eps));
+}
 
 // residual term "LayerNorm(r)" with the statistics written by w2v2_ln_rows_stats: the SAME expression as ln_rows_kernel, so
 // the value is bit-identical to the fp32 LayerNorm output it replaces
@@ -93,6 +117,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   const bool f_hi = (EPI >= 0) ? bool(EPI & EPI_HI) : (p.out_hi != nullptr);
   const bool f_lo = (EPI >= 0) ? bool(EPI & EPI_LO) : (p.out_lo != nullptr);
   const bool f_scale = (EPI >= 0) ? bool(EPI & EPI_SCALE) : (p.scale != nullptr);
+  const bool f_fold = (EPI >= 0) ? bool(EPI & EPI_LNFOLD) : (p.ln_fold_stats != nullptr);
   constexpr int NCH = BLOCK_N / 32;
   constexpr int NMINE = (NCH >= 4) ? NCH / 2 : NCH;  // chunks per warp (grp 1 idles when NCH < 4)
   const int lane = lane_id();
@@ -122,9 +147,16 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   const bool f_ln = f_res && p.ln_stats != nullptr;
   float ln_mean = 0.0f, ln_rstd = 0.0f;
   if (f_ln && row_ok) {
-    const float2 st = __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
+    const float2 st = (p.res_ln_parts > 0) ? mean_rstd_from_parts(p.ln_stats, orow, p.res_ln_parts, 1.0f / (float)p.N, p.ln_eps)
+                                           : __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
     ln_mean = st.x;
     ln_rstd = st.y;
+  }
+  float fold_rs = p.acc_scale, fold_nm = 0.0f;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
+  if (f_fold && row_ok) {
+    const float2 st = mean_rstd_from_parts(p.ln_fold_stats, orow, p.ln_fold_parts, p.ln_fold_inv_dim, p.ln_eps);
+    fold_rs = st.y * p.acc_scale;
+    fold_nm = -st.y * st.x;
   }
 
   // staged 32 x 128 B block -> global, 8 lanes per row (PIECES = 8) or 4 lanes per row (PIECES = 4: 64-byte rows)
@@ -217,7 +249,13 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 16 * hf + 4 * j);
-        if (f_scale) {
+        if (f_fold) {
+          const float4 cs = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 16 * hf + 4 * j);
+          v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), fold_rs, fmaf(fold_nm, cs.x, bb.x));
+          v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), fold_rs, fmaf(fold_nm, cs.y, bb.y));
+          v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), fold_rs, fmaf(fold_nm, cs.z, bb.z));
+          v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), fold_rs, fmaf(fold_nm, cs.w, bb.w));
+        } else if (f_scale) {
           const float4 sc = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 16 * hf + 4 * j);
           v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), sc.x, bb.x);
           v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), sc.y, bb.y);
@@ -259,6 +297,25 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   if (p.debug == 2) {
     if (__uint_as_float(r[0][0] ^ r[NMINE - 1][31]) == 1.2345e-30f) p.out_f32[0] = 0.0f;
     return;
+  }
+  if (EPI < 0 && p.row_stats_out != nullptr && row_ok) {
+    // (sum, sum of squares) of this row's output per 64-column group = per chunk pair (N % 64 == 0: checked by the launcher)
+#pragma unroll
+    for (int i = 0; i + 1 < NMINE; i += 2) {
+      const int n = n0 + chunk_of(i) * 32;
+      if (chunk_of(i) >= NCH || n >= p.N) continue;
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float x = __uint_as_float(r[i + u][j]);
+          s1 += x;
+          s2 = fmaf(x, x, s2);
+        }
+      }
+      reinterpret_cast<float2*>(p.row_stats_out)[orow * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
+    }
   }
 
   // ---- pass B: stores
@@ -359,7 +416,7 @@ __device__ __forceinline__ void gemm_epilogue_prepare(const GemmParams& p, int e
   const size_t boff = (size_t)b * p.bias_bstride + n0 + et;
   if (et < BLOCK_N) {
     sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + boff) : 0.0f;
-    if (f_scale) sb[2 * BLOCK_N + et] = (n0 + et < p.N) ? __ldg(p.scale + boff) : 1.0f;  // scale slices follow the bias slices
+    if (f_scale) sb[2 * BLOCK_N + et] = (n0 + et < p.N) ? __ldg(p.scale + boff) : 1.0f;  // scale (or LayerNorm-fold colsum) slices follow the bias slices
   }
   const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
   if (f_res && row_ok) {

@@ -302,6 +302,12 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.fp16 = mode_fp16(a->passes) ? 1 : 0;
   p.acc_scale = mode_fp16(a->passes) ? ACC_UNSCALE : 1.0f;
   p.out_format = a->out_format;
+  p.ln_fold_stats = a->ln_fold_parts > 0 ? a->ln_fold_stats : nullptr;
+  p.ln_fold_parts = a->ln_fold_parts;
+  p.ln_fold_inv_dim = 1.0f / (float)a->K;
+  p.ln_eps = a->ln_eps;
+  p.row_stats_out = a->row_stats_out;
+  p.res_ln_parts = a->res_ln_parts;
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
   p.mn_major = (a->flags & W2V2_GEMM_MN_MAJOR) ? 1 : 0;
@@ -398,7 +404,12 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   W2V2_CHECK_ARG((np == 1 && !mode_f8(a->passes)) || (a->a_lo && a->w_lo), "multi-plane modes need the second planes");
   W2V2_CHECK_ARG(a->out_format >= 0 && a->out_format <= 2, "out_format must be 0 (bf16), 1 (fp16) or 2 (fp16 + e4m3 pairs)");
   W2V2_CHECK_ARG(a->out_format != 2 || (a->out_hi && a->out_lo && a->N % 64 == 0), "out_format 2 writes both planes and needs N % 64 == 0");
-  W2V2_CHECK_ARG(!mode_fp16(a->passes) || a->scale == nullptr, "per-column scale is not combined with the scaled fp16 planes");
+  W2V2_CHECK_ARG(!mode_fp16(a->passes) || a->scale == nullptr || a->ln_fold_parts > 0, "per-column scale is not combined with the scaled fp16 planes");
+  W2V2_CHECK_ARG(a->ln_fold_parts == 0 || (a->ln_fold_parts > 0 && a->ln_fold_stats && a->scale && a->bias && a->bias_batch_stride == 0),
+                 "ln_fold_parts > 0 needs ln_fold_stats, scale (= colsum(gamma o W)) and bias (= beta W + b), shared by all batch entries");
+  W2V2_CHECK_ARG(a->row_stats_out == nullptr || (a->N % 64 == 0 && a->out_f32 != nullptr && !(a->flags & W2V2_GEMM_MN_MAJOR)),
+                 "row_stats_out needs out_f32 and N % 64 == 0");
+  W2V2_CHECK_ARG(a->res_ln_parts >= 0 && a->ln_fold_parts >= 0, "partial-sum counts must be non-negative");
   W2V2_CHECK_ARG(a->K > 0 && a->K % GEMM_BLOCK_K == 0, "K must be a positive multiple of 64");
   W2V2_CHECK_ARG(a->N > 0 && a->rows_per_batch > 0 && a->batch > 0, "N, rows_per_batch, batch must be positive");
   W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements (16 B)");
@@ -458,4 +469,4 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
 }
 
 extern "C" const char* w2v2_last_error_string(void) { return w2v2::g_last_error; }
-extern "C" int w2v2_version(void) { return 130; }   // 1.3: epilogue dropout / row replacement / tf-approximate GELU in w2v2_gemm_args, gelu_kind arguments
+extern "C" int w2v2_version(void) { return 140; }   // 1.4: precision modes 17 / 19 / 25, output formats, LayerNorm fold (ln_fold_*, row_stats_out)

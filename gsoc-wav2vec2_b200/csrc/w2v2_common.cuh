@@ -534,6 +534,13 @@ __device__ __forceinline__ uint32_t split_f16_f8x2(float v0, float v1, uint16_t&
   return hi;
 }
 
+// one half of that: HALF == 0 -> the two residual bytes, HALF == 1 -> the two hi bytes (v already scaled by ACT_SCALE)
+template <int HALF>
+__device__ __forceinline__ uint32_t f8_pair_of(float v0, float v1) {
+  const uint32_t hi = pack_f16x2(v0, v1);
+  const float h0 = f16_lo_to_f32(hi), h1 = f16_hi_to_f32(hi);
+  return HALF == 0 ? pack_e4m3x2((v0 - h0) * F8_UP, (v1 - h1) * F8_UP) : pack_e4m3x2(h0 * F8_DOWN, h1 * F8_DOWN);
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -36,7 +36,8 @@ class GemmArgs(C.Structure):
         ("w_row_stride", C.c_int64),
         ("row_replace_mask", C.c_void_p), ("row_replace_value", C.c_void_p),
         ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("drop_seed", C.c_uint64),
-        ("out_format", C.c_int32), ("reserved0", C.c_int32),
+        ("out_format", C.c_int32), ("ln_fold_parts", C.c_int32), ("ln_fold_stats", C.c_void_p),
+        ("ln_eps", C.c_float), ("res_ln_parts", C.c_int32), ("row_stats_out", C.c_void_p),
     ]
 
 

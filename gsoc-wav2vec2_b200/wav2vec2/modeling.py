@@ -174,6 +174,20 @@ def _split(t: torch.Tensor, lo) -> Pair:
     return Pair(hi, torch.cat([h8, l8], dim=2).reshape(tuple(t.shape[:-1]) + (2 * K,)).contiguous())
 
 
+def _effective_weight(p: Pair, mode: int) -> torch.Tensor:
+    """fp32 value the tensor cores effectively multiply by for weight planes packed by ``_split(w, mode)``."""
+    if mode in (1, 3):
+        return p.hi.float() if p.lo is None else p.hi.float() + p.lo.float()
+    hi = p.hi.float()
+    if mode == 17:
+        return hi / 2048.0
+    if mode == 19:
+        return (hi + p.lo.float()) / 2048.0
+    rows, K = hi.shape
+    l8 = p.lo.reshape(rows, K // 64, 2, 64)[:, :, 1].contiguous().view(torch.float8_e4m3fn).float().reshape(rows, K)
+    return (hi + l8 / 64.0) / 2048.0
+
+
 def pack_posconv_kernel(kern: torch.Tensor, groups: int) -> torch.Tensor:
     """TF grouped-conv kernel [k, cin/groups, cout] -> the posconv kernel's layout [groups][k][cin/8][cout/groups][8]."""
     k, cpg, d = kern.shape
@@ -356,6 +370,28 @@ class _B200Model:
             ff = f"wav2vec2/encoder/layers/{i}/feed_forward/"
             P[f"l{i}.ff1.w"] = _split(v[ff + "intermediate_dense/kernel"].t(), lo)
             P[f"l{i}.ff2.w"] = _split(v[ff + "output_dense/kernel"].t(), lo)
+        # LayerNorm folded into the Dense that follows it (QKV of layers >= 1 and every FFN1; include/w2v2.h ln_fold_*):
+        #   LN(x) W + b = rstd (x (gamma o W)) - rstd mean colsum(gamma o W) + (beta W + b)
+        self._fold = (self.precision != "bf16x3" and cfg.hidden_size % 64 == 0 and cfg.num_layers > 0
+                      and os.environ.get("W2V2_LN_FOLD", "1") != "0")
+        if self._fold:
+            pre = cfg.attention_norm_type == "prenorm"
+            for i in range(cfg.num_layers):
+                lb = f"wav2vec2/encoder/layers/{i}/"
+                ln_qkv = (lb + "layer_norm/") if pre else (f"wav2vec2/encoder/layers/{i - 1}/final_layer_norm/" if i > 0 else None)
+                ln_ff1 = lb + ("final_layer_norm/" if pre else "layer_norm/")
+                base = lb + "attention/"
+                wqkv = torch.cat([v[base + "q_proj/kernel"].t() * scale, v[base + "k_proj/kernel"].t(), v[base + "v_proj/kernel"].t()], 0)
+                for key, w, b, ln in (("qkv", wqkv, P[f"l{i}.qkv.b"], ln_qkv),
+                                      ("ff1", v[lb + "feed_forward/intermediate_dense/kernel"].t(),
+                                       v[lb + "feed_forward/intermediate_dense/bias"], ln_ff1)):
+                    if ln is None or (key == "qkv" and i == 0):
+                        continue               # layer 0's QKV reads the output of a real LayerNorm pass (after the positional conv)
+                    g, bt = v[ln + "gamma"], v[ln + "beta"]
+                    wf = _split(w * g[None, :], lo)
+                    P[f"l{i}.{key}.wf"] = wf
+                    P[f"l{i}.{key}.cs"] = _effective_weight(wf, lo).sum(dim=1).contiguous()
+                    P[f"l{i}.{key}.bf"] = (b + w @ bt).contiguous()
         if self.with_head:
             w = v["lm_head/kernel"].t().contiguous()                                 # [V, d]
             V = w.shape[0]
@@ -454,6 +490,10 @@ class _B200Model:
         if training and (cfg.dropout or cfg.survival_prob < 1.0):
             raise NotImplementedError("training-mode forward with dropout / StochasticDepth needs the base architecture without an "
                                       "attention mask (see _training_forward); use dropout=0 and survival_prob=1 here")
+        if self.__dict__.get("_fold_stale"):
+            # a trainer updated the Dense kernels / LayerNorm gains in place: the gamma-folded copies are derived from both
+            self._packed = None
+            self._fold_stale = False
         last_f32, B, T = self._features(batch)
         P, A = self._packed, self._arena
         md = self._modes
@@ -508,43 +548,77 @@ class _B200Model:
         ctx = A.planes("ctx", (M, d), kind)
         mid = A.planes("mid", (M, cfg.intermediate_size), kind)
         x1_f32 = A.get("x1.f32", (M, d), f32) if pre else None
-        H, dh, ffn = cfg.num_heads, cfg.head_size, cfg.intermediate_size
-        if not pre and cfg.num_layers == 0:
+        H, dh, ffn, nl = cfg.num_heads, cfg.head_size, cfg.intermediate_size, cfg.num_layers
+        approx = bool(cfg.is_gelu_approx)
+        qfmt = _KINDS[md.qkv][2]
+        if not pre and nl == 0:
             ops.ln_rows(y, res_ln[1], res_ln[2], eps, M, d, out_f32=xs_f32)
-        for i in range(cfg.num_layers):
+        # LayerNorm fold (see _pack): the residual GEMMs also write the operand planes `ys` of their (un-normalised) fp32 sum and its
+        # per-row partial (sum, sum of squares); QKV / FFN1 consume `ys` with gamma folded into their weights and apply mean / rstd
+        # in their epilogue - no stand-alone LayerNorm pass between the positional conv and the final encoder output.
+        fold = bool(getattr(self, "_fold", False))
+        ys = A.planes("ys", (M, d), kind) if fold else None
+        parts = [A.get(f"ln.parts.{k}", (M, d // 64, 2), f32) for k in "ab"] if fold else None
+        cur, nparts = None, 0                   # partial statistics of the current stream tensor (None: a real LayerNorm ran)
+
+        def next_parts():
+            nonlocal nparts
+            nparts += 1
+            return parts[nparts & 1]
+        for i in range(nl):
             lb = f"{enc}layers/{i}/"
             g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
             g2, b2 = v[lb + "final_layer_norm/gamma"], v[lb + "final_layer_norm/beta"]
-            if pre:
-                ops.ln_rows(xs_f32, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
-            ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi,
-                     out_lo=qkv.lo, passes=passes, out_format=_KINDS[md.qkv][2])
+            last = i == nl - 1
+            # ---- q / k / v projection (encoder.py:24-31) on LN(stream)
+            if cur is not None:
+                ops.gemm(ys, P[f"l{i}.qkv.wf"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.bf"], out_hi=qkv.hi,
+                         out_lo=qkv.lo, passes=passes, out_format=qfmt, ln_fold=(cur, P[f"l{i}.qkv.cs"]), ln_eps=eps)
+            else:
+                if pre:
+                    ops.ln_rows(xs_f32, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
+                ops.gemm(xs, P[f"l{i}.qkv.w"], K=d, N=3 * d, rows_per_batch=M, bias=P[f"l{i}.qkv.b"], out_hi=qkv.hi,
+                         out_lo=qkv.lo, passes=passes, out_format=qfmt)
             ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, md.attn, out_format=ofmt)
-            if pre:
-                # x1 = x + out_proj(ctx)
-                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
-                         residual=xs_f32, out_f32=x1_f32, passes=passes)
-                ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
+            # ---- output projection + residual (encoder.py:117-121)
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=next_parts()) if fold else {}
+            ob = v[lb + "attention/out_proj/bias"]
+            if pre:     # x1 = x + out_proj(ctx)
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=xs_f32, out_f32=x1_f32,
+                         passes=passes, **po)
+            else:       # y <- LN(y) + out_proj(ctx), the LayerNorm of the residual recomputed from its row statistics
+                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=y, res_ln=res_ln, out_f32=y,
+                         passes=passes, ln_eps=eps, **po)
+            # ---- feed forward (encoder.py:126-131) on LN(x1)
+            if fold:
+                cur = po["row_stats_out"]
+                ops.gemm(ys, P[f"l{i}.ff1.wf"], K=d, N=ffn, rows_per_batch=M, bias=P[f"l{i}.ff1.bf"], gelu=True, gelu_approx=approx,
+                         out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt, ln_fold=(cur, P[f"l{i}.ff1.cs"]), ln_eps=eps)
+                res_ln = (cur, g1, b1)
             else:
-                # y <- LN(y) + out_proj(ctx);  x1 = LN1(y) as bf16 operand + row statistics
-                ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
-                         residual=y, res_ln=res_ln, out_f32=y, passes=passes)
-                ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st, out_format=ofmt)
-                res_ln = (st, g1, b1)
-            ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M,
-                     bias=v[lb + "feed_forward/intermediate_dense/bias"], gelu=True, gelu_approx=bool(cfg.is_gelu_approx),
-                     out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt)
+                if pre:
+                    ops.ln_rows(x1_f32, g2, b2, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, out_format=ofmt)
+                else:   # x1 = LN1(y) as GEMM operand + row statistics
+                    ops.ln_rows(y, g1, b1, eps, M, d, out_hi=xs.hi, out_lo=xs.lo, stats=st, out_format=ofmt)
+                    res_ln = (st, g1, b1)
+                ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
+                         gelu=True, gelu_approx=approx, out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt)
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=next_parts()) if (fold and not last) else {}
+            fb = v[lb + "feed_forward/output_dense/bias"]
             if pre:
-                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
-                         bias=v[lb + "feed_forward/output_dense/bias"], residual=x1_f32, out_f32=xs_f32, passes=passes)
-            else:
-                # y <- LN1(y) + FFN(x1);  the last layer's LayerNorm also writes the fp32 hidden states
-                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M,
-                         bias=v[lb + "feed_forward/output_dense/bias"], residual=y, res_ln=res_ln, out_f32=y, passes=passes)
-                last = i == cfg.num_layers - 1
-                ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32 if last else None, out_hi=xs.hi, out_lo=xs.lo,
-                            stats=None if last else st, out_format=ofmt)
-                res_ln = (st, g2, b2)
+                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=x1_f32, out_f32=xs_f32,
+                         passes=passes, **po)
+            else:       # y <- LN1(y) + FFN(x1)
+                ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=y, res_ln=res_ln, out_f32=y,
+                         passes=passes, ln_eps=eps, **po)
+            cur = po.get("row_stats_out")
+            if not pre:
+                if cur is not None:
+                    res_ln = (cur, g2, b2)
+                else:   # a real LayerNorm pass: the unfolded path, and always after the last layer (fp32 hidden states)
+                    ops.ln_rows(y, g2, b2, eps, M, d, out_f32=xs_f32 if last else None, out_hi=xs.hi, out_lo=xs.lo,
+                                stats=None if last else st, out_format=ofmt)
+                    res_ln = (st, g2, b2)
         if pre:
             out_f32 = A.get("enc.out", (M, d), f32)
             ops.ln_rows(xs_f32, v[enc + "layer_norm/gamma"], v[enc + "layer_norm/beta"], eps, M, d, out_f32=out_f32,
@@ -565,6 +639,8 @@ class _B200Model:
     def _graphed(self, fn, batch, attention_mask):
         """Run ``fn(static_batch, static_mask)`` through a cached CUDA graph keyed by the input shapes."""
         key = (tuple(batch.shape), attention_mask is not None, fn.__name__)
+        if self.__dict__.get("_fold_stale"):
+            self._packed, self._fold_stale = None, False # derived (LayerNorm-folded) weights are out of date: re-pack, drop the graphs
         if self._packed is None:
             self._pack()                                 # before the lookup: packing drops the graphs of the old weights
         entry = self._graphs.get(key)

@@ -61,10 +61,14 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          a_batch_stride: Optional[int] = None, bias=None, scale=None, bias_batch_stride=0, residual=None,
          row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
-         res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None, out_format=0):
+         res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None, out_format=0,
+         ln_fold=None, row_stats_out=None, ln_eps=1e-5):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
     ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
     ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride].
+    ``res_ln[0]`` may also be the partial-sum tensor [rows, parts, 2] that ``row_stats_out`` of an earlier GEMM wrote.
+    ``ln_fold = (stats [rows, parts, 2], colsum [N])``: LayerNorm folded into this GEMM (``a`` = un-normalised input, ``w`` packed
+    as gamma o W, ``bias`` = beta W + b).  ``row_stats_out`` [rows, N/64, 2]: (sum, sum of squares) of the fp32 result.
     ``gelu_approx``: the GELU is tf.nn.gelu(approximate=True) (config.is_gelu_approx).  ``row_replace = (mask uint8 [rows],
     value fp32 [N])``: SpecAugment row replacement; ``drop = (rate, seed, site)``: dropout before the residual add."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
@@ -91,9 +95,18 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     args.scale, args.bias_batch_stride = _ptr(scale), bias_batch_stride
     args.out_f32, args.out_hi, args.out_lo = _ptr(out_f32), _ptr(out_hi), _ptr(out_lo)
     args.out_format = out_format
+    args.ln_eps = float(ln_eps)
     if res_ln is not None:
         _need_cuda(*res_ln)
         args.res_ln_stats, args.res_ln_gamma, args.res_ln_beta = (_ptr(t) for t in res_ln)
+        args.res_ln_parts = res_ln[0].shape[1] if res_ln[0].dim() == 3 else 0
+    if ln_fold is not None:
+        _need_cuda(*ln_fold)
+        args.ln_fold_stats, args.ln_fold_parts = _ptr(ln_fold[0]), ln_fold[0].shape[1]
+        args.scale = _ptr(ln_fold[1])
+    if row_stats_out is not None:
+        _need_cuda(row_stats_out)
+        args.row_stats_out = _ptr(row_stats_out)
     _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
 
 

@@ -265,6 +265,7 @@ class Stage2Trainer:
         if getattr(self, "_pack_tables", None) is None or self._pack_refs[0] is not model._packed or self._pack_refs[1] is not self._wt:
             self._build_pack_jobs()
         ops.pack_weights(*self._pack_tables)
+        model._fold_stale = True                      # the LayerNorm-folded inference copies are re-derived at the next eval call
         cfg, v = model.config, model.variables
         pc = "wav2vec2/encoder/pos_conv_embed/conv/"
         wv, wg = v[pc + "weight_v"], v[pc + "weight_g"]

@@ -118,7 +118,17 @@ typedef struct w2v2_gemm_args {
   uint32_t drop_site;
   uint64_t drop_seed;
   int32_t out_format;              /* layout of out_hi / out_lo: W2V2_OUT_BF16 (0), W2V2_OUT_FP16 (1), W2V2_OUT_FP16F8 (2) */
-  int32_t reserved0;
+  /* LayerNorm folded into the Dense that follows it (encoder.py:116-132: LN -> q/k/v Dense, LN -> intermediate Dense):
+   *   LN(x) W + b = rstd (x (gamma o W)) - rstd mean colsum(gamma o W) + (beta W + b)
+   * The A operand is then the UN-normalised x, W is packed as gamma o W, `bias` = beta W + b, `scale` = colsum(gamma o W) [N]
+   * (NOT a multiplier in this mode), and the per-row (mean, rstd) come from ln_fold_stats: [rows][ln_fold_parts][2] partial
+   * (sum, sum of squares) pairs over the K input columns, written by the producer of x through row_stats_out. */
+  int32_t ln_fold_parts;           /* 0 = no fold */
+  const float* ln_fold_stats;
+  float ln_eps;                    /* epsilon of the folded LayerNorm and of res_ln_* when given as partial sums */
+  int32_t res_ln_parts;            /* 0: res_ln_stats holds (mean, rstd) per row; > 0: that many partial (sum, sum of squares) pairs per row */
+  float* row_stats_out;            /* optional [rows][N / 64][2]: (sum, sum of squares) of the fp32 result per 64-column group
+                                      (needs out_f32 semantics: the statistics are those of the value written to out_f32; N % 64 == 0) */
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);

@@ -73,21 +73,23 @@ def terms(a, b):
         # the recipe as the kernels would implement it: operands pre-scaled (activation x 2^4, weight x 2^11; both x 2^4 when the
         # "weight" is an activation too), fp16 main product, e4m3 cross terms at 2^+-6, everything at scale 2^15 (2^8) in ONE
         # fp32 accumulator, un-scaled by the epilogue
-        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv", "pos") else 2.0 ** 4)
+        sa, sb = 2.0 ** 4, (2.0 ** 4 if SITE["cur"] in ("qk", "pv") else 2.0 ** 11)
         a2, b2 = (a * sa).clamp(-65504, 65504), (b * sb).clamp(-65504, 65504)
         ah, bh = _r(a2, torch.float16), _r(b2, torch.float16)
         al, bl = a2 - ah, b2 - bh
         s = 1.0 / (sa * sb)
         return [(ah, bh, s), (_e4m3(al * 64.0), _e4m3(bh / 64.0), s), (_e4m3(ah / 64.0), _e4m3(bl * 64.0), s)]
     if m == "f16s":
-        sa, sb = 2.0 ** 4, (2.0 ** 11 if SITE["cur"] in ("dense", "conv", "pos") else 2.0 ** 4)
+        sa, sb = 2.0 ** 4, (2.0 ** 4 if SITE["cur"] in ("qk", "pv") else 2.0 ** 11)
         a2, b2 = (a * sa).clamp(-65504, 65504), (b * sb).clamp(-65504, 65504)
         return [(_r(a2, torch.float16), _r(b2, torch.float16), 1.0 / (sa * sb))]
     raise ValueError(m)
 
 
 def q_dense(x, kernel, bias):
-    SITE["cur"] = "dense"
+    # finer site names for the Dense layers, from their shapes: proj 512->d, qkv/out d->d, ffn1 d->4d, ffn2 4d->d, lm d->vocab
+    kin, kout = kernel.shape
+    SITE["cur"] = SITE.get("force") or ("lm" if kout < 64 else "proj" if kin == 512 else "ffn1" if kout > kin else "ffn2" if kin > kout else "dd")
     return sum(s * (a @ b) for a, b, s in terms(x, kernel)) + bias
 
 
@@ -108,9 +110,11 @@ def q_attention(x, p, cfg, base, additive_mask=None, drop=None, layer=0):
 
     def split(t):
         return t.reshape(B, T, H, dh).permute(0, 2, 1, 3)
+    SITE["force"] = "qkv"
     q = split(q_dense(x, p[base + "q_proj/kernel"], p[base + "q_proj/bias"])) * dh ** (-0.5)
     k = split(q_dense(x, p[base + "k_proj/kernel"], p[base + "k_proj/bias"]))
     v = split(q_dense(x, p[base + "v_proj/kernel"], p[base + "v_proj/bias"]))
+    SITE["force"] = None
     SITE["cur"] = "qk"
     scores = sum(s * (a @ b.transpose(-1, -2)) for a, b, s in terms(q, k))
     if additive_mask is not None:
@@ -119,7 +123,10 @@ def q_attention(x, p, cfg, base, additive_mask=None, drop=None, layer=0):
     SITE["cur"] = "pv"
     ctx = sum(s * (a @ b) for a, b, s in terms(pr, v))
     ctx = ctx.permute(0, 2, 1, 3).reshape(B, T, D)
-    return q_dense(ctx, p[base + "out_proj/kernel"], p[base + "out_proj/bias"])
+    SITE["force"] = "out"
+    y = q_dense(ctx, p[base + "out_proj/kernel"], p[base + "out_proj/bias"])
+    SITE["force"] = None
+    return y
 
 
 def main():

@@ -261,3 +261,26 @@ def test_training_call_applies_spec_augment_in_the_projection_epilogue():
     ref = O.wav2vec2_model(x, params, cfg, attention_mask=am, spec_mask=torch.from_numpy(mask).bool())
     assert mask.sum() > 0
     assert (got - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("arch", ["base", "robust"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16", "fp16f8"])
+def test_layernorm_fold_equals_the_unfolded_path(arch, precision, monkeypatch):
+    """The LayerNorm fold (gamma into the next Dense, mean / rstd in its epilogue, no stand-alone LayerNorm pass) against the
+    same model with W2V2_LN_FOLD=0, and against the oracle: the fold must not cost accuracy in any precision mode."""
+    cls = Wav2Vec2Config if arch == "base" else RobustWav2Vec2Config
+    cfg = cls(num_layers=3)
+    params = O.random_params(cfg, seed=2)
+    # LayerNorm inputs with a mean well away from zero in some rows: the fold subtracts rstd * mean * colsum explicitly
+    x = torch.randn(2, 20000, generator=torch.Generator().manual_seed(4)) + 0.3
+    ref = O.wav2vec2_for_ctc(x, params, cfg)
+    errs = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("W2V2_LN_FOLD", fold)
+        m = Wav2Vec2ForCTC(cfg, precision=precision)
+        m.set_variables(params)
+        errs[fold] = (m(x.cuda()).cpu() - ref).abs().max().item()
+        assert m._fold == (fold == "1")
+    print(f"{arch}/{precision}: logits max-abs err folded {errs['1']:.3e}, unfolded {errs['0']:.3e}")
+    tol = {"bf16": 1e-1, "fp16": 6e-3, "fp16f8": 1e-3}[precision]
+    assert errs["1"] < tol and errs["1"] < 2.0 * errs["0"] + 1e-4
