@@ -72,7 +72,7 @@ template <int EPI, int PASSES>
 __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const Gemm2OutMaps& om, uint32_t taddr, int cg,
                                                     int n0, int t_warp0, int b, int rows_valid, bool zero_row,
                                                     const float* sb, uint8_t* stage, uint64_t* res_bar,
-                                                    uint32_t tmem_empty_cluster_addr) {
+                                                    uint32_t tmem_empty_cluster_addr, float4 rowc) {
   constexpr int BLOCK_N = GEMM2_BLOCK_N;
   const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
   const bool f_fast = (EPI >= 0) ? bool(EPI & EPI_FASTGELU) : (p.gelu == 2);  // tanh-form GELU: single-pass mode
@@ -103,19 +103,8 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   if (rows_valid <= 0 || n >= p.N) return;
   const size_t orow0 = (size_t)b * p.rows_per_batch + t_warp0;
   const bool f_ln = f_res && p.ln_stats != nullptr;
-  float ln_mean = 0.0f, ln_rstd = 0.0f;
-  if (f_ln && lane < rows_valid) {
-    const float2 st = (p.res_ln_parts > 0) ? mean_rstd_from_parts(p.ln_stats, orow0 + lane, p.res_ln_parts, 1.0f / (float)p.N, p.ln_eps)
-                                           : __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow0 + lane);
-    ln_mean = st.x;
-    ln_rstd = st.y;
-  }
-  float fold_rs = p.acc_scale, fold_nm = 0.0f;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
-  if (f_fold && lane < rows_valid) {
-    const float2 st = mean_rstd_from_parts(p.ln_fold_stats, orow0 + lane, p.ln_fold_parts, p.ln_fold_inv_dim, p.ln_eps);
-    fold_rs = st.y * p.acc_scale;
-    fold_nm = -st.y * st.x;
-  }
+  const float ln_mean = rowc.x, ln_rstd = rowc.y;
+  const float fold_rs = rowc.z, fold_nm = rowc.w;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
 
   if constexpr (Gemm2Smem<EPI>::TMA_RES) {
     // out = acc + bias + residual, fp32.  Slab q (16 columns, 64-byte rows) of the residual was TMA-loaded into block
@@ -170,7 +159,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
           s2 = fmaf(x, x, s2);
         }
       }
-      reinterpret_cast<float2*>(p.row_stats_out)[(orow0 + lane) * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
+      reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(n >> 6) * ((size_t)p.batch * p.rows_per_batch) + orow0 + lane] = make_float2(s1, s2);
     }
     if constexpr ((EPI & EPI_HI) != 0) {
       // operand planes of the SUM (the un-normalised LayerNorm input the next GEMM consumes): the two staging blocks are free
@@ -324,7 +313,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         s2 = fmaf(x, x, s2);
       }
     }
-    reinterpret_cast<float2*>(p.row_stats_out)[(orow0 + lane) * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
+    reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(n >> 6) * ((size_t)p.batch * p.rows_per_batch) + orow0 + lane] = make_float2(s1, s2);
   }
 
   // ---- pass B: outputs, one 64-byte column slab per bulk store
@@ -591,11 +580,13 @@ gemm_bf16_2sm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_co
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 32));
       }
+      // per-row LayerNorm constants (residual LayerNorm / folded LayerNorm): their loads fly while this tile's MMAs run
+      const float4 rowc = epilogue_row_constants<EPI>(p, (size_t)b * p.rows_per_batch + t_warp0 + lane, lane < rows_valid);
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
       gemm2_epilogue_warp<EPI, PASSES>(p, om, taddr, cg, n0, t_warp0, b, rows_valid, zero_row, sb, stage, res_bar,
-                               mapa_cluster(smem_u32(&tmem_empty[acc]), 0));
+                               mapa_cluster(smem_u32(&tmem_empty[acc]), 0), rowc);
       park_bias(acc ^ 1, next_bias);
       asm volatile("bar.sync 1, 512;" ::: "memory");   // every warp is done with this tile's slice; the next one is visible
       if (++acc == ACC_STAGES) {

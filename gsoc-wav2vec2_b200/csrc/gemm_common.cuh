@@ -49,11 +49,11 @@ struct GemmParams {
   DropSpec drop;               // dropout on the activation (after bias / GELU, before the residual); thr16 == 0: off
   // LayerNorm folded into this GEMM (w2v2.h ln_fold_*): out = rstd_r * acc - rstd_r * mean_r * colsum[n] + bias[n]; (mean, rstd) of
   // row r come from partial (sum, sum of squares) pairs over 64-column groups of the K input columns
-  const float* ln_fold_stats;  // [rows][ln_fold_parts][2] or null
+  const float* ln_fold_stats;  // [ln_fold_parts][rows][2] or null
   int ln_fold_parts;
   float ln_fold_inv_dim;       // 1 / K
   float ln_eps;
-  float* row_stats_out;        // optional [rows][N / 64][2]: (sum, sum of squares) of the fp32 output per 64-column group
+  float* row_stats_out;        // optional [N / 64][rows][2]: (sum, sum of squares) of the fp32 output per 64-column group
   int res_ln_parts;            // 0: ln_stats holds (mean, rstd) per row; > 0: partial sums over N columns in that many groups
   int fp16;               // 1: the 16-bit operand planes are fp16 (idesc format 0) instead of bf16
   float acc_scale;        // accumulator -> value: 1, or 2^-15 for the scaled fp16 operand planes (ACT_SCALE * WGT_SCALE)
@@ -64,17 +64,50 @@ struct GemmParams {
 };
 
 // (mean, rstd) of one row from its partial sums: `parts` (sum, sum of squares) pairs, added in index order (deterministic)
-__device__ __forceinline__ float2 mean_rstd_from_parts(const float* stats, size_t row, int parts, float inv_dim, float eps) {
-  const float2* p2 = reinterpret_cast<const float2*>(stats) + row * parts;
+// Layout [parts][rows][2]: the 32 rows of a warp are contiguous, so each of the `parts` loads is two full lines per warp.
+// NOTE the hot path does not come here: 12 predicated loads + their address arithmetic per thread and tile cost the FFN1 epilogue
+// ~5 extra instructions per element (ncu: 42 M vs 30 M warp instructions, 57 % vs 75 % tensor-pipe activity), so the model reduces
+// the partial sums to (mean, rstd) once per row with w2v2_row_stats_finalize and the GEMMs read ONE float2 per row.
+__device__ __forceinline__ float2 mean_rstd_from_parts(const float* stats, size_t row, size_t rows_total, int parts, float inv_dim,
+                                                       float eps) {
+  // all (<= 16) loads are issued before the first add: a rolled load -> add loop serialises `parts` L2 latencies per tile
+  const float2* p2 = reinterpret_cast<const float2*>(stats) + row;
+  float2 v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (i < parts) ? __ldg(p2 + (size_t)i * rows_total) : make_float2(0.0f, 0.0f);
   float s1 = 0.0f, s2 = 0.0f;
-  for (int i = 0; i < parts; ++i) {
-    const float2 v = __ldg(p2 + i);
-    s1 += v.x;
-    s2 += v.y;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    s1 += v[i].x;
+    s2 += v[i].y;
   }
   const float mean = s1 * inv_dim;
   const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.0f);
   return make_float2(mean, rsqrtf(var + eps));
+}
+
+// Per-row LayerNorm constants of one output row, fetched BEFORE the epilogue waits for its accumulator (their load latency - up
+// to 2 x 16 scattered partial sums per thread - then hides behind the MMAs of the tile): x = mean, y = rstd of the residual's
+// LayerNorm; z = rstd * acc_scale, w = -rstd * mean of the LayerNorm folded into this GEMM (z = acc_scale, w = 0 without fold).
+template <int EPI>
+__device__ __forceinline__ float4 epilogue_row_constants(const GemmParams& p, size_t orow, bool row_ok) {
+  const bool f_res = (EPI >= 0) ? bool(EPI & EPI_RESID) : (p.residual != nullptr);
+  const bool f_fold = (EPI >= 0) ? bool(EPI & EPI_LNFOLD) : (p.ln_fold_stats != nullptr);
+  float4 c = make_float4(0.0f, 0.0f, p.acc_scale, 0.0f);
+  const size_t rows_total = (size_t)p.batch * p.rows_per_batch;
+  if (f_res && p.ln_stats != nullptr && row_ok) {
+    const float2 st = (p.res_ln_parts > 0) ? mean_rstd_from_parts(p.ln_stats, orow, rows_total, p.res_ln_parts, 1.0f / (float)p.N, p.ln_eps)
+                                           : __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
+    c.x = st.x;
+    c.y = st.y;
+  }
+  if (f_fold && row_ok) {
+    const float2 st = (p.ln_fold_parts > 0) ? mean_rstd_from_parts(p.ln_fold_stats, orow, rows_total, p.ln_fold_parts, p.ln_fold_inv_dim, p.ln_eps)
+                                            : __ldg(reinterpret_cast<const float2*>(p.ln_fold_stats) + orow);
+    c.z = st.y * p.acc_scale;
+    c.w = -st.y * st.x;
+  }
+  return c;
 }
 
 // residual term "LayerNorm(r)" with the statistics written by w2v2_ln_rows_stats: the SAME expression as ln_rows_kernel, so
@@ -108,7 +141,7 @@ __device__ __forceinline__ void epilogue_dropout16(const DropSpec& d, size_t e0,
 template <int BLOCK_N, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t taddr, int grp, int n0, size_t orow,
                                                    int rows_valid, bool zero_row, const float* sb, uint8_t* stage,
-                                                   uint32_t tmem_empty_cluster_addr) {
+                                                   uint32_t tmem_empty_cluster_addr, float4 rowc) {
   // compile-time epilogue recipe (EPI >= 0) or run-time flags (EPI < 0)
   const bool f_gelu = (EPI >= 0) ? bool(EPI & EPI_GELU) : (p.gelu != 0);
   const bool f_fast = (EPI >= 0) ? bool(EPI & EPI_FASTGELU) : (p.gelu == 2);  // tanh-form GELU: single-pass mode
@@ -145,19 +178,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   const bool row_ok = lane < rows_valid;
   const size_t orow0 = orow - lane;  // first row of this warp's block
   const bool f_ln = f_res && p.ln_stats != nullptr;
-  float ln_mean = 0.0f, ln_rstd = 0.0f;
-  if (f_ln && row_ok) {
-    const float2 st = (p.res_ln_parts > 0) ? mean_rstd_from_parts(p.ln_stats, orow, p.res_ln_parts, 1.0f / (float)p.N, p.ln_eps)
-                                           : __ldg(reinterpret_cast<const float2*>(p.ln_stats) + orow);
-    ln_mean = st.x;
-    ln_rstd = st.y;
-  }
-  float fold_rs = p.acc_scale, fold_nm = 0.0f;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
-  if (f_fold && row_ok) {
-    const float2 st = mean_rstd_from_parts(p.ln_fold_stats, orow, p.ln_fold_parts, p.ln_fold_inv_dim, p.ln_eps);
-    fold_rs = st.y * p.acc_scale;
-    fold_nm = -st.y * st.x;
-  }
+  const float ln_mean = rowc.x, ln_rstd = rowc.y;
+  const float fold_rs = rowc.z, fold_nm = rowc.w;   // LayerNorm fold: v = acc * (rstd * acc_scale) + (-rstd * mean) * colsum + bias
 
   // staged 32 x 128 B block -> global, 8 lanes per row (PIECES = 8) or 4 lanes per row (PIECES = 4: 64-byte rows)
   auto flush = [&](uint8_t* gbase, size_t row_stride_bytes, int pieces, bool atomic = false) {
@@ -314,7 +336,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
           s2 = fmaf(x, x, s2);
         }
       }
-      reinterpret_cast<float2*>(p.row_stats_out)[orow * (p.N >> 6) + (n >> 6)] = make_float2(s1, s2);
+      reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(n >> 6) * ((size_t)p.batch * p.rows_per_batch) + orow] = make_float2(s1, s2);
     }
   }
 

@@ -227,11 +227,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __gri
       float* sb = s_bias + acc * BLOCK_N;
       gemm_epilogue_prepare<BLOCK_N, EPI_RUNTIME>(p, et, grp, n0, orow, row_ok, sb, b);
 
+      const float4 rowc = epilogue_row_constants<EPI_RUNTIME>(p, orow, row_ok);   // in flight while the MMAs of this tile run
+
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + acc * BLOCK_N;
 
-      gemm_epilogue_tile<BLOCK_N, EPI_RUNTIME>(p, taddr, grp, n0, orow, rows_valid, zero_row, sb, stage, smem_u32(&tmem_empty[acc]));
+      gemm_epilogue_tile<BLOCK_N, EPI_RUNTIME>(p, taddr, grp, n0, orow, rows_valid, zero_row, sb, stage, smem_u32(&tmem_empty[acc]), rowc);
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
@@ -302,7 +304,7 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.fp16 = mode_fp16(a->passes) ? 1 : 0;
   p.acc_scale = mode_fp16(a->passes) ? ACC_UNSCALE : 1.0f;
   p.out_format = a->out_format;
-  p.ln_fold_stats = a->ln_fold_parts > 0 ? a->ln_fold_stats : nullptr;
+  p.ln_fold_stats = a->ln_fold_stats;
   p.ln_fold_parts = a->ln_fold_parts;
   p.ln_fold_inv_dim = 1.0f / (float)a->K;
   p.ln_eps = a->ln_eps;
@@ -404,12 +406,14 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   W2V2_CHECK_ARG((np == 1 && !mode_f8(a->passes)) || (a->a_lo && a->w_lo), "multi-plane modes need the second planes");
   W2V2_CHECK_ARG(a->out_format >= 0 && a->out_format <= 2, "out_format must be 0 (bf16), 1 (fp16) or 2 (fp16 + e4m3 pairs)");
   W2V2_CHECK_ARG(a->out_format != 2 || (a->out_hi && a->out_lo && a->N % 64 == 0), "out_format 2 writes both planes and needs N % 64 == 0");
-  W2V2_CHECK_ARG(!mode_fp16(a->passes) || a->scale == nullptr || a->ln_fold_parts > 0, "per-column scale is not combined with the scaled fp16 planes");
-  W2V2_CHECK_ARG(a->ln_fold_parts == 0 || (a->ln_fold_parts > 0 && a->ln_fold_stats && a->scale && a->bias && a->bias_batch_stride == 0),
-                 "ln_fold_parts > 0 needs ln_fold_stats, scale (= colsum(gamma o W)) and bias (= beta W + b), shared by all batch entries");
+  W2V2_CHECK_ARG(!mode_fp16(a->passes) || a->scale == nullptr || a->ln_fold_stats != nullptr, "per-column scale is not combined with the scaled fp16 planes");
+  W2V2_CHECK_ARG(a->ln_fold_stats == nullptr || (a->scale && a->bias && a->bias_batch_stride == 0),
+                 "ln_fold_stats needs scale (= colsum(gamma o W)) and bias (= beta W + b), shared by all batch entries");
+  W2V2_CHECK_ARG(a->ln_fold_parts == 0 || a->ln_fold_stats != nullptr, "ln_fold_parts > 0 needs ln_fold_stats");
   W2V2_CHECK_ARG(a->row_stats_out == nullptr || (a->N % 64 == 0 && a->out_f32 != nullptr && !(a->flags & W2V2_GEMM_MN_MAJOR)),
                  "row_stats_out needs out_f32 and N % 64 == 0");
-  W2V2_CHECK_ARG(a->res_ln_parts >= 0 && a->ln_fold_parts >= 0, "partial-sum counts must be non-negative");
+  W2V2_CHECK_ARG(a->res_ln_parts >= 0 && a->ln_fold_parts >= 0 && a->res_ln_parts <= 16 && a->ln_fold_parts <= 16,
+                 "partial-sum counts must be in [0, 16] (LayerNorm widths up to 1024)");
   W2V2_CHECK_ARG(a->K > 0 && a->K % GEMM_BLOCK_K == 0, "K must be a positive multiple of 64");
   W2V2_CHECK_ARG(a->N > 0 && a->rows_per_batch > 0 && a->batch > 0, "N, rows_per_batch, batch must be positive");
   W2V2_CHECK_ARG(a->a_row_stride % 8 == 0 && a->a_batch_stride % 8 == 0, "A strides must be multiples of 8 elements (16 B)");

@@ -331,6 +331,26 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
+// ------------------------------------------------------------------------------------ LayerNorm statistics from partial sums
+// stats[r] = (mean, rstd) of row r from `parts` partial (sum, sum of squares) pairs laid out [parts][rows][2] - what the residual
+// GEMMs write through w2v2_gemm_args.row_stats_out (one pair per 64-column group).  Added in index order: deterministic.
+__global__ void __launch_bounds__(256)
+row_stats_finalize_kernel(const float2* __restrict__ parts, int nparts, int rows, float inv_dim, float eps, float2* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows) return;
+  float s1 = 0.0f, s2 = 0.0f;
+  for (int i = 0; i < nparts; ++i) {
+    const float2 v = __ldg(parts + (size_t)i * rows + r);
+    s1 += v.x;
+    s2 += v.y;
+  }
+  const float mean = s1 * inv_dim;
+  const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.0f);
+  stats[r] = make_float2(mean, rsqrtf(var + eps));
+}
+
 // ------------------------------------------------------------------------------------ utterance normalisation
 // Wav2Vec2Processor._normalize (processor.py:101-106): (x - mean) / sqrt(var + 1e-5), biased variance, per utterance over
 // its `len` real samples ("before padding", data_utils.py:233); samples past `len` are written as the padding value 0.
@@ -491,6 +511,16 @@ extern "C" int w2v2_ln_rows_ex(const float* x, const float* gamma, const float* 
     W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
   else
     W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
+  return 0;
+}
+
+extern "C" int w2v2_row_stats_finalize(const float* parts, int nparts, int64_t rows, int dim, float eps, float* stats,
+                                       void* stream) {
+  W2V2_CHECK_ARG(parts && stats && nparts > 0 && dim > 0, "null pointer or empty reduction");
+  if (rows <= 0) return 0;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  W2V2_CUDA(launch_pdl(row_stats_finalize_kernel, dim3((unsigned)((rows + 255) / 256)), dim3(256), 0, s, 0,
+                       reinterpret_cast<const float2*>(parts), nparts, (int)rows, 1.0f / (float)dim, eps, reinterpret_cast<float2*>(stats)));
   return 0;
 }
 

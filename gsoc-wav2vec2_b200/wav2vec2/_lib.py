@@ -76,6 +76,7 @@ SIGNATURES = {
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows_stats": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _P],
     "w2v2_ln_rows_ex": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _I, _P],
+    "w2v2_row_stats_finalize": [_P, _I, _L, _I, _F, _P, _P],
     "w2v2_normalize_utterances": [_P, _P, _I, _I, _F, _P, _P],
     "w2v2_split_bf16": [_P, _L, _P, _P, _P],
     "w2v2_attn_fwd": [_P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P],

@@ -558,13 +558,16 @@ class _B200Model:
         # in their epilogue - no stand-alone LayerNorm pass between the positional conv and the final encoder output.
         fold = bool(getattr(self, "_fold", False))
         ys = A.planes("ys", (M, d), kind) if fold else None
-        parts = [A.get(f"ln.parts.{k}", (M, d // 64, 2), f32) for k in "ab"] if fold else None
-        cur, nparts = None, 0                   # partial statistics of the current stream tensor (None: a real LayerNorm ran)
+        parts = A.get("ln.parts", (d // 64, M, 2), f32) if fold else None     # partial sums written by a residual GEMM ...
+        fstats = [A.get(f"ln.fstats.{k}", (M, 2), f32) for k in "ab"] if fold else None   # ... reduced to (mean, rstd) per row
+        cur, nstat = None, 0                    # (mean, rstd) of the current stream tensor (None: a real LayerNorm ran)
 
-        def next_parts():
-            nonlocal nparts
-            nparts += 1
-            return parts[nparts & 1]
+        def finalize():
+            # one tiny launch per LayerNorm instead of P predicated loads per thread and tile in the consuming GEMMs; two buffers
+            # because the residual GEMM that reads one set of statistics is followed by the launch that writes the next
+            nonlocal nstat
+            nstat += 1
+            return ops.row_stats_finalize(parts, d, eps, fstats[nstat & 1])
         for i in range(nl):
             lb = f"{enc}layers/{i}/"
             g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
@@ -581,7 +584,7 @@ class _B200Model:
                          out_lo=qkv.lo, passes=passes, out_format=qfmt)
             ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, md.attn, out_format=ofmt)
             # ---- output projection + residual (encoder.py:117-121)
-            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=next_parts()) if fold else {}
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts) if fold else {}
             ob = v[lb + "attention/out_proj/bias"]
             if pre:     # x1 = x + out_proj(ctx)
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=xs_f32, out_f32=x1_f32,
@@ -591,7 +594,7 @@ class _B200Model:
                          passes=passes, ln_eps=eps, **po)
             # ---- feed forward (encoder.py:126-131) on LN(x1)
             if fold:
-                cur = po["row_stats_out"]
+                cur = finalize()
                 ops.gemm(ys, P[f"l{i}.ff1.wf"], K=d, N=ffn, rows_per_batch=M, bias=P[f"l{i}.ff1.bf"], gelu=True, gelu_approx=approx,
                          out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt, ln_fold=(cur, P[f"l{i}.ff1.cs"]), ln_eps=eps)
                 res_ln = (cur, g1, b1)
@@ -603,7 +606,7 @@ class _B200Model:
                     res_ln = (st, g1, b1)
                 ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
                          gelu=True, gelu_approx=approx, out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt)
-            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=next_parts()) if (fold and not last) else {}
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts) if (fold and not last) else {}
             fb = v[lb + "feed_forward/output_dense/bias"]
             if pre:
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=x1_f32, out_f32=xs_f32,
@@ -611,7 +614,7 @@ class _B200Model:
             else:       # y <- LN1(y) + FFN(x1)
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=y, res_ln=res_ln, out_f32=y,
                          passes=passes, ln_eps=eps, **po)
-            cur = po.get("row_stats_out")
+            cur = finalize() if po else None
             if not pre:
                 if cur is not None:
                     res_ln = (cur, g2, b2)

@@ -66,9 +66,9 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
     ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
     ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride].
-    ``res_ln[0]`` may also be the partial-sum tensor [rows, parts, 2] that ``row_stats_out`` of an earlier GEMM wrote.
-    ``ln_fold = (stats [rows, parts, 2], colsum [N])``: LayerNorm folded into this GEMM (``a`` = un-normalised input, ``w`` packed
-    as gamma o W, ``bias`` = beta W + b).  ``row_stats_out`` [rows, N/64, 2]: (sum, sum of squares) of the fp32 result.
+    ``res_ln[0]`` may also be the partial-sum tensor [parts, rows, 2] that ``row_stats_out`` of an earlier GEMM wrote.
+    ``ln_fold = (stats [parts, rows, 2], colsum [N])``: LayerNorm folded into this GEMM (``a`` = un-normalised input, ``w`` packed
+    as gamma o W, ``bias`` = beta W + b).  ``row_stats_out`` [N/64, rows, 2]: (sum, sum of squares) of the fp32 result.
     ``gelu_approx``: the GELU is tf.nn.gelu(approximate=True) (config.is_gelu_approx).  ``row_replace = (mask uint8 [rows],
     value fp32 [N])``: SpecAugment row replacement; ``drop = (rate, seed, site)``: dropout before the residual add."""
     _need_cuda(a.hi, w.hi, bias, scale, residual, row_valid, out_f32, out_hi, out_lo)
@@ -99,10 +99,10 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     if res_ln is not None:
         _need_cuda(*res_ln)
         args.res_ln_stats, args.res_ln_gamma, args.res_ln_beta = (_ptr(t) for t in res_ln)
-        args.res_ln_parts = res_ln[0].shape[1] if res_ln[0].dim() == 3 else 0
+        args.res_ln_parts = res_ln[0].shape[0] if res_ln[0].dim() == 3 else 0
     if ln_fold is not None:
         _need_cuda(*ln_fold)
-        args.ln_fold_stats, args.ln_fold_parts = _ptr(ln_fold[0]), ln_fold[0].shape[1]
+        args.ln_fold_stats, args.ln_fold_parts = _ptr(ln_fold[0]), (ln_fold[0].shape[0] if ln_fold[0].dim() == 3 else 0)
         args.scale = _ptr(ln_fold[1])
     if row_stats_out is not None:
         _need_cuda(row_stats_out)
@@ -165,6 +165,15 @@ def ln_rows(x, gamma, beta, eps, rows, d, gelu=False, out_f32=None, out_hi=None,
     _count(); _lib.check(_lib.load().w2v2_ln_rows_ex(_ptr(x), _ptr(gamma), _ptr(beta), float(eps), rows, d, int(gelu),
                                            _ptr(out_f32), _ptr(out_hi), _ptr(out_lo), _ptr(stats), out_format, _stream()),
                          "w2v2_ln_rows")
+
+
+def row_stats_finalize(parts, dim, eps, stats):
+    """parts [P, rows, 2] partial (sum, sum of squares) -> stats [rows, 2] = (mean, rstd) of a LayerNorm over ``dim`` columns."""
+    _need_cuda(parts, stats)
+    P, rows, _ = parts.shape
+    _count(); _lib.check(_lib.load().w2v2_row_stats_finalize(_ptr(parts), P, rows, int(dim), float(eps), _ptr(stats), _stream()),
+                         "w2v2_row_stats_finalize")
+    return stats
 
 
 def attn_fwd(qkv: Pair, B, T, H, dh, kv_len, out: Pair, passes=1, out_format=None):

@@ -121,13 +121,13 @@ typedef struct w2v2_gemm_args {
   /* LayerNorm folded into the Dense that follows it (encoder.py:116-132: LN -> q/k/v Dense, LN -> intermediate Dense):
    *   LN(x) W + b = rstd (x (gamma o W)) - rstd mean colsum(gamma o W) + (beta W + b)
    * The A operand is then the UN-normalised x, W is packed as gamma o W, `bias` = beta W + b, `scale` = colsum(gamma o W) [N]
-   * (NOT a multiplier in this mode), and the per-row (mean, rstd) come from ln_fold_stats: [rows][ln_fold_parts][2] partial
+   * (NOT a multiplier in this mode), and the per-row (mean, rstd) come from ln_fold_stats: [ln_fold_parts][rows][2] partial
    * (sum, sum of squares) pairs over the K input columns, written by the producer of x through row_stats_out. */
-  int32_t ln_fold_parts;           /* 0 = no fold */
-  const float* ln_fold_stats;
+  int32_t ln_fold_parts;           /* 0: ln_fold_stats holds (mean, rstd) per row [rows][2]; > 0: partial sums [parts][rows][2] */
+  const float* ln_fold_stats;      /* NULL = no fold */
   float ln_eps;                    /* epsilon of the folded LayerNorm and of res_ln_* when given as partial sums */
-  int32_t res_ln_parts;            /* 0: res_ln_stats holds (mean, rstd) per row; > 0: that many partial (sum, sum of squares) pairs per row */
-  float* row_stats_out;            /* optional [rows][N / 64][2]: (sum, sum of squares) of the fp32 result per 64-column group
+  int32_t res_ln_parts;            /* 0: res_ln_stats holds (mean, rstd) per row; > 0: that many partial (sum, sum of squares) pairs per row, laid out [parts][rows][2] */
+  float* row_stats_out;            /* optional [N / 64][rows][2]: (sum, sum of squares) of the fp32 result per 64-column group
                                       (needs out_f32 semantics: the statistics are those of the value written to out_f32; N % 64 == 0) */
 } w2v2_gemm_args;
 
@@ -178,6 +178,11 @@ int w2v2_ln_rows_stats(const float* x, const float* gamma, const float* beta, fl
 /* same, with the layout of out_hi / out_lo chosen by out_format (W2V2_OUT_BF16 / W2V2_OUT_FP16 / W2V2_OUT_FP16F8) */
 int w2v2_ln_rows_ex(const float* x, const float* gamma, const float* beta, float eps, int64_t rows, int d, int gelu,
                     float* out_f32, void* out_hi, void* out_lo, float* stats, int out_format, void* stream);
+
+/* (mean, rstd) per row [rows][2] from the partial (sum, sum of squares) pairs [nparts][rows][2] that a residual GEMM wrote through
+ * w2v2_gemm_args.row_stats_out: the statistics of the LayerNorm (over `dim` columns, biased variance) that the NEXT GEMM folds
+ * (ln_fold_stats with ln_fold_parts == 0) and that the next residual add recomputes (res_ln_stats with res_ln_parts == 0). */
+int w2v2_row_stats_finalize(const float* parts, int nparts, int64_t rows, int dim, float eps, float* stats, void* stream);
 
 /* Wav2Vec2Processor._normalize (processor.py:101-106) on the device: per utterance (x - mean) / sqrt(var + eps) with the
  * biased variance over its lengths[b] real samples (NULL: all num_samples); the padded tail is written as 0
