@@ -273,13 +273,81 @@ def run_train(args, rank, world, local_rank):
     }))
 
 
+def run_sweep(args, rank, world, local_rank):
+    """--mode sweep: BASELINE.json configs[4] - wav2vec2-base forward over seq in {16000, 64000, 246000} x batch in {1, 8, 32, 128}
+    per GPU on `world` GPUs (batch sharded, no collective; one CUDA-graph replay per step), next to the CPU oracle port timed once
+    per sequence length on the host cores (rank 0, a 2-utterance sample).  One JSON line with the whole table."""
+    import torch.distributed as dist
+    from wav2vec2 import Wav2Vec2Config, Wav2Vec2ForCTC
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = Wav2Vec2Config()
+    model = Wav2Vec2ForCTC(cfg, precision=args.precision, device=dev).init_random(seed=0)
+    model.enable_cuda_graph(True)
+    W, K = max(args.warmup, 3), args.steps
+    cells, cpu = [], {}
+    for L in (16000, 64000, 246000):
+        if rank == 0 and not args.no_cpu_baseline:
+            from oracle import w2v2_oracle as O
+            torch.set_num_threads(os.cpu_count() or 1)
+            params = {k: v.detach().cpu() for k, v in model.variables.items()}
+            xs = torch.randn(2, L, generator=torch.Generator().manual_seed(0))
+            with torch.no_grad():
+                O.wav2vec2_for_ctc(xs[:1, :16000], params, cfg)
+                t0 = time.perf_counter()
+                O.wav2vec2_for_ctc(xs, params, cfg)
+                cpu[L] = 2 * L / SAMPLE_RATE / (time.perf_counter() - t0)
+        for B in (1, 8, 32, 128):
+            x = torch.randn(B, L, generator=torch.Generator().manual_seed(rank)).to(dev)
+            for _ in range(W):
+                model(x)
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(K):
+                model(x)
+            b.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item() / K
+            cells.append({"seq": L, "batch_per_gpu": B, "ms_per_step": round(ms, 4),
+                          "audio_s_per_s": round(world * B * L / SAMPLE_RATE / (ms / 1e3), 1)})
+            model._invalidate_graphs()      # one graph (and arena) per shape: drop it before the next cell
+            del x
+            torch.cuda.empty_cache()
+    if world > 1:
+        dist.destroy_process_group()
+    if rank == 0:
+        for c in cells:
+            if c["seq"] in cpu:
+                c["cpu_audio_s_per_s"] = round(cpu[c["seq"]], 1)
+                c["vs_cpu"] = round(c["audio_s_per_s"] / cpu[c["seq"]], 1)
+        print(json.dumps({"metric": "audio-sec/s", "unit": "audio-sec/s", "n_gpus": world, "steps": K, "warmup": W, "dtype": args.precision,
+                          "data": "synthetic", "scaling": "weak", "higher_is_better": True,
+                          "config": {"workload": "wav2vec2-base inference sweep seq x batch (BASELINE configs[4])",
+                                     "parallelism": f"dp{world} (batch sharded, no collective)"},
+                          "cpu_baseline": {"kind": "port", "cores": os.cpu_count() or 1, "unit": "audio-sec/s",
+                                           "sample": "oracle port (torch CPU fp32) on 2 utterances per sequence length, one run",
+                                           "value_by_seq": {str(k): round(v, 1) for k, v in cpu.items()}},
+                          "cells": cells}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"], help="infer: BASELINE configs[1] (default, the headline); train: configs[2], the stage-2 fine-tune step")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "sweep"],
+                    help="infer: BASELINE configs[1] (default, the headline); train: configs[2], the stage-2 fine-tune step; sweep: configs[4], seq x batch")
     ap.add_argument("--batch", type=int, default=None, help="utterances per GPU (default 32 for infer, 8 for train)")
     ap.add_argument("--seq", type=int, default=246000)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3", "fp16", "fp16f8"])
@@ -298,6 +366,9 @@ def main():
         return
     if args.mode == "train":
         run_train(args, rank, world, local_rank)
+        return
+    if args.mode == "sweep":
+        run_sweep(args, rank, world, local_rank)
         return
 
     import torch.distributed as dist
@@ -575,15 +646,16 @@ def train_subrecord(cfg_unused, dev, rank, world, L, W, K, barrier):
     lab[:, :24] = np.random.randint(1, 30, size=(Bt, 24))
     labels = torch.from_numpy(lab).to(dev)
     n0 = ops.LAUNCHES
-    losses = [trainer.step(x, labels).item()]
+    # next_speech: the frozen extractor's forward of the NEXT batch overlaps this step's gradient all-reduce
+    losses = [trainer.step(x, labels, next_speech=x).item()]
     per_step = ops.LAUNCHES - n0
     for _ in range(max(W, 3) - 1):
-        losses.append(trainer.step(x, labels).item())
+        losses.append(trainer.step(x, labels, next_speech=x).item())
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(K):
-        loss = trainer.step(x, labels)
+        loss = trainer.step(x, labels, next_speech=x)
     b.record()
     barrier()
     losses.append(loss.item())

@@ -254,11 +254,13 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
     for (int j = 0; j < 4; ++j) {
       const float4 bb = *reinterpret_cast<const float4*>(sb + c0 + 4 * j);
       if (f_fold) {
+        // packed fp32x2: 2 FFMA2 per column pair (same issue count as the plain bias add of the unfolded epilogue)
         const float4 cs = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 4 * j);
-        v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), fold_rs, fmaf(fold_nm, cs.x, bb.x));
-        v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), fold_rs, fmaf(fold_nm, cs.y, bb.y));
-        v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), fold_rs, fmaf(fold_nm, cs.z, bb.z));
-        v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), fold_rs, fmaf(fold_nm, cs.w, bb.w));
+        const uint64_t rs2 = pack2(fold_rs, fold_rs), nm2 = pack2(fold_nm, fold_nm);
+        unpack2(fma2(pack2(__uint_as_float(r[i][16 * hf + 4 * j + 0]), __uint_as_float(r[i][16 * hf + 4 * j + 1])), rs2,
+                     fma2(nm2, pack2(cs.x, cs.y), pack2(bb.x, bb.y))), v[4 * j + 0], v[4 * j + 1]);
+        unpack2(fma2(pack2(__uint_as_float(r[i][16 * hf + 4 * j + 2]), __uint_as_float(r[i][16 * hf + 4 * j + 3])), rs2,
+                     fma2(nm2, pack2(cs.z, cs.w), pack2(bb.z, bb.w))), v[4 * j + 2], v[4 * j + 3]);
       } else if (f_scale) {
         const float4 sc = *reinterpret_cast<const float4*>(sb + 2 * BLOCK_N + c0 + 4 * j);
         v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), sc.x, bb.x);
@@ -266,10 +268,12 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
         v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), sc.z, bb.z);
         v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), sc.w, bb.w);
       } else {
-        v[4 * j + 0] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 0]), p.acc_scale, bb.x);   // fmaf(a, 1, b) == a + b
-        v[4 * j + 1] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 1]), p.acc_scale, bb.y);
-        v[4 * j + 2] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 2]), p.acc_scale, bb.z);
-        v[4 * j + 3] = fmaf(__uint_as_float(r[i][16 * hf + 4 * j + 3]), p.acc_scale, bb.w);
+        // fmaf(a, 1, b) == a + b bit for bit; packed: one FFMA2 per column pair
+        const uint64_t as2 = pack2(p.acc_scale, p.acc_scale);
+        unpack2(fma2(pack2(__uint_as_float(r[i][16 * hf + 4 * j + 0]), __uint_as_float(r[i][16 * hf + 4 * j + 1])), as2, pack2(bb.x, bb.y)),
+                v[4 * j + 0], v[4 * j + 1]);
+        unpack2(fma2(pack2(__uint_as_float(r[i][16 * hf + 4 * j + 2]), __uint_as_float(r[i][16 * hf + 4 * j + 3])), as2, pack2(bb.z, bb.w)),
+                v[4 * j + 2], v[4 * j + 3]);
       }
     }
     if (f_gelu) {
@@ -298,8 +302,13 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = __ldg(p.row_value + n0 + c0 + j);   // N % 8 == 0 and n0 + c0 < N: a full 16-column slab unless N % 16
     }
+    if (p.row_valid != nullptr) {     // uniform: without a frame mask no per-element select is issued
 #pragma unroll
-    for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
+      for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = __float_as_uint(v[j]);
+    }
   }
 
   if (EPI < 0 && p.row_stats_out != nullptr && lane < rows_valid) {

@@ -46,7 +46,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 }
 
 template <int PASSES>
-__global__ void __launch_bounds__(PC_THREADS, 1)
+__global__ void __launch_bounds__(PC_THREADS, 2)   // two CTAs per SM when the smem budget allows: one's epilogue / window load overlaps the other's MMAs
 posconv_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
                const PosconvParams p) {
   constexpr int NPL = (PASSES == 3) ? 2 : 1;
@@ -251,7 +251,10 @@ static int launch_posconv(const w2v2_posconv_args* a, cudaStream_t stream) {
   p.w_lo = reinterpret_cast<const __nv_bfloat16*>(a->w_lo);
   const int a_bytes = NPL * cpc * PC_WIN_ROWS * 16;
   const int stage_bytes = NPL * PC_TAPS_PER_STAGE * cpg * cpg * 2;
-  int stages = (232448 - 1280 - a_bytes) / stage_bytes;
+  // prefer a footprint that lets TWO CTAs share an SM (113 KB each, TMEM 2 x 128 columns): the kernel has no intra-CTA overlap
+  // between its window load, its 128-tap MMA chain and its epilogue
+  int stages = (115712 - 1280 - a_bytes) / stage_bytes;
+  if (stages < 2) stages = (232448 - 1280 - a_bytes) / stage_bytes;
   if (stages > 4) stages = 4;
   if (stages < 1) return fail(-1, "%s: shared memory budget too small for %ld channels per group", __func__, cpg);
   p.stages = stages;

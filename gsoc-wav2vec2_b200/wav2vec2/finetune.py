@@ -59,8 +59,22 @@ def _run_stage(trainer, epochs, train_data, val_data, model, loss_fn, args, stag
         if lr_of_epoch is not None:
             trainer.lr = lr_of_epoch(epoch)                     # tf.keras.callbacks.LearningRateScheduler
         running, seen = 0.0, 0
-        for step, (speech, labels) in enumerate(train_data()):
-            loss = float(trainer.step(speech.to(model.device), labels.to(model.device)))
+        # one batch of look-ahead: stage 2 runs the NEXT batch's frozen-extractor forward while its gradient all-reduce is in flight
+        lookahead = isinstance(trainer, Stage2Trainer)
+        it = iter(train_data())
+        nxt = next(it, None)
+        if nxt is not None:
+            nxt = (nxt[0].to(model.device), nxt[1].to(model.device))
+        step = -1
+        while nxt is not None:
+            step += 1
+            (speech, labels), nxt = nxt, next(it, None)
+            if nxt is not None:
+                nxt = (nxt[0].to(model.device), nxt[1].to(model.device))
+            if lookahead:
+                loss = float(trainer.step(speech, labels, next_speech=None if nxt is None else nxt[0]))
+            else:
+                loss = float(trainer.step(speech, labels))
             running, seen = running + loss, seen + 1
             if log_fn is not None and step % args.logging_steps == 0:
                 log_fn({"stage": stage, "epoch": epoch, "step": step, "loss": running / seen, "lr": trainer.lr})

@@ -278,7 +278,11 @@ class Stage2Trainer:
     def _forward(self, speech, spec_mask=None, layer_keep=None):
         model = self.model
         cfg, v = model.config, model.variables
-        last_f32, B, T = model._features(speech)          # frozen extractor: the inference kernels, nothing kept
+        pre = self.__dict__.pop("_prefetched", None)
+        if pre is not None and pre[0] is speech:
+            last_f32, B, T = pre[1]                       # extractor output computed during the previous step's all-reduce
+        else:
+            last_f32, B, T = model._features(speech)      # frozen extractor: the inference kernels, nothing kept
         P, A = model._packed, model._arena
         passes = _PRECISIONS[model.precision]
         lo = passes == 3
@@ -513,10 +517,20 @@ class Stage2Trainer:
         return loss
 
     @torch.no_grad()
-    def step(self, speech, labels, spec_mask=None):
+    def step(self, speech, labels, spec_mask=None, next_speech=None):
+        """One optimisation step.  ``next_speech``: the NEXT step's waveform batch (already on the device).  The conv extractor is
+        frozen in stage 2 (main.py:236-237), so its forward does not depend on this step's update: it runs on the compute stream
+        WHILE the gradient all-reduce is in flight on NCCL's stream and is handed to the next ``step`` call (which must receive
+        the same tensor object) - the step's single collective is hidden behind ~40 % of the next forward."""
         loss = self.loss_and_gradients(speech, labels, spec_mask)
+        work = None
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)          # the step's single collective
+            work = dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, async_op=True)   # the step's single collective
+        if next_speech is not None:
+            nxt = next_speech.to(self.model.device)
+            self._prefetched = (next_speech, self.model._features(nxt))
+        if work is not None:
+            work.wait()                                   # the compute stream waits for the reduced gradients
         self.t += 1
         lr_t = self.lr * (1.0 - self.b2 ** self.t) ** 0.5 / (1.0 - self.b1 ** self.t)
         ops.adam(self.flat_w, self.flat_g, self.m, self.v, lr_t, self.b1, self.b2, self.eps)
