@@ -34,15 +34,6 @@ constexpr int AT_THREADS = 256; // warpgroup 0 (warps 0-3): softmax; warpgroup 1
 constexpr int AT_REGS_SOFTMAX = 208;  // setmaxnreg split (2 CTAs/SM): 128 x 208 + 128 x 40 registers per CTA
 constexpr int AT_REGS_CONTROL = 40;
 constexpr int AT_TILE = AT_BM * AT_DH * 2;  // 16 KB: one [128][64] bf16 tile
-#ifndef AT_POLY_EVERY
-#define AT_POLY_EVERY 4    // single-pass modes: every 4th pair of exponentials runs on the FMA pipe instead of MUFU (0 = off)
-#endif
-#ifndef AT_DEFAULT_POLY
-#define AT_DEFAULT_POLY 1
-#endif
-#ifndef AT_DEFAULT_KERNEL
-#define AT_DEFAULT_KERNEL 128   // 128: two CTAs per SM, 128-key chunks; 64: three CTAs per SM, 64-key chunks (single-pass modes)
-#endif
 #ifndef AT_P_IN_TMEM
 #define AT_P_IN_TMEM 1   // single-pass mode: keep the probabilities in TMEM (A operand of the PV MMAs) instead of smem
 #endif
@@ -76,8 +67,11 @@ struct AttnParams {
 // (Round 2 tried, on this kernel: pulling S out of TMEM piece by piece with the next piece's load in flight during the current
 //  piece's exponentials + per-piece lazy rescaling, and a degree-3 exp2 polynomial on the FMA pipe for every 4th pair.  Every
 //  combination measured 1.65 - 1.70 ms per step against 1.46 - 1.50 for this one-wait / one-max form: the per-piece bookkeeping costs
-//  more issue slots and dependent latency than the hidden TMEM load saves, and the kernel is not MUFU-throughput bound - see the
-//  three-CTA variant below for what does help.)
+//  more issue slots and dependent latency than the hidden TMEM load saves, and the kernel is not MUFU-throughput bound.  A third
+//  variant - 64-key chunks, P written over the S columns, 128 TMEM columns and 65 KB of smem per CTA so that THREE CTAs share an
+//  SM - measured 1.60 - 1.64 ms: Q K(j+1)^T can then only be issued after P V(j) has read P, and that serial chain per CTA costs
+//  more than the third resident CTA hides.  ncu of this kernel: MUFU pipe 55 %, tensor pipe 27 %, issue slots 36 %, ~660 warp
+//  instructions per softmax warp and chunk in ~4000 cycles - a dependent-latency problem of two warps per scheduler.)
 template <int PASSES, bool FP16>
 __global__ void __launch_bounds__(AT_THREADS, (PASSES == 1) ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant__ CUtensorMap tm_lo,
@@ -440,330 +434,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
-// =====================================================================================================
-// Single-pass variant with 64-key chunks and THREE CTAs per SM (W2V2_ATTN_KERNEL=64).
-// At head size 64 the kernel above is bound by the exponentials (16 MUFU.EX2 per clock and SM = 1024 cycles per
-// 128 x 128 chunk against 512 cycles of MMAs), yet ncu shows the MUFU pipe only ~55 % busy: with two CTAs per SM each
-// scheduler has two softmax warps, and whenever both sit in a non-exponential phase (TMEM load, max, pack, store,
-// barrier) the pipe idles.  A third independent CTA per SM does not fit 3 x 256 TMEM columns, so this variant halves the
-// chunk: S (64 fp32 columns) + O (64) = 128 columns, the bf16 / fp16 probabilities are written OVER the S columns they
-// were computed from (a thread only ever touches its own TMEM lane), K / V stages are 16 KB, smem 65 KB per CTA.  The
-// price is that Q K(j+1)^T can only be issued once P V(j) has read P - a serial chain per CTA that the two other CTAs
-// cover.  Registers: 3 x 256 x 80 at launch, redistributed to 136 (softmax) / 24 (control) per thread.
-// =====================================================================================================
-constexpr int A6_BN = 64;
-constexpr int A6_KV_STAGES = 3;
-constexpr int A6_KV_TILE = A6_BN * AT_DH * 2;                 // 8 KB: [64 keys][64] 16-bit
-constexpr int A6_KV_OFF = AT_TILE;                            // after the Q tile
-constexpr int A6_BAR_OFF = A6_KV_OFF + A6_KV_STAGES * 2 * A6_KV_TILE;
-constexpr int A6_SMEM = A6_BAR_OFF + 128;                     // 65664 B: 3 x (this + 1 KB reserved) fits 228 KB
-constexpr int A6_REGS_SOFTMAX = 136, A6_REGS_CONTROL = 24;
-
-template <bool FP16, int POLY>
-__global__ void __launch_bounds__(AT_THREADS, 3)
-attn_fwd64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, const AttnParams p) {
-  constexpr int TMEM_COLS = 128;   // S / P: columns [0, 64) (P = 32 packed columns over S), O: columns [64, 128)
-  constexpr float LOG2E = FP16 ? 1.4426950408889634f / (ACT_SCALE * ACT_SCALE) : 1.4426950408889634f;
-
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
-  if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A6_BAR_OFF);
-  uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;    // [3]
-  uint64_t* kv_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;
-  uint64_t* p_full = bars + 8;
-  uint64_t* pv_done = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = lane_id();
-  const int q0 = blockIdx.x * AT_BM;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int kv_raw = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
-  const int kv_len = (kv_raw <= 0) ? p.T : kv_raw;      // no valid key: the reference's uniform -10000 cancels (see above)
-  const int nchunks = (kv_len + A6_BN - 1) / A6_BN;
-
-  if (warp == 4 && elect_one()) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_kv);
-  }
-  if (warp == 5 && elect_one()) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < A6_KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(pv_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_trigger();
-  pdl_wait();
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
-
-  if (warp >= 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(A6_REGS_CONTROL));
-    if (warp == 4) {
-      // ---------------------------------------------------------------- TMA producer
-      if (elect_one()) {
-        mbar_arrive_expect_tx(q_full, AT_TILE);
-        tma_load_3d(smem, &tm_q, q_full, h * AT_DH, q0, b);
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int j = 0; j < nchunks; ++j) {
-          mbar_wait(&kv_empty[stage], phase ^ 1);
-          uint8_t* kbuf = smem + A6_KV_OFF + stage * 2 * A6_KV_TILE;
-          mbar_arrive_expect_tx(&kv_full[stage], 2 * A6_KV_TILE);
-          tma_load_3d(kbuf, &tm_kv, &kv_full[stage], p.d + h * AT_DH, j * A6_BN, b);
-          tma_load_3d(kbuf + A6_KV_TILE, &tm_kv, &kv_full[stage], 2 * p.d + h * AT_DH, j * A6_BN, b);
-          if (++stage == A6_KV_STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-      }
-    } else if (warp == 5) {
-      // ---------------------------------------------------------------- MMA issuer
-      if (elect_one()) {
-        constexpr uint32_t idesc_s = idesc_16bit(FP16, AT_BM, A6_BN, 0, 0);    // S = Q K^T: A, B K-major
-        constexpr uint32_t idesc_pv = idesc_16bit(FP16, AT_BM, AT_DH, 0, 1);   // O += P V: A = P (TMEM), B = V MN-major
-        const uint64_t dq = desc_kmajor_sw128(smem_u32(smem));
-        mbar_wait(q_full, 0);
-        for (int j = 0; j < nchunks; ++j) {
-          const int stage = j % A6_KV_STAGES;
-          const uint32_t k_addr = smem_u32(smem + A6_KV_OFF + stage * 2 * A6_KV_TILE);
-          mbar_wait(&kv_full[stage], (j / A6_KV_STAGES) & 1);
-          if (j > 0) mbar_wait(pv_done, (j - 1) & 1);     // P V(j-1) has read P: the S / P columns are free again
-          tc_fence_after();
-          const uint64_t dk = desc_kmajor_sw128(k_addr);
-#pragma unroll
-          for (int k = 0; k < AT_DH / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-          umma_commit(s_full);
-          mbar_wait(p_full, j & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int ks = 0; ks < A6_BN / 16; ++ks) {
-            const uint64_t dv = desc_mnmajor_sw128(k_addr + A6_KV_TILE + ks * 2048, 1024, 1024);
-            umma_f16_tmem_a(tmem_o, tmem_s + ks * 8, dv, idesc_pv, (j | ks) != 0);
-          }
-          umma_commit(pv_done);
-          umma_commit(&kv_empty[stage]);
-        }
-      }
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(A6_REGS_SOFTMAX));
-    // ---------------------------------------------------------------- softmax / output (one row per thread)
-    const int r = warp * 32 + lane;
-    const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-    const uint32_t s_addr = tmem_s + lane_sel, o_addr = tmem_o + lane_sel;
-    float m_used = -INFINITY, l_run = 0.0f;
-    for (int j = 0; j < nchunks; ++j) {
-      const uint32_t par = j & 1;
-      const int key0 = j * A6_BN;
-      const bool partial = key0 + A6_BN > kv_len;
-      uint32_t sr[2][32];
-      mbar_wait(s_full, par);
-      tc_fence_after();
-      tmem_ld_32x32b_x32(s_addr, sr[0]);
-      tmem_ld_32x32b_x32(s_addr + 32, sr[1]);
-      tmem_ld_wait();
-      if (partial) {
-#pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (key0 + pc * 32 + i >= kv_len) sr[pc][i] = 0xff800000u;
-        }
-      }
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-#pragma unroll
-      for (int pc = 0; pc < 2; ++pc) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            mx[c] = fmaxf(fmaxf(mx[c], __uint_as_float(sr[pc][i + 2 * c])), __uint_as_float(sr[pc][i + 2 * c + 1]));
-        }
-      }
-      const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      // lazy rescaling: the exponent reference only moves when the chunk maximum outgrows it by more than 2^8
-      if (__any_sync(0xffffffffu, (cmax - m_used) * LOG2E > 8.0f)) {
-        const float m_new = fmaxf(m_used, cmax);
-        const float alpha = ex2_approx((m_used - m_new) * LOG2E);   // 0 for a first reference, 1 for rows that did not grow
-        if (j > 0) {   // O holds chunks < j (P V(j-1) retired before Q K(j)^T was issued)
-#pragma unroll
-          for (int piece = 0; piece < 2; ++piece) {
-            uint32_t ob[32];
-            tmem_ld_32x32b_x32(o_addr + piece * 32, ob);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) ob[i] = __float_as_uint(__uint_as_float(ob[i]) * alpha);
-            tmem_st_32x32b_x32(o_addr + piece * 32, ob);
-          }
-          tmem_st_wait();
-        }
-        l_run *= alpha;
-        m_used = m_new;
-      }
-      const float mneg = -m_used * LOG2E;
-      const uint64_t l2e2 = pack2(LOG2E, LOG2E), mneg2 = pack2(mneg, mneg);
-      uint64_t sum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
-#pragma unroll
-      for (int pc = 0; pc < 2; ++pc) {
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t arg = fma2(pack2(__uint_as_float(sr[pc][i]), __uint_as_float(sr[pc][i + 1])), l2e2, mneg2);
-          float a0, a1;
-          unpack2(arg, a0, a1);
-          if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == 0) {
-            // exp2 on the FMA pipe: Cody-Waite split + degree-3 polynomial (7.5e-5 relative, below the rounding of the 16-bit P)
-            const uint64_t x = pack2(fmaxf(a0, -126.0f), fmaxf(a1, -126.0f));
-            const uint64_t magic = pack2(12582912.0f, 12582912.0f);
-            const uint64_t t = add2(x, magic);
-            const uint64_t fr = add2(x, fma2(t, pack2(-1.0f, -1.0f), magic));
-            uint64_t pl = fma2(fr, pack2(0.0551716685f, 0.0551716685f), pack2(0.24261114f, 0.24261114f));
-            pl = fma2(pl, fr, pack2(0.69326097f, 0.69326097f));
-            pl = fma2(pl, fr, pack2(0.99992806f, 0.99992806f));
-            float t0, t1, p0, p1;
-            unpack2(t, t0, t1);
-            unpack2(pl, p0, p1);
-            a0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-            a1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-          } else {
-            a0 = ex2_approx(a0);
-            a1 = ex2_approx(a1);
-          }
-          sum2[(i >> 1) & 3] = add2(sum2[(i >> 1) & 3], pack2(a0, a1));
-          sr[pc][i] = __float_as_uint(a0);
-          sr[pc][i + 1] = __float_as_uint(a1);
-        }
-      }
-      {
-        float s0, s1, s2, s3, s4, s5, s6, s7;
-        unpack2(sum2[0], s0, s1);
-        unpack2(sum2[1], s2, s3);
-        unpack2(sum2[2], s4, s5);
-        unpack2(sum2[3], s6, s7);
-        l_run += ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-      }
-      if (p.drop.thr16) {   // training: dropout on the probabilities AFTER the softmax (the row sum is the undropped one)
-        const uint64_t rg = attn_row_group(b * p.H + h, q0 + r, p.T) + (uint64_t)(key0 >> 2);
-#pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
-#pragma unroll
-          for (int i4 = 0; i4 < 8; ++i4) {
-            const uint64_t bits = drop_bits4(p.drop, rg + pc * 8 + i4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v = __uint_as_float(sr[pc][4 * i4 + e]);
-              sr[pc][4 * i4 + e] = drop_keep(bits, e, p.drop.thr16) ? __float_as_uint(v * p.drop.scale) : 0u;
-            }
-          }
-        }
-      }
-      // P (16-bit pairs) over the S columns this thread just read: 64 keys = 32 packed columns, the A operand of P V
-      uint32_t pk[32];
-#pragma unroll
-      for (int c = 0; c < 32; ++c)
-        pk[c] = FP16 ? pack_f16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]))
-                     : pack_bf16x2(__uint_as_float(sr[c >> 4][(2 * c) & 31]), __uint_as_float(sr[c >> 4][(2 * c + 1) & 31]));
-      tmem_st_32x32b_x32(s_addr, pk);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-    }
-
-    // ---- epilogue: O / l
-    mbar_wait(pv_done, (nchunks - 1) & 1);
-    tc_fence_after();
-    const int t = q0 + r;
-    const float inv = (1.0f / l_run) * ((FP16 ? 1.0f / ACT_SCALE : 1.0f) * (p.out_format != 0 ? ACT_SCALE : 1.0f));
-    const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
-#pragma unroll
-    for (int piece = 0; piece < 2; ++piece) {
-      uint32_t rr[32];
-      tmem_ld_32x32b_x32(o_addr + piece * 32, rr);
-      tmem_ld_wait();
-      if (t < p.T) {
-        if (p.out_format == 2) {
-          uint8_t* p8 = reinterpret_cast<uint8_t*>(p.out_lo) + ((size_t)b * p.T + t) * p.d * 2 + (size_t)h * 128 + piece * 32;
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            uint32_t hi[8];
-            uint16_t l8[8], h8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              hi[e] = split_f16_f8x2(__uint_as_float(rr[16 * q + 2 * e]) * inv, __uint_as_float(rr[16 * q + 2 * e + 1]) * inv, l8[e], h8[e]);
-            *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 16 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 16 * q + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-            *reinterpret_cast<uint4*>(p8 + 16 * q) = make_uint4(l8[0] | ((uint32_t)l8[1] << 16), l8[2] | ((uint32_t)l8[3] << 16),
-                                                                l8[4] | ((uint32_t)l8[5] << 16), l8[6] | ((uint32_t)l8[7] << 16));
-            *reinterpret_cast<uint4*>(p8 + 64 + 16 * q) = make_uint4(h8[0] | ((uint32_t)h8[1] << 16), h8[2] | ((uint32_t)h8[3] << 16),
-                                                                     h8[4] | ((uint32_t)h8[5] << 16), h8[6] | ((uint32_t)h8[7] << 16));
-          }
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float v0 = __uint_as_float(rr[8 * q + 2 * e]) * inv, v1 = __uint_as_float(rr[8 * q + 2 * e + 1]) * inv;
-              hi[e] = (p.out_format == 0) ? split_bf16x2(v0, v1, lo[e]) : split_f16x2(v0, v1, lo[e]);
-            }
-            *reinterpret_cast<uint4*>(p.out_hi + off + piece * 32 + 8 * q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            if (p.out_lo != nullptr)
-              *reinterpret_cast<uint4*>(p.out_lo + off + piece * 32 + 8 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          }
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  if (warp == 4) tmem_dealloc<TMEM_COLS>(tmem_base);
-}
-
-template <bool FP16, int POLY>
-static int launch_attn64(const void* qkv_hi, int B, int T, int H, const int* kv_len, void* out_hi, void* out_lo, int out_format,
-                         DropSpec drop, cudaStream_t stream) {
-  const int d = H * AT_DH;
-  CUtensorMap tm_q, tm_kv;
-  const uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)T, (uint64_t)B};
-  const uint64_t strides[2] = {(uint64_t)3 * d * 2, (uint64_t)T * 3 * d * 2};
-  const uint32_t box_q[3] = {AT_DH, AT_BM, 1}, box_kv[3] = {AT_DH, A6_BN, 1};
-  int rc = make_tmap(&tm_q, qkv_hi, 3, dims, strides, box_q, CU_TENSOR_MAP_SWIZZLE_128B);
-  if (rc) return rc;
-  if ((rc = make_tmap(&tm_kv, qkv_hi, 3, dims, strides, box_kv, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  AttnParams p;
-  p.T = T;
-  p.d = d;
-  p.kv_len = kv_len;
-  p.out_hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
-  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  p.drop = drop;
-  p.H = H;
-  p.out_format = out_format;
-  auto kern = attn_fwd64_kernel<FP16, POLY>;
-  static unsigned long long smem_attr_done = 0;
-  W2V2_CUDA(ensure_dyn_smem(kern, A6_SMEM, smem_attr_done));
-  dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
-  W2V2_CUDA(launch_pdl(kern, grid, dim3(AT_THREADS), (size_t)A6_SMEM, stream, 0, tm_q, tm_kv, p));
-  return 0;
-}
-
 template <int PASSES, bool FP16>
 static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int H, const int* kv_len, void* out_hi,
                        void* out_lo, int out_format, DropSpec drop, cudaStream_t stream) {
@@ -811,16 +481,6 @@ static int attn_fwd_impl(const void* qkv_hi, const void* qkv_lo, int batch, int 
   W2V2_CHECK_ARG(out_format >= 0 && out_format <= 2 && (out_format != 2 || out_lo), "out_format must be 0, 1 or 2 (2 writes out_lo)");
   W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  // A/B switches (read once): W2V2_ATTN_KERNEL=64 selects the 64-key-chunk, three-CTAs-per-SM variant for the single-pass modes;
-  // W2V2_ATTN_POLY=0 keeps every exponential of that variant on MUFU (else one pair in AT_POLY_EVERY runs on the FMA pipe)
-  static const int poly = [] { const char* e = getenv("W2V2_ATTN_POLY"); return e ? atoi(e) : AT_DEFAULT_POLY; }();
-  static const int k64 = [] { const char* e = getenv("W2V2_ATTN_KERNEL"); return e ? (atoi(e) == 64) : (AT_DEFAULT_KERNEL == 64); }();
-  if (k64 && (passes == 1 || passes == 17)) {
-    if (passes == 1) return poly ? launch_attn64<false, AT_POLY_EVERY>(qkv_hi, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s)
-                                 : launch_attn64<false, 0>(qkv_hi, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
-    return poly ? launch_attn64<true, AT_POLY_EVERY>(qkv_hi, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s)
-                : launch_attn64<true, 0>(qkv_hi, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s);
-  }
 #define AT_LAUNCH(P, F) launch_attn<P, F>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s)
   if (passes == 1) return AT_LAUNCH(1, false);
   if (passes == 17) return AT_LAUNCH(1, true);

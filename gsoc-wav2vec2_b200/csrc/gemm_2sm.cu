@@ -87,7 +87,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   const int n = n0 + c_base;        // ... and in the output
 
   uint32_t r[2][32];
-  if (p.debug != 3) {
+  if (!W2V2_DBG(p, 3)) {
     tmem_ld_32x32b_x32(taddr + c_base, r[0]);
     tmem_ld_32x32b_x32(taddr + c_base + 32, r[1]);
     tmem_ld_wait();
@@ -95,8 +95,8 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(tmem_empty_cluster_addr);  // accumulator stage is free again
-  if (p.debug == 3) return;
-  if (p.debug == 1) {
+  if (W2V2_DBG(p, 3)) return;
+  if (W2V2_DBG(p, 1)) {
     if (__uint_as_float(r[0][0] ^ r[1][31]) == 1.2345e-30f) p.out_f32[0] = 0.0f;
     return;
   }

@@ -7,6 +7,13 @@
 
 namespace w2v2 {
 
+// The epilogue ablation switches (GemmParams::debug) are profiling aids: release builds compile them out
+#ifdef W2V2_GEMM_DEBUG
+#define W2V2_DBG(p, v) ((p).debug == (v))
+#else
+#define W2V2_DBG(p, v) false
+#endif
+
 constexpr int GEMM_BLOCK_M = 128;
 constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
 constexpr int GEMM_STAGES_MAX = 4;
@@ -33,7 +40,7 @@ struct GemmParams {
   int N;                // valid output columns == leading dimension of every output / residual
   int gelu;            // 0 = none, 1 = erf-exact, 2 = tanh-form fit of the erf GELU (single-pass mode), 3 = tf "approximate" GELU
   int vec_ok;           // N % 8 == 0: 16-byte vector stores are aligned
-  int debug;            // profiling aid: 1 = epilogue only drains TMEM, 2 = no global stores
+  int debug;            // profiling aid, only compiled with -DW2V2_GEMM_DEBUG: 1 = epilogue only drains TMEM, 2 = no global stores, 3 = no TMEM read
   int atomic_f32;       // 1: out_f32 += result with fp32 atomics (split-K partial sums into a zeroed buffer)
   int mn_major;         // 1: both operands are MN-major (reduction over the ROW index of two row-major matrices: wgrad)
   const float* bias;      // [N] (or [batch][N] with bias_bstride = N) or null
@@ -157,7 +164,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   // chunk index of my i-th chunk: pairs (0,1),(4,5),.. for grp 0 and (2,3),(6,7),.. for grp 1
   auto chunk_of = [&](int i) { return 4 * (i >> 1) + 2 * grp + (i & 1); };
   uint32_t r[NMINE][32];
-  if (p.debug != 3) {
+  if (!W2V2_DBG(p, 3)) {
 #pragma unroll
     for (int i = 0; i < NMINE; ++i)
       if (chunk_of(i) < NCH) tmem_ld_32x32b_x32(taddr + chunk_of(i) * 32, r[i]);
@@ -166,8 +173,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
   tc_fence_before();
   __syncwarp();
   if (lane == 0) mbar_arrive_cluster(tmem_empty_cluster_addr);  // accumulator stage is free again
-  if (p.debug == 3) return;
-  if (p.debug == 1) {
+  if (W2V2_DBG(p, 3)) return;
+  if (W2V2_DBG(p, 1)) {
     uint32_t x = 0;
 #pragma unroll
     for (int i = 0; i < NMINE; ++i) x ^= r[i][i];
@@ -316,7 +323,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t
       for (int j = 0; j < 16; ++j) r[i][16 * hf + j] = zero_row ? 0u : __float_as_uint(v[j]);
     }
   }
-  if (p.debug == 2) {
+  if (W2V2_DBG(p, 2)) {
     if (__uint_as_float(r[0][0] ^ r[NMINE - 1][31]) == 1.2345e-30f) p.out_f32[0] = 0.0f;
     return;
   }
