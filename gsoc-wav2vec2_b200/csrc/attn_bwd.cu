@@ -459,6 +459,9 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
   }
 }
 
+int launch_attn_bwd_tc(const void* qkv_hi, const void* dctx_hi, int B, int T, int H, const int* kv_len, float q_scale,
+                       float* lse2, float* dsum, void* dqkv_hi, DropSpec dr, cudaStream_t stream);   // attn_bwd_tc.cu
+
 }  // namespace w2v2
 
 using namespace w2v2;
@@ -478,6 +481,11 @@ extern "C" int w2v2_attn_bwd(const void* qkv_hi, const void* ctx_hi, const void*
   float* dsum = lse2 + (size_t)batch * num_heads * frames;
   W2V2_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f, "drop_p must be in [0, 1)");
   const DropSpec dr = make_drop(drop_p, seed, site);
+  // default: the tcgen05 / TMEM kernels of attn_bwd_tc.cu; W2V2_ATTN_BWD=mma keeps the mma.sync pair below (the reference
+  // implementation the new kernels were validated against, and an A/B switch)
+  static const bool use_mma = [] { const char* e = getenv("W2V2_ATTN_BWD"); return e && strcmp(e, "mma") == 0; }();
+  if (!use_mma)
+    return launch_attn_bwd_tc(qkv_hi, dctx_hi, batch, frames, num_heads, kv_len, q_scale, lse2, dsum, dqkv_hi, dr, s);
   dim3 grid((frames + AB_BLK - 1) / AB_BLK, batch * num_heads);
   attn_bwd_dq_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(qkv_hi),
                                           reinterpret_cast<const __nv_bfloat16*>(ctx_hi),
