@@ -29,7 +29,7 @@ CPU_SAMPLE_BATCH = 2
 
 def _ncu_traffic():
     """dram bytes per launch of the two roofline kernels from the committed ncu --set full capture (B=32 x 246000 only)."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_traffic.json")
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
     if os.path.isfile(path):
         with open(path) as fh:
             return json.load(fh)

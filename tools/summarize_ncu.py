@@ -11,7 +11,9 @@ from collections import OrderedDict
 mode, path = sys.argv[1], sys.argv[2]
 
 if mode == "full":
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # `path`: a .ncu-rep, or the `ncu -i <rep> --page raw --csv` export made on the GPU box (the reports exceed gpurun's 64 MiB)
+    raw = open(path).read() if path.endswith(".csv") else \
+        subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     cols = OrderedDict([
@@ -19,6 +21,7 @@ if mode == "full":
         ("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram rd"), ("dram__bytes_write.sum", "dram wr"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
         ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor %"),
+        ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu %"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps %"),
     ])
