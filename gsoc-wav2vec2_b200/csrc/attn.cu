@@ -228,7 +228,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
   }
   } else {
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(AT_REGS_SOFTMAX));
+  // one CTA per SM in the 3-pass modes (launch allocation 256 registers per thread): the softmax warps take 240 and stop spilling
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"((PASSES == 1) ? AT_REGS_SOFTMAX : 240));
   {
     // ---------------------------------------------------------------- softmax / output (one row per thread)
     const int r = warp * 32 + lane;

@@ -226,50 +226,65 @@ attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_c
           }
         }
       }
-      if (!sweep2) {
-        // ---- online statistics of this thread's 64 keys (log2 domain)
-        float cmax = -INFINITY;
+      const bool ragged = key0 + 64 > klen;          // only the last chunk can hold masked keys
+      if (ragged) {
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float v = __uint_as_float(sS[pc][i]) * BT_LOG2E;
-            if (key0 + pc * 32 + i >= klen) v = -INFINITY;
-            sS[pc][i] = __float_as_uint(v);
-            cmax = fmaxf(cmax, v);
+          for (int i = 0; i < 32; ++i)
+            if (key0 + pc * 32 + i >= klen) sS[pc][i] = 0xff800000u;   // -inf: probability exactly 0 in both sweeps
+        }
+      }
+      if (!sweep2) {
+        // ---- online statistics of this thread's 64 keys (log2 domain); packed fp32x2 math, 4 independent max chains
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              mx[c] = fmaxf(fmaxf(mx[c], __uint_as_float(sS[pc][i + 2 * c])), __uint_as_float(sS[pc][i + 2 * c + 1]));
           }
         }
+        const float cmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * BT_LOG2E;
         const float m_new = fmaxf(m_run, cmax);
-        float ps = 0.0f, pd = 0.0f;
         if (m_new > -INFINITY) {
+          const uint64_t l2 = pack2(BT_LOG2E, BT_LOG2E), mn2 = pack2(-m_new, -m_new);
+          uint64_t ps2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)}, pd2[2] = {pack2(0.f, 0.f), pack2(0.f, 0.f)};
 #pragma unroll
           for (int pc = 0; pc < 2; ++pc) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float e = ex2_approx(__uint_as_float(sS[pc][i]) - m_new);
-              ps += e;
-              pd = fmaf(e, __uint_as_float(sD[pc][i]), pd);
+            for (int i = 0; i < 32; i += 2) {
+              float a0, a1;
+              unpack2(fma2(pack2(__uint_as_float(sS[pc][i]), __uint_as_float(sS[pc][i + 1])), l2, mn2), a0, a1);
+              const uint64_t e2 = pack2(ex2_approx(a0), ex2_approx(a1));
+              ps2[(i >> 1) & 1] = add2(ps2[(i >> 1) & 1], e2);
+              pd2[(i >> 1) & 1] = fma2(e2, pack2(__uint_as_float(sD[pc][i]), __uint_as_float(sD[pc][i + 1])), pd2[(i >> 1) & 1]);
             }
           }
+          float p0, p1, p2, p3, d0, d1, d2, d3;
+          unpack2(ps2[0], p0, p1);
+          unpack2(ps2[1], p2, p3);
+          unpack2(pd2[0], d0, d1);
+          unpack2(pd2[1], d2, d3);
           const float resc = ex2_approx(m_run - m_new);   // 0 when nothing had been accumulated
-          l_run = l_run * resc + ps;
-          a_run = a_run * resc + pd;
+          l_run = l_run * resc + ((p0 + p1) + (p2 + p3));
+          a_run = a_run * resc + ((d0 + d1) + (d2 + d3));
           m_run = m_new;
         }
       } else {
         // ---- dS = P o (dP - D) -> bf16 pairs -> TMEM (A operand of dQ += dS K)
         uint32_t pk[32];
+        const uint64_t l2 = pack2(BT_LOG2E, BT_LOG2E), nl2 = pack2(-lse, -lse), nd2 = pack2(-dsum, -dsum);
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          float ds[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int i = 2 * c + e;
-            const float sv = __uint_as_float(sS[i >> 5][i & 31]);
-            const float pv = (key0 + i < klen) ? ex2_approx(fmaf(sv, BT_LOG2E, -lse)) : 0.0f;
-            ds[e] = pv * (__uint_as_float(sD[i >> 5][i & 31]) - dsum);
-          }
-          pk[c] = pack_bf16x2(ds[0], ds[1]);
+          const int i = 2 * c;
+          float a0, a1, r0, r1;
+          unpack2(fma2(pack2(__uint_as_float(sS[i >> 5][i & 31]), __uint_as_float(sS[i >> 5][(i & 31) + 1])), l2, nl2), a0, a1);
+          const uint64_t p2 = pack2(ex2_approx(a0), ex2_approx(a1));   // masked keys: ex2(-inf) = 0
+          unpack2(mul2(p2, add2(pack2(__uint_as_float(sD[i >> 5][i & 31]), __uint_as_float(sD[i >> 5][(i & 31) + 1])), nd2)), r0, r1);
+          pk[c] = pack_bf16x2(r0, r1);
         }
         const int u = s - nchunks;
         if (u > 0) mbar_wait(ds_empty, (u - 1) & 1);      // the previous dQ MMAs have read the dS columns
@@ -457,20 +472,36 @@ attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(sd_empty);
       uint32_t pp[32], pd[32];     // P^T (dropped) and dS^T as bf16 pairs over this thread's 64 queries
+      const uint64_t l2 = pack2(BT_LOG2E, BT_LOG2E);
+      const float rowmask = key_ok ? 0.0f : -INFINITY;     // a masked key row: every probability exactly 0
 #pragma unroll
-      for (int cc = 0; cc < 32; ++cc) {
-        float pv2[2], ds2[2];
+      for (int g4 = 0; g4 < 16; ++g4) {                    // four queries per step: one 16-byte smem read of lse and of D
+        const float4 l4 = *reinterpret_cast<const float4*>(lsev + cs + 4 * g4);
+        const float4 d4 = *reinterpret_cast<const float4*>(dv_ + cs + 4 * g4);
+        const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int i = 2 * cc + e, ql = (int)cs + i;
-          const float pv = key_ok ? ex2_approx(fmaf(__uint_as_float(sS[i >> 5][i & 31]), BT_LOG2E, -lsev[ql])) : 0.0f;
-          float kf = 1.0f;
-          if (p.drop.thr16) kf = ((kp[ql * 32 + (r >> 2)] >> (r & 3)) & 1u) ? p.drop.scale : 0.0f;
-          pv2[e] = pv * kf;                                              // dV uses the dropped probabilities
-          ds2[e] = pv * (__uint_as_float(sD[i >> 5][i & 31]) * kf - dv_[ql]);
+        for (int hp = 0; hp < 2; ++hp) {
+          const int i = 4 * g4 + 2 * hp;
+          float a0, a1;
+          unpack2(fma2(pack2(__uint_as_float(sS[i >> 5][i & 31]), __uint_as_float(sS[i >> 5][(i & 31) + 1])), l2,
+                       pack2(rowmask - lq[2 * hp], rowmask - lq[2 * hp + 1])), a0, a1);
+          const uint64_t p2 = pack2(ex2_approx(a0), ex2_approx(a1));
+          uint64_t dp2 = pack2(__uint_as_float(sD[i >> 5][i & 31]), __uint_as_float(sD[i >> 5][(i & 31) + 1]));
+          uint64_t pdrop2 = p2;
+          if (p.drop.thr16) {
+            const int ql = (int)cs + i;
+            const float k0f = ((kp[ql * 32 + (r >> 2)] >> (r & 3)) & 1u) ? p.drop.scale : 0.0f;
+            const float k1f = ((kp[(ql + 1) * 32 + (r >> 2)] >> (r & 3)) & 1u) ? p.drop.scale : 0.0f;
+            const uint64_t kf2 = pack2(k0f, k1f);
+            dp2 = mul2(dp2, kf2);
+            pdrop2 = mul2(p2, kf2);                                      // dV uses the dropped probabilities
+          }
+          float q0v, q1v, s0v, s1v;
+          unpack2(pdrop2, q0v, q1v);
+          unpack2(mul2(p2, add2(dp2, pack2(-dq4[2 * hp], -dq4[2 * hp + 1]))), s0v, s1v);
+          pp[i >> 1] = pack_bf16x2(q0v, q1v);
+          pd[i >> 1] = pack_bf16x2(s0v, s1v);
         }
-        pp[cc] = pack_bf16x2(pv2[0], pv2[1]);
-        pd[cc] = pack_bf16x2(ds2[0], ds2[1]);
       }
       if (c > 0) mbar_wait(pds_empty, (c - 1) & 1);
       tc_fence_after();

@@ -354,3 +354,62 @@ def test_gemm_residual_is_layernorm_recomputed(M, K, N, cluster):
     mean, var = y.mean(-1), y.var(-1, unbiased=False)
     assert (stats[:, 0] - mean).abs().max().item() < 1e-5 and (stats[:, 1] - torch.rsqrt(var + 1e-5)).abs().max().item() < 1e-4
     assert torch.equal(got, want)              # same arithmetic as the LayerNorm kernel: bit-identical
+
+
+@pytest.mark.parametrize("passes", [1, 17, 25])
+def test_gemm_layernorm_fold_and_row_statistics(passes):
+    """The LayerNorm fold at kernel level (include/w2v2.h ln_fold_* / row_stats_out / w2v2_row_stats_finalize):
+    producer  y = r + x W1 + b1 (residual GEMM) also writes the operand planes of y and per-row partial (sum, sum of squares);
+    consumer  LN(y) W2 + b2 computed from those planes with gamma folded into W2 and mean / rstd applied in the epilogue -
+    against the explicit fp64 LayerNorm + matmul of the same fp32 data."""
+    from wav2vec2.modeling import _KINDS, _effective_weight, _split
+    torch.manual_seed(7)
+    M, K1, d, N2 = 128 * 5 + 17, 256, 768, 512
+    kind = {1: "bf16", 17: "fp16", 25: "fp16f8"}[passes]
+    hi_dt, lo_kind, ofmt = _KINDS[kind]
+
+    def planes_of(x):          # operand planes of an fp32 activation, as a producing kernel would write them
+        if passes == 1:
+            return Pair(x.to(torch.bfloat16).contiguous(), None)
+        hi = torch.empty(x.shape, dtype=torch.float16, device=DEV)
+        lo = torch.empty(x.shape[0], 2 * x.shape[1], dtype=torch.uint8, device=DEV) if passes == 25 else None
+        s = torch.clamp(x * 16.0, -65504, 65504)
+        hi.copy_(s.to(torch.float16))
+        if lo is not None:
+            res = s - hi.float()
+            rows, C = x.shape
+            l8 = torch.clamp(res * 64, -448, 448).to(torch.float8_e4m3fn).view(torch.uint8).reshape(rows, C // 64, 1, 64)
+            h8 = torch.clamp(hi.float() / 64, -448, 448).to(torch.float8_e4m3fn).view(torch.uint8).reshape(rows, C // 64, 1, 64)
+            lo.copy_(torch.cat([l8, h8], 2).reshape(rows, 2 * C))
+        return Pair(hi, lo)
+    x = torch.randn(M, K1, device=DEV)
+    r = torch.randn(M, d, device=DEV) * 2 + 0.5                      # residual with a non-zero mean per row
+    w1, b1 = torch.randn(d, K1, device=DEV) / math.sqrt(K1), torch.randn(d, device=DEV)
+    gamma, beta = 1 + 0.2 * torch.randn(d, device=DEV), 0.3 * torch.randn(d, device=DEV)
+    w2, b2 = torch.randn(N2, d, device=DEV) / math.sqrt(d), torch.randn(N2, device=DEV)
+    # ---- producer
+    y = r.clone()
+    ys = Pair(torch.empty(M, d, dtype=hi_dt, device=DEV), torch.empty(M, 2 * d, dtype=torch.uint8, device=DEV) if passes == 25 else None)
+    parts = torch.full((d // 64, M, 2), float("nan"), device=DEV)
+    ops.gemm(planes_of(x), _split(w1, passes), K=K1, N=d, rows_per_batch=M, bias=b1, residual=y, out_f32=y, out_hi=ys.hi, out_lo=ys.lo,
+             out_format=ofmt, row_stats_out=parts, passes=passes)
+    stats = ops.row_stats_finalize(parts, d, 1e-5, torch.empty(M, 2, device=DEV))
+    torch.cuda.synchronize()
+    y_ref = r.double() + x.double() @ w1.double().t() + b1.double()
+    tol_y = {1: 5e-2, 17: 5e-3, 25: 3e-4}[passes]
+    assert (y.double() - y_ref).abs().max().item() < tol_y
+    mean, var = y.double().mean(1), y.double().var(1, unbiased=False)
+    assert (stats[:, 0].double() - mean).abs().max().item() < 1e-4
+    assert (stats[:, 1].double() * torch.sqrt(var + 1e-5) - 1).abs().max().item() < 1e-4
+    # ---- consumer with the folded LayerNorm
+    wf = _split(w2 * gamma[None, :], passes)
+    cs = _effective_weight(wf, passes).sum(1).contiguous()
+    bf = (b2 + w2 @ beta).contiguous()
+    out = torch.empty(M, N2, device=DEV)
+    ops.gemm(ys, wf, K=d, N=N2, rows_per_batch=M, bias=bf, out_f32=out, passes=passes, ln_fold=(stats, cs), ln_eps=1e-5)
+    torch.cuda.synchronize()
+    ln = torch.nn.functional.layer_norm(y.double(), (d,), gamma.double(), beta.double(), 1e-5)
+    ref = ln @ w2.double().t() + b2.double()
+    err = (out.double() - ref).abs().max().item()
+    print(f"LayerNorm fold, mode {passes}: max err {err:.3e}")
+    assert err < {1: 1.5e-1, 17: 2e-2, 25: 1.5e-3}[passes]
