@@ -24,7 +24,8 @@ struct GemmSmem {
   static constexpr int A_BYTES = GEMM_BLOCK_M * GEMM_BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * GEMM_BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : 4;
+  // narrow tiles serve the small problems, where a CTA's serial k-loop is bound by TMA latency / ring depth: as deep as smem allows
+  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128) ? 5 : 7;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int BAR_BYTES = 256;
   static constexpr int BIAS_BYTES = 4 * BLOCK_N * 4;  // per accumulator stage: bias slice; scale slices follow
@@ -440,7 +441,14 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
     if (bn == 64) return launch_gemm<64, 1, 1>(a, s);
     return fail(-1, "%s: MN-major mode supports block_n 64 or 128", __func__);
   }
-  if (bn == 0) bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;
+  if (bn == 0) {
+    bn = (a->N % 256 == 0) ? 256 : (a->N % 128 == 0) ? 128 : (a->N % 64 == 0) ? 64 : 32;
+    // Small problems (fewer 256-wide tiles than a quarter of the SMs): every CTA walks its whole K loop alone, bound by TMA
+    // latency / ring depth, and most SMs idle.  64-wide tiles give 4x the CTAs and a 7-stage ring (FFN2 at 49 frames: 3 CTAs x 48
+    // k-blocks through 3 stages -> 12 CTAs through 7).  Same accumulation order per output element, so results are bit-identical.
+    const long tiles256 = (long)a->batch * ((a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M) * ((a->N + 255) / 256);
+    if (bn > 64 && a->N % 64 == 0 && tiles256 < 37) bn = 64;
+  }
   W2V2_CHECK_ARG(a->w_rows >= ((a->N + bn - 1) / bn) * bn, "weight matrix must be padded to a multiple of block_n rows");
   // clusters of 2 (weight-tile multicast) for the wide tiles whenever there are at least two m-tiles
   const long m_tiles = (long)a->batch * ((a->rows_per_batch + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M);
