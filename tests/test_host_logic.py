@@ -199,3 +199,27 @@ def test_stage2_learning_rate_schedule():
     from wav2vec2.finetune import FineTuneArgs, stage2_learning_rate
     a = FineTuneArgs(stage2_lr1=1e-4, stage2_lr2=5e-5, stage2_transition_epochs=2)
     assert [stage2_learning_rate(e, a) for e in range(5)] == [1e-4, 1e-4, 1e-4, 5e-5, 5e-5]
+
+
+def test_weight_planes_of_every_precision_mode_decode_to_the_weight():
+    """`_split(w, mode)` (the packing of every Dense / conv kernel) against `_effective_weight` (what the tensor cores multiply by):
+    bf16 2^-9, bf16x3 2^-17, fp16 2^-12, fp16x3 2^-23, fp16f8 2^-15 relative (+ the e4m3 residual's subnormal floor);
+    the fp16f8 byte plane holds, per 64-wide k-block, 64 hi bytes then 64 residual bytes (include/w2v2.h)."""
+    import math
+    from wav2vec2.modeling import _effective_weight, _split, _Modes
+    torch.manual_seed(0)
+    w = torch.randn(96, 128) / math.sqrt(128)
+    for mode, tol in ((1, 2.0 ** -8), (3, 2.0 ** -16), (17, 2.0 ** -11), (19, 2.0 ** -21), (25, 2.0 ** -14)):
+        p = _split(w, mode)
+        eff = _effective_weight(p, mode)
+        rel = ((eff - w).abs() / (w.abs() + 2.0 ** -8)).max().item()
+        assert rel < tol, (mode, rel)
+    p = _split(w, 25)
+    assert p.hi.dtype == torch.float16 and p.lo.dtype == torch.uint8 and tuple(p.lo.shape) == (96, 256)
+    blk = p.lo.reshape(96, 2, 2, 64)                                  # [row][k-block][hi8 | lo8][64]
+    hi8 = blk[:, :, 0].contiguous().view(torch.float8_e4m3fn).float().reshape(96, 128)
+    assert ((hi8 * 64 - p.hi.float()).abs() <= 0.07 * p.hi.float().abs() + 0.13).all()     # a 4-bit copy of the fp16 plane / 64
+    assert torch.equal(_split(w, True).lo, _split(w, 3).lo) and _split(w, False).lo is None and _split(w, 1).lo is None
+    for prec, (g, a, ps) in {"bf16": (1, 1, 1), "bf16x3": (3, 3, 3), "fp16": (17, 17, 17), "fp16f8": (25, 17, 17)}.items():
+        m = _Modes(prec)
+        assert (m.gemm, m.attn, m.pos) == (g, a, ps)
