@@ -21,6 +21,14 @@
 //     Final: O / l -> bf16 hi(/lo).
 // Two CTAs are resident per SM (<= 113 KB smem, 256 TMEM columns each) so one CTA's MMAs overlap the
 // other's softmax.  PASSES = 3 (parity mode) adds the hi/lo cross terms for both contractions.
+//
+// The kernel is PERSISTENT: grid = resident CTAs (2 x SMs, 1 x SMs in the 3-pass modes), every CTA walks the tile list
+// (q tile fastest, then head, then utterance) with stride gridDim.x.  The K/V ring, the S / P / O hand-shakes and their
+// mbarrier phases run straight across tile boundaries: while the softmax warps finish the last chunk and write the
+// context of tile i, the producer has already fetched Q and the first K/V stages of tile i+1 and the MMA warp has
+// issued its Q K(0)^T - the 2.2 us prologue (barrier init, TMEM alloc, first loads) and most of the 1.6 us epilogue
+// that a one-tile CTA exposes 2304 times (30 % of its lifetime, measured with %globaltimer stamps: profiles/r2_attn_fwd.md)
+// are paid once per CTA.
 #include "host_util.h"
 #include "w2v2_common.cuh"
 #include "../../include/w2v2.h"
@@ -61,7 +69,21 @@ struct AttnParams {
   DropSpec drop;       // attention-probability dropout of the training forward (encoder.py:42); thr16 == 0: off
   int H;
   int out_format;      // W2V2_OUT_*: 0 bf16 hi(/lo), 1 fp16 hi(/lo) of value * 2^4, 2 fp16 hi + e4m3 pair plane [rows][2 d]
+  int q_tiles;         // ceil(T / 128)
+  int n_tiles;         // q_tiles * H * B
 };
+
+// Optional timeline instrumentation (-DAT_STAMPS): %globaltimer stamps of thread 0 / the MMA thread per tile, read back with
+// w2v2_attn_debug_stamps (tools/attn_stamps.py).  Compiled out of release builds.
+#ifdef AT_STAMPS
+__device__ unsigned long long g_attn_stamps[4096 * 32];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAMPX(tile, i) do { if ((tile) < 4096) g_attn_stamps[(tile) * 32 + (i)] = gtime(); } while (0)
+#define STAMP(tile, i) do { if (threadIdx.x == 0) STAMPX(tile, i); } while (0)
+#else
+#define STAMPX(tile, i) do { } while (0)
+#define STAMP(tile, i) do { } while (0)
+#endif
 
 // FP16: q / k / v are fp16 planes of value * 2^4 (modes 17 / 19): S comes out at 2^8, O at 2^4; P is packed as fp16.
 // (Round 2 tried, on this kernel: pulling S out of TMEM piece by piece with the next piece's load in flight during the current
@@ -94,18 +116,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   uint64_t* p_full = bars + 9;
   uint64_t* p_empty = bars + 10;
   uint64_t* pv_done = bars + 11;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* q_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = lane_id();
-  const int q0 = blockIdx.x * AT_BM;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
+  // tile t -> (q tile, head, utterance), q tile fastest: CTAs that run together share the K / V of a head in L2
+  auto tile_coords = [&](int t, int& q0, int& h, int& b) {
+    q0 = (t % p.q_tiles) * AT_BM;
+    const int bh = t / p.q_tiles;
+    h = bh % p.H;
+    b = bh / p.H;
+  };
   // An utterance with NO valid key: the reference adds the same -10000 to every score (encoder.py:256-263), which the
   // softmax cancels - i.e. it attends over all T keys.  Reproduce that instead of producing exp(-inf - -inf) = NaN.
-  const int kv_raw = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
-  const int kv_len = (kv_raw <= 0) ? p.T : kv_raw;
-  const int nchunks = (kv_len + AT_BN - 1) / AT_BN;
+  // (kv_len is only read after pdl_wait(): the first use is inside the role loops)
+  auto tile_kv_len = [&](int b) {
+    const int kv_raw = (p.kv_len != nullptr) ? min(p.kv_len[b], p.T) : p.T;
+    return (kv_raw <= 0) ? p.T : kv_raw;
+  };
 
   if (warp == 4 && elect_one()) {
     tma_prefetch_desc(&tm_hi);
@@ -122,6 +151,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     mbar_init(p_full, 4);
     mbar_init(p_empty, 1);
     mbar_init(pv_done, 1);
+    mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == 4) tmem_alloc<TMEM_COLS>(tmem_slot);
@@ -140,25 +170,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
   if (warp == 4) {
     // ---------------------------------------------------------------- TMA producer
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, S::NPL * AT_TILE);
-      tma_load_3d(smem + S::Q_OFF, &tm_hi, q_full, h * AT_DH, q0, b);
-      if (PASSES == 3) tma_load_3d(smem + S::Q_OFF + AT_TILE, &tm_lo, q_full, h * AT_DH, q0, b);
       int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < nchunks; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        uint8_t* kbuf = smem + S::KV_OFF + stage * S::KV_STAGE_BYTES;
-        uint8_t* vbuf = kbuf + S::NPL * AT_TILE;
-        mbar_arrive_expect_tx(&kv_full[stage], S::KV_STAGE_BYTES);
-        tma_load_3d(kbuf, &tm_hi, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
-        tma_load_3d(vbuf, &tm_hi, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
-        if (PASSES == 3) {
-          tma_load_3d(kbuf + AT_TILE, &tm_lo, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
-          tma_load_3d(vbuf + AT_TILE, &tm_lo, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
-        }
-        if (++stage == KV_STAGES) {
-          stage = 0;
-          phase ^= 1;
+      uint32_t phase = 0, it = 0;
+      for (int t = blockIdx.x; t < p.n_tiles; t += gridDim.x, ++it) {
+        int q0, h, b;
+        tile_coords(t, q0, h, b);
+        const int nchunks = (tile_kv_len(b) + AT_BN - 1) / AT_BN;
+        mbar_wait(q_empty, (it & 1) ^ 1);      // the last Q K^T of the previous tile has read the Q buffer
+        mbar_arrive_expect_tx(q_full, S::NPL * AT_TILE);
+        tma_load_3d(smem + S::Q_OFF, &tm_hi, q_full, h * AT_DH, q0, b);
+        if (PASSES == 3) tma_load_3d(smem + S::Q_OFF + AT_TILE, &tm_lo, q_full, h * AT_DH, q0, b);
+        for (int j = 0; j < nchunks; ++j) {
+          mbar_wait(&kv_empty[stage], phase ^ 1);
+          uint8_t* kbuf = smem + S::KV_OFF + stage * S::KV_STAGE_BYTES;
+          uint8_t* vbuf = kbuf + S::NPL * AT_TILE;
+          mbar_arrive_expect_tx(&kv_full[stage], S::KV_STAGE_BYTES);
+          tma_load_3d(kbuf, &tm_hi, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
+          tma_load_3d(vbuf, &tm_hi, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
+          if (PASSES == 3) {
+            tma_load_3d(kbuf + AT_TILE, &tm_lo, &kv_full[stage], p.d + h * AT_DH, j * AT_BN, b);
+            tma_load_3d(vbuf + AT_TILE, &tm_lo, &kv_full[stage], 2 * p.d + h * AT_DH, j * AT_BN, b);
+          }
+          if (++stage == KV_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -169,8 +205,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
       constexpr uint32_t idesc_pv = idesc_16bit(FP16, AT_BM, AT_DH, 0, 1);  // PV: A = P K-major, B = V MN-major
       const uint32_t q_addr = smem_u32(smem + S::Q_OFF);
       const uint32_t p_addr = smem_u32(smem + S::P_OFF);
-      mbar_wait(q_full, 0);
-      auto issue_qk = [&](int stage) {
+      auto chunks_of = [&](int t) {
+        int q0, h, b;
+        tile_coords(t, q0, h, b);
+        return (tile_kv_len(b) + AT_BN - 1) / AT_BN;
+      };
+      // Q K^T of one chunk; `last_of_tile`: the Q buffer may be refilled once these MMAs have retired
+      auto issue_qk = [&](int stage, bool last_of_tile) {
         const uint32_t k_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES);
 #pragma unroll
         for (int pass = 0; pass < PASSES; ++pass) {
@@ -181,49 +222,74 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
           for (int k = 0; k < AT_DH / 16; ++k) umma_f16(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, (pass | k) != 0);
         }
         umma_commit(s_full);
+        if (last_of_tile) umma_commit(q_empty);
       };
-      // kv stage of chunk j is j % KV_STAGES with phase (j / KV_STAGES) & 1
-      mbar_wait(&kv_full[0], 0);
-      tc_fence_after();
-      issue_qk(0);
-      for (int j = 0; j < nchunks; ++j) {
-        const uint32_t par = j & 1;
-        const int stage = j % KV_STAGES;
-        const uint32_t v_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES) + S::NPL * AT_TILE;
-        if (j + 1 < nchunks) {
-          // S(j) has been copied to registers -> overwrite it with Q K(j+1)^T while the softmax math runs
-          const int nstage = (j + 1) % KV_STAGES;
-          mbar_wait(&kv_full[nstage], ((j + 1) / KV_STAGES) & 1);
-          mbar_wait(s_empty, par);
-          tc_fence_after();
-          issue_qk(nstage);
-        }
-        // ---- O += P V
-        mbar_wait(p_full, par);
+      // The chunks of all tiles of this CTA form ONE sequence g = 0, 1, ...: chunk g lives in K/V stage g % KV_STAGES, its
+      // S / P hand-shakes complete phase g & 1.  Iteration g issues Q K^T of chunk g + 1 (possibly the first chunk of the
+      // NEXT tile, with that tile's Q) and then P V of chunk g.
+      int stage = 0;                 // K/V stage of chunk g
+      uint32_t kv_phase = 0;         // ... and its ring phase
+      uint32_t g = 0, it = 0;
+      int t = blockIdx.x;
+      int nchunks = (t < p.n_tiles) ? chunks_of(t) : 0;
+      if (t < p.n_tiles) {
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
         tc_fence_after();
-        if (P_IN_TMEM) {
-          // single-pass mode: P was written to TMEM columns [192, 256) by tcgen05.st (two bf16 per column) and is the A operand
-#pragma unroll
-          for (int ks = 0; ks < AT_BN / 16; ++ks) {
-            const uint64_t dv = desc_mnmajor_sw128(v_addr + ks * 2048, 1024, 1024);
-            umma_f16_tmem_a(tmem_o, tmem_p + ks * 8, dv, idesc_pv, (j | ks) != 0);
+        issue_qk(0, nchunks == 1);
+      }
+      for (; t < p.n_tiles; t += gridDim.x, ++it) {
+        const int t_next = t + gridDim.x;
+        const int nchunks_next = (t_next < p.n_tiles) ? chunks_of(t_next) : 0;
+        for (int j = 0; j < nchunks; ++j, ++g) {
+          const uint32_t par = g & 1;
+          const uint32_t v_addr = smem_u32(smem + S::KV_OFF + stage * S::KV_STAGE_BYTES) + S::NPL * AT_TILE;
+          int nstage = stage + 1;
+          uint32_t nphase = kv_phase;
+          if (nstage == KV_STAGES) {
+            nstage = 0;
+            nphase ^= 1;
           }
-        } else {
-#pragma unroll
-          for (int pass = 0; pass < PASSES; ++pass) {
-            const uint32_t pa = p_addr + ((pass == 1) ? 2 * AT_TILE : 0);
-            const uint32_t va = v_addr + ((pass == 2) ? AT_TILE : 0);
+          const bool same_tile = j + 1 < nchunks;
+          if (same_tile || nchunks_next > 0) {
+            // S(g) has been copied to registers -> overwrite it with Q K(g+1)^T while the softmax math runs
+            if (!same_tile) mbar_wait(q_full, (it + 1) & 1);   // first chunk of the next tile: its Q has landed
+            mbar_wait(&kv_full[nstage], nphase);
+            mbar_wait(s_empty, par);
+            tc_fence_after();
+            issue_qk(nstage, same_tile ? (j + 2 == nchunks) : (nchunks_next == 1));
+          }
+          // ---- O += P V   (the first MMA of a tile overwrites O: the softmax warps finished reading the previous tile's O
+          //                  before they arrived on p_full for this chunk)
+          mbar_wait(p_full, par);
+          tc_fence_after();
+          if (P_IN_TMEM) {
+            // single-pass mode: P was written to TMEM columns [192, 256) by tcgen05.st (two bf16 per column) and is the A operand
 #pragma unroll
             for (int ks = 0; ks < AT_BN / 16; ++ks) {
-              const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
-              const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
-              umma_f16(tmem_o, dp, dv, idesc_pv, (j | pass | ks) != 0);
+              const uint64_t dv = desc_mnmajor_sw128(v_addr + ks * 2048, 1024, 1024);
+              umma_f16_tmem_a(tmem_o, tmem_p + ks * 8, dv, idesc_pv, (j | ks) != 0);
+            }
+          } else {
+#pragma unroll
+            for (int pass = 0; pass < PASSES; ++pass) {
+              const uint32_t pa = p_addr + ((pass == 1) ? 2 * AT_TILE : 0);
+              const uint32_t va = v_addr + ((pass == 2) ? AT_TILE : 0);
+#pragma unroll
+              for (int ks = 0; ks < AT_BN / 16; ++ks) {
+                const uint64_t dp = desc_kmajor_sw128(pa + (ks >> 2) * AT_TILE) + 2 * (ks & 3);
+                const uint64_t dv = desc_mnmajor_sw128(va + ks * 2048, 1024, 1024);
+                umma_f16(tmem_o, dp, dv, idesc_pv, (j | pass | ks) != 0);
+              }
             }
           }
+          umma_commit(pv_done);
+          umma_commit(p_empty);
+          umma_commit(&kv_empty[stage]);
+          stage = nstage;
+          kv_phase = nphase;
         }
-        umma_commit(pv_done);
-        umma_commit(p_empty);
-        umma_commit(&kv_empty[stage]);
+        nchunks = nchunks_next;
       }
     }
   }
@@ -238,17 +304,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     uint8_t* p_lo = p_hi + 2 * AT_TILE;
     const uint32_t row_off = (uint32_t)r * 128u;
     const uint32_t swz = (uint32_t)(r & 7);
-    float m_used = -INFINITY;   // max the exponent is taken against (may lag the true running max by < 2^8)
-    float l_run = 0.0f;
     const uint32_t s_addr = tmem_s + lane_sel;
     const uint32_t o_addr = tmem_o + lane_sel;
+    uint32_t g = 0;             // chunk counter across the tiles of this CTA: the S / P hand-shakes of chunk g complete phase g & 1
 
-    for (int j = 0; j < nchunks; ++j) {
-      const uint32_t par = j & 1;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int q0, h, b;
+    tile_coords(tile, q0, h, b);
+    const int kv_len = tile_kv_len(b);
+    const int nchunks = (kv_len + AT_BN - 1) / AT_BN;
+    float m_used = -INFINITY;   // max the exponent is taken against (may lag the true running max by < 2^8)
+    float l_run = 0.0f;
+    STAMP(tile, 0);
+#ifdef AT_STAMPS
+    if (threadIdx.x == 0 && tile < 4096) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_attn_stamps[tile * 32 + 15] = sm; }
+#endif
+    for (int j = 0; j < nchunks; ++j, ++g) {
+      const uint32_t par = g & 1;
       const int key0 = j * AT_BN;
       const bool partial = key0 + AT_BN > kv_len;
       uint32_t sr[4][32];   // the whole S row of this chunk
       mbar_wait(s_full, par);
+      if (j < 6) STAMP(tile, 3 + j);
       tc_fence_after();
 #pragma unroll
       for (int pc = 0; pc < 4; ++pc) tmem_ld_32x32b_x32(s_addr + pc * 32, sr[pc]);
@@ -381,7 +458,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     }
 
     // ---- epilogue: O / l
-    mbar_wait(pv_done, (nchunks - 1) & 1);
+    STAMP(tile, 9);
+    mbar_wait(pv_done, (g - 1) & 1);
+    STAMP(tile, 10);
     tc_fence_after();
     const int t = q0 + r;
     // O sits at the scale of v (2^4 in the fp16 modes); the fp16 output planes want value * 2^4 again
@@ -426,6 +505,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
         }
       }
     }
+    tc_fence_before();   // the O reads above are ordered before this thread's next p_full arrive (-> next tile's first P V)
+    STAMP(tile, 11);
+    }  // tiles
   }
   }
 
@@ -460,10 +542,18 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
   p.drop = drop;
   p.H = H;
   p.out_format = out_format;
+  p.q_tiles = (T + AT_BM - 1) / AT_BM;
+  p.n_tiles = p.q_tiles * H * B;
   auto kern = attn_fwd_kernel<PASSES, FP16>;
   static unsigned long long smem_attr_done = 0;   // per template instantiation, one bit per device
   W2V2_CUDA(ensure_dyn_smem(kern, S::TOTAL, smem_attr_done));
-  dim3 grid((T + AT_BM - 1) / AT_BM, H, B);
+  int dev = 0, sms = 0;
+  W2V2_CUDA(cudaGetDevice(&dev));
+  W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  // persistent: one CTA per residency slot (W2V2_ATTN_PERSIST=0: one tile per CTA, the hardware scheduler hands them out)
+  static const bool persist = [] { const char* e = getenv("W2V2_ATTN_PERSIST"); return e ? atoi(e) != 0 : true; }();
+  const int resident = persist ? sms * ((PASSES == 1) ? 2 : 1) : p.n_tiles;
+  dim3 grid(p.n_tiles < resident ? p.n_tiles : resident);
   W2V2_CUDA(launch_pdl(kern, grid, dim3(AT_THREADS), (size_t)S::TOTAL, stream, 0, tm_hi, tm_lo, p));
   return 0;
 }
@@ -511,3 +601,9 @@ extern "C" int w2v2_attn_fwd_train(const void* qkv_hi, const void* qkv_lo, int b
   return attn_fwd_impl(qkv_hi, qkv_lo, batch, frames, num_heads, head_size, kv_len, out_hi, out_lo, passes,
                        (passes & 16) ? 1 : 0, w2v2::make_drop(drop_p, seed, site), stream);
 }
+
+#ifdef AT_STAMPS
+extern "C" int w2v2_attn_debug_stamps(unsigned long long* host_out, int n) {
+  return (int)cudaMemcpyFromSymbol(host_out, w2v2::g_attn_stamps, sizeof(unsigned long long) * n);
+}
+#endif
