@@ -466,11 +466,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_hi, const __grid_constant
     // O sits at the scale of v (2^4 in the fp16 modes); the fp16 output planes want value * 2^4 again
     const float inv = (1.0f / l_run) * ((FP16 ? 1.0f / ACT_SCALE : 1.0f) * (p.out_format != 0 ? ACT_SCALE : 1.0f));
     const size_t off = ((size_t)b * p.T + t) * p.d + (size_t)h * AT_DH;
+    uint32_t ro[2][32];          // both halves of the O row in flight, one wait
+    tmem_ld_32x32b_x32(o_addr, ro[0]);
+    tmem_ld_32x32b_x32(o_addr + 32, ro[1]);
+    tmem_ld_wait();
 #pragma unroll
     for (int piece = 0; piece < 2; ++piece) {
-      uint32_t rr[32];
-      tmem_ld_32x32b_x32(o_addr + piece * 32, rr);
-      tmem_ld_wait();
+      uint32_t (&rr)[32] = ro[piece];
       if (t < p.T) {
         if (p.out_format == 2) {
           // fp16 plane + e4m3 pair plane: this head's 64 columns are one 128-byte group of the byte plane [rows][2 d]
