@@ -252,28 +252,37 @@ conv0_kernel(const float* __restrict__ wave, int L, int T0, int C, const float* 
 // registers), optional GELU, outputs fp32 and/or bf16 hi(/lo).  One warp per row, float4 accesses.
 // EXACT: d == 128 * MAXV (every lane owns exactly MAXV float4: 512 / 768 / 1024 channels) - no bounds predicates.
 template <int MAXV, bool EXACT = false>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (MAXV <= 6) ? 3 : (MAXV <= 8) ? 2 : 1)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                int rows, int d, int gelu, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
                __nv_bfloat16* __restrict__ out_lo, float* __restrict__ stats, int out_format) {
   pdl_trigger();
   pdl_wait();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // Persistent over rows: warp w of the grid takes rows w, w + W, ... and fetches its NEXT row before it reduces the current
+  // one, so every warp keeps two rows (2 x 4 d bytes) in flight - a grid of one-row warps drains and refills the SM instead.
   const int lane = lane_id();
   const int nvec = d >> 2;
-  const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * d);
+  const int wstride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 nx[MAXV];
+  {
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * d);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) nx[i] = (EXACT || lane + 32 * i < nvec) ? __ldg(xp + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (; row < rows; row += wstride) {
   float4 v[MAXV];
   float s = 0.0f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int idx = lane + 32 * i;
-    if (EXACT || idx < nvec) {
-      v[i] = __ldg(xp + idx);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-    } else {
-      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    v[i] = nx[i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  if (row + wstride < rows) {
+    const float4* xn = reinterpret_cast<const float4*>(x + (size_t)(row + wstride) * d);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) nx[i] = (EXACT || lane + 32 * i < nvec) ? __ldg(xn + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float mean = warp_sum(s) / (float)d;
   float q = 0.0f;
@@ -329,6 +338,7 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       }
     }
   }
+  }  // rows of this warp
 }
 
 // ------------------------------------------------------------------------------------ LayerNorm statistics from partial sums
@@ -498,19 +508,33 @@ extern "C" int w2v2_ln_rows_ex(const float* x, const float* gamma, const float* 
   W2V2_CHECK_ARG(out_lo == nullptr || out_hi != nullptr, "out_lo requires out_hi");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
   auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
   auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
-  if (d == 512)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<4, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
-  else if (d == 768)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<6, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
-  else if (d == 1024)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<8, true>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
-  else if (d <= 1024)
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<8>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
-  else
-    W2V2_CUDA(launch_pdl(ln_rows_kernel<16>, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, stats, out_format));
+#define LN_LAUNCH(MAXV, EXACT)                                                                                          \
+  do {                                                                                                                  \
+    auto kern = ln_rows_kernel<MAXV, EXACT>;                                                                            \
+    static int resident[64] = {0}; /* persistent grid = resident CTAs of this instantiation, per device */              \
+    int dev = 0;                                                                                                        \
+    W2V2_CUDA(cudaGetDevice(&dev));                                                                                     \
+    if (resident[dev & 63] == 0) {                                                                                      \
+      int sms = 0, per_sm = 0;                                                                                          \
+      W2V2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));                                     \
+      W2V2_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));                                  \
+      const char* e = getenv("W2V2_LN_CTAS_PER_SM"); /* A/B switch; 999 = one row per warp */                           \
+      if (e && atoi(e) > 0) per_sm = atoi(e);                                                                           \
+      resident[dev & 63] = sms * (per_sm > 0 ? per_sm : 1);                                                             \
+    }                                                                                                                   \
+    const long long want = (rows + 7) / 8;                                                                              \
+    const unsigned grid = (unsigned)(want < resident[dev & 63] ? want : resident[dev & 63]);                            \
+    W2V2_CUDA(launch_pdl(kern, dim3(grid), dim3(256), 0, s, 0, x, gamma, beta, eps, (int)rows, d, gelu, out_f32, hi, lo, \
+                         stats, out_format));                                                                           \
+  } while (0)
+  if (d == 512) LN_LAUNCH(4, true);
+  else if (d == 768) LN_LAUNCH(6, true);
+  else if (d == 1024) LN_LAUNCH(8, true);
+  else if (d <= 1024) LN_LAUNCH(8, false);
+  else LN_LAUNCH(16, false);
+#undef LN_LAUNCH
   return 0;
 }
 
