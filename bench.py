@@ -747,6 +747,7 @@ def profile_classes(model, x, cfg, steps):
     wrap("conv0", lambda *a, **kw: "conv0")
     wrap("conv0_im2col", lambda *a, **kw: "conv0")
     wrap("conv0_gn_gelu", lambda *a, **kw: "conv0")
+    wrap("conv0_ln_gelu", lambda *a, **kw: "conv0")
     wrap("wave_stats", lambda *a, **kw: "conv0 stats+fold")
     wrap("conv0_fold", lambda *a, **kw: "conv0 stats+fold")
     wrap("ln_rows", lambda *a, **kw: "layernorm")

@@ -14,6 +14,10 @@
 //    outputs leave as 16-byte stores, a quad writes 64 contiguous bytes, no shuffles, no smem transpose;
 //  * PASSES == 3 (parity mode): x and w as bf16 hi+lo planes, 3 MMAs, erf-exact GELU, hi+lo outputs;
 //    PASSES == 1 (throughput mode): single MMA, tanh-form GELU (|err| < 5e-4, below bf16 resolution), hi output.
+//  * LN (the "layer"-norm extractor of the robust / large checkpoints, feature_extractor.py:48-50): the normalisation runs over
+//    the 512 CHANNELS of a frame, and a CTA holds all of them for its 256 frames - the row statistics are two block reductions
+//    per 16-frame m-tile (quad shuffle, 8 warp partials through smem; two-pass: mean, then centred squares) and the fp32
+//    conv output (1.6 GB written and read back by w2v2_ln_rows at 16 x 246000) never exists.
 #include "host_util.h"
 #include "w2v2_common.cuh"
 #include "../../include/w2v2.h"
@@ -34,14 +38,17 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
 // TF_APPROX: tf.nn.gelu(approximate=True), the reference's is_gelu_approx switch.  OUT_FMT (w2v2.h W2V2_OUT_*): 0 = bf16 hi
 // (+ lo when PASSES == 3), 1 = fp16 plane of value * 2^4, 2 = fp16 plane + e4m3 pair plane (fp16f8 mode); formats 1 / 2 always
 // run the 3-MMA window product (the kernel is HBM-bound, the extra MMAs are free) and the erf-exact GELU.
-template <int PASSES, bool TF_APPROX = false, int OUT_FMT = 0>
+// LN: scale = gamma [512], shift = beta [512] (no batch axis), cbias = conv bias [512] or null, eps = LayerNorm epsilon
+template <int PASSES, bool TF_APPROX = false, int OUT_FMT = 0, bool LN = false>
 __global__ void __launch_bounds__(256, 2)
 conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __restrict__ kernel /*[10][512]*/,
                  const float* __restrict__ scale /*[B][512]*/, const float* __restrict__ shift /*[B][512]*/,
-                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+                 __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                 const float* __restrict__ cbias = nullptr, float eps = 0.0f) {
   constexpr int NPLANES = (PASSES == 3) ? 2 : 1;
   // xs[plane][copy][i]: copy 0 = samples, copy 1 = samples shifted by one (xs[.][1][i] = x[i + 1])
   __shared__ __align__(16) __nv_bfloat16 xs[NPLANES][2][CM_NS];
+  __shared__ float red[LN ? 2 : 1][8][16];     // LN: [pass][warp][row of the m-tile] partial sums
   const int b = blockIdx.y;
   const int t_base = blockIdx.x * CM_TT;
   const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -93,8 +100,9 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int co = wbase + 32 * (i >> 2) + 8 * q + 2 * (i & 3);
-    const float2 s2 = __ldg(reinterpret_cast<const float2*>(scale + (size_t)b * CM_C + co));
-    const float2 h2 = __ldg(reinterpret_cast<const float2*>(shift + (size_t)b * CM_C + co));
+    const size_t bo = LN ? 0 : (size_t)b * CM_C;
+    const float2 s2 = __ldg(reinterpret_cast<const float2*>(scale + bo + co));
+    const float2 h2 = __ldg(reinterpret_cast<const float2*>(shift + bo + co));
     sc[i] = pack2(s2.x, s2.y);
     sh[i] = pack2(h2.x, h2.y);
   }
@@ -125,11 +133,75 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.0f;
+      if (LN && cbias != nullptr) {     // conv bias (config.conv_bias): the accumulators start from it
+        const float2 cb = __ldg(reinterpret_cast<const float2*>(cbias + wbase + 32 * (i >> 2) + 8 * q + 2 * (i & 3)));
+        acc[i][0] = acc[i][2] = cb.x;
+        acc[i][1] = acc[i][3] = cb.y;
+      }
       if (PASSES == 3) {
         mma_bf16_16816(acc[i], al, bh[i][0], bh[i][1]);
         mma_bf16_16816(acc[i], ah, bl[i][0], bl[i][1]);
       }
       mma_bf16_16816(acc[i], ah, bh[i][0], bh[i][1]);
+    }
+    if constexpr (LN) {
+      // LayerNorm over the 512 channels of rows g and g + 8 (biased variance, two-pass like w2v2_ln_rows)
+      float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        s0 += acc[i][0] + acc[i][1];
+        s1 += acc[i][2] + acc[i][3];
+      }
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      if (q == 0) {
+        red[0][warp][g] = s0;
+        red[0][warp][g + 8] = s1;
+      }
+      __syncthreads();
+      float m0 = 0.0f, m1 = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        m0 += red[0][w][g];
+        m1 += red[0][w][g + 8];
+      }
+      m0 *= 1.0f / CM_C;
+      m1 *= 1.0f / CM_C;
+      float q0 = 0.0f, q1 = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] -= m0;
+        acc[i][1] -= m0;
+        acc[i][2] -= m1;
+        acc[i][3] -= m1;
+        q0 += acc[i][0] * acc[i][0] + acc[i][1] * acc[i][1];
+        q1 += acc[i][2] * acc[i][2] + acc[i][3] * acc[i][3];
+      }
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 1);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+      q0 += __shfl_xor_sync(0xffffffffu, q0, 2);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, 2);
+      if (q == 0) {
+        red[LN ? 1 : 0][warp][g] = q0;
+        red[LN ? 1 : 0][warp][g + 8] = q1;
+      }
+      __syncthreads();   // (the next m-tile's first partials go to red[0], read by everybody before this barrier)
+      float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        v0 += red[LN ? 1 : 0][w][g];
+        v1 += red[LN ? 1 : 0][w][g + 8];
+      }
+      const float r0 = rsqrtf(v0 * (1.0f / CM_C) + eps), r1 = rsqrtf(v1 * (1.0f / CM_C) + eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i][0] *= r0;
+        acc[i][1] *= r0;
+        acc[i][2] *= r1;
+        acc[i][3] *= r1;
+      }
     }
     uint32_t oh[2][8], ol[(PASSES == 3) ? 2 : 1][8];
 #pragma unroll
@@ -217,15 +289,40 @@ extern "C" int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples,
   if (passes == 17 || passes == 25) {
     auto kern = passes == 17 ? (gelu_approx ? conv0_mma_kernel<3, true, 1> : conv0_mma_kernel<3, false, 1>)
                              : (gelu_approx ? conv0_mma_kernel<3, true, 2> : conv0_mma_kernel<3, false, 2>);
-    W2V2_CUDA(launch_pdl(kern, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+    W2V2_CUDA(launch_pdl(kern, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo, (const float*)nullptr, 0.0f));
   } else if (gelu_approx) {
     if (passes == 1)
-      W2V2_CUDA(launch_pdl(conv0_mma_kernel<1, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+      W2V2_CUDA(launch_pdl(conv0_mma_kernel<1, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo, (const float*)nullptr, 0.0f));
     else
-      W2V2_CUDA(launch_pdl(conv0_mma_kernel<3, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+      W2V2_CUDA(launch_pdl(conv0_mma_kernel<3, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo, (const float*)nullptr, 0.0f));
   } else if (passes == 1)
-    W2V2_CUDA(launch_pdl(conv0_mma_kernel<1>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+    W2V2_CUDA(launch_pdl(conv0_mma_kernel<1>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo, (const float*)nullptr, 0.0f));
   else
-    W2V2_CUDA(launch_pdl(conv0_mma_kernel<3>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo));
+    W2V2_CUDA(launch_pdl(conv0_mma_kernel<3>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, scale, shift, hi, lo, (const float*)nullptr, 0.0f));
+  return 0;
+}
+
+extern "C" int w2v2_conv0_ln_gelu(const float* wave, int batch, int num_samples, int channels, const float* kernel,
+                                  const float* conv_bias, const float* gamma, const float* beta, float eps, void* out_hi,
+                                  void* out_lo, int passes, int gelu_approx, void* stream) {
+  W2V2_CHECK_ARG(wave && kernel && gamma && beta && out_hi, "null pointer");
+  W2V2_CHECK_ARG(channels == CM_C, "extractor layer 0 is built for 512 output channels");
+  W2V2_CHECK_ARG(batch > 0 && num_samples >= 10, "need batch > 0 and at least 10 samples");
+  W2V2_CHECK_ARG(passes == 1 || passes == 3 || passes == 17 || passes == 25, "passes must be 1, 3, 17 (fp16) or 25 (fp16f8)");
+  W2V2_CHECK_ARG((passes == 3 || passes == 25) == (out_lo != nullptr), "out_lo is written exactly in the two-plane modes (3, 25)");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int T0 = 1 + (num_samples - 10) / 5;
+  dim3 grid((T0 + CM_TT - 1) / CM_TT, batch);
+  auto* hi = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  auto* lo = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  // the LayerNorm output feeds a GELU of unit-variance arguments: every mode takes the erf-exact (or tf-approximate) form,
+  // the bf16 mode keeps its single MMA
+#define C0LN(P, A, F) W2V2_CUDA(launch_pdl(conv0_mma_kernel<P, A, F, true>, grid, dim3(256), 0, s, 0, wave, num_samples, T0, kernel, \
+                                           gamma, beta, hi, lo, conv_bias, eps))
+  if (passes == 17) { if (gelu_approx) C0LN(3, true, 1); else C0LN(3, false, 1); }
+  else if (passes == 25) { if (gelu_approx) C0LN(3, true, 2); else C0LN(3, false, 2); }
+  else if (passes == 1) { if (gelu_approx) C0LN(1, true, 0); else C0LN(1, false, 0); }
+  else { if (gelu_approx) C0LN(3, true, 0); else C0LN(3, false, 0); }
+#undef C0LN
   return 0;
 }

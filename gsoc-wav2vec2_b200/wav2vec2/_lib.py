@@ -72,6 +72,7 @@ SIGNATURES = {
     "w2v2_conv0_fold": [_P, _P, _P, _P, _I, _I, _I, _F, _P, _P, _P, _P],
     "w2v2_conv0_im2col": [_P, _I, _I, _P, _P, _P],
     "w2v2_conv0_gn_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _P, _I, _I, _P],
+    "w2v2_conv0_ln_gelu": [_P, _I, _I, _I, _P, _P, _P, _P, _F, _P, _P, _I, _I, _P],
     "w2v2_conv0": [_P, _I, _I, _I, _P, _I, _P, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P],
     "w2v2_ln_rows_stats": [_P, _P, _P, _F, _L, _I, _I, _P, _P, _P, _P, _P],

@@ -452,12 +452,12 @@ class _B200Model:
                            1e-5, scale=fs)
             ops.conv0_gn_gelu(x, P["conv0.w"], fs, fb, act, passes, gelu_approx=approx)
         else:
-            raw_elems = max(B * t * c for t, c in zip(frames, cfg.filter_sizes))
+            raw_elems = max([B * t * c for t, c in zip(frames[1:], cfg.filter_sizes[1:])] or [1])
             raw_flat = A.get("conv.raw", (raw_elems,), f32)   # pre-norm conv output, reused by every layer
-            raw = raw_flat[: B * T0 * C0].view(B * T0, C0)
-            ops.conv0(x, P["conv0.w"], 0, v.get(fe + "0/conv/bias") if cfg.conv_bias else None, 0, False, out_f32=raw, channels=C0)
-            ops.ln_rows(raw, v[fe + "0/layer_norm/gamma"], v[fe + "0/layer_norm/beta"], 1e-5, B * T0, C0, gelu=ln_gelu,
-                        out_hi=act.hi, out_lo=act.lo, out_format=ofmt)
+            # conv + bias + LayerNorm over the 512 channels + GELU in one kernel: a CTA holds every channel of its frames, the
+            # fp32 conv output (the largest tensor of the robust forward) is never written
+            ops.conv0_ln_gelu(x, P["conv0.w"], v.get(fe + "0/conv/bias") if cfg.conv_bias else None, v[fe + "0/layer_norm/gamma"],
+                              v[fe + "0/layer_norm/beta"], 1e-5, act, passes, gelu_approx=approx)
         # ---- extractor layers 1.. as implicit GEMMs
         last_f32 = None
         for i in range(1, nconv):

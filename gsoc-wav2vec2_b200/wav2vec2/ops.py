@@ -139,6 +139,17 @@ def conv0_gn_gelu(wave, kernel, scale, shift, out: Pair, passes=1, gelu_approx=F
                          "w2v2_conv0_gn_gelu")
 
 
+def conv0_ln_gelu(wave, kernel, conv_bias, gamma, beta, eps, out: Pair, passes=1, gelu_approx=False):
+    """Layer 0 of the layer-norm extractor in one kernel: conv (+ bias) + LayerNorm over the channels + GELU -> operand planes."""
+    _need_cuda(wave, kernel, conv_bias, gamma, beta, out.hi)
+    B, L = wave.shape
+    two = passes in (3, 25)
+    _count(); _lib.check(_lib.load().w2v2_conv0_ln_gelu(_ptr(wave), B, L, kernel.shape[-1], _ptr(kernel), _ptr(conv_bias),
+                                              _ptr(gamma), _ptr(beta), float(eps), _ptr(out.hi),
+                                              _ptr(out.lo) if two else None, passes, 1 if gelu_approx else 0, _stream()),
+                         "w2v2_conv0_ln_gelu")
+
+
 def conv0(wave, weights, w_batch_stride, bias, b_batch_stride, gelu, out_f32=None, out_hi=None, out_lo=None,
           channels=512):
     _need_cuda(wave, weights, bias, out_f32, out_hi, out_lo)

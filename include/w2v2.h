@@ -161,6 +161,13 @@ int w2v2_conv0_gn_gelu(const float* wave, int batch, int num_samples, int channe
                        const float* scale /*[batch][C]*/, const float* shift /*[batch][C]*/, void* out_hi,
                        void* out_lo /*NULL unless passes == 3*/, int passes,
                        int gelu_approx /*0: erf GELU (config.py:14 default); 1: tf.nn.gelu(approximate=True)*/, void* stream);
+/* Fused layer 0 of the "layer"-norm extractor (robust / large checkpoints: feature_extractor.py:48-50,54-59 with
+ * config.feature_extractor_norm_type == "layer"): out = gelu(LayerNorm_c(conv(wave)[b][t][:] + conv_bias) * gamma + beta), the
+ * LayerNorm over the 512 channels of a frame (biased variance, two-pass, eps) computed inside the CTA that holds them - replaces
+ * w2v2_conv0 (fp32 output) + w2v2_ln_rows.  Same planes / passes / gelu_approx as w2v2_conv0_gn_gelu. */
+int w2v2_conv0_ln_gelu(const float* wave, int batch, int num_samples, int channels, const float* kernel /*[10][C]*/,
+                       const float* conv_bias /*[C] or NULL*/, const float* gamma /*[C]*/, const float* beta /*[C]*/, float eps,
+                       void* out_hi, void* out_lo /*NULL unless passes == 3 or 25*/, int passes, int gelu_approx, void* stream);
 int w2v2_conv0(const float* wave, int batch, int num_samples, int channels, const float* weights,
                int weights_batch_stride, const float* bias /*or NULL*/, int bias_batch_stride, int gelu,
                float* out_f32, void* out_hi, void* out_lo, void* stream);

@@ -232,6 +232,34 @@ def test_conv0_fused(passes, L):
 
 
 @pytest.mark.parametrize("passes", [1, 3])
+@pytest.mark.parametrize("L,bias", [(20011, True), (1285, False), (14, True)])
+def test_conv0_layernorm_fused(passes, L, bias):
+    """Layer 0 of the layer-norm extractor in one kernel (w2v2_conv0_ln_gelu): conv (+ bias), LayerNorm over the 512 channels of a
+    frame inside the CTA, GELU (feature_extractor.py:48-50,54-59).  Checked against the oracle's conv -> layer_norm -> gelu."""
+    torch.manual_seed(11)
+    B, C = 3, 512
+    lo = passes == 3
+    x = torch.randn(B, L)
+    x[1] = x[1] * 0.3 + 0.05
+    kern = torch.randn(10, 1, C) * 0.3
+    cb = 0.2 * torch.randn(C) if bias else None
+    gamma, beta = 1 + 0.1 * torch.randn(C), 0.1 * torch.randn(C)
+    ref = O.gelu_erf(O.layer_norm(O.conv1d_valid(x[:, :, None], kern, cb, stride=5), gamma, beta, 1e-5))
+    T0 = ref.shape[1]
+    guard = 64
+    hi = torch.full((B * T0 + guard, C), 7.0, dtype=torch.bfloat16, device=DEV)
+    lo_t = torch.full((B * T0 + guard, C), 7.0, dtype=torch.bfloat16, device=DEV) if lo else None
+    ops.conv0_ln_gelu(x.to(DEV), kern.reshape(10, C).to(DEV), None if cb is None else cb.to(DEV), gamma.to(DEV), beta.to(DEV),
+                      1e-5, Pair(hi, lo_t), passes)
+    torch.cuda.synchronize()
+    got = (hi.float() + (lo_t.float() if lo else 0))[: B * T0].view(B, T0, C).cpu()
+    err = (got - ref).abs().max().item()
+    print(f"conv0 + LayerNorm fused L={L} passes={passes} bias={bias}: max err {err:.3e} (|ref| max {ref.abs().max():.2f})")
+    assert err < (0.08 if passes == 1 else 3e-4)
+    assert torch.all(hi[B * T0:].float() == 7.0)
+
+
+@pytest.mark.parametrize("passes", [1, 3])
 @pytest.mark.parametrize("T", [145, 768, 49])
 def test_attention(passes, T):
     torch.manual_seed(5)
