@@ -546,7 +546,9 @@ def main():
                 "d2h_bytes_per_step": out_host.numel() * 4},
         "gpu_launches": launches,
         "model_tflops": fl["total"] * B * world / (ms / K / 1e3) / 1e12,
-        "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}] + bias + GELU",
+        "roofline": {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05 FFN1 [{B * T}x{cfg.hidden_size}]x[{cfg.hidden_size}x{cfg.intermediate_size}]"
+                                                   + (" + folded LayerNorm (mean / rstd applied in the epilogue)" if getattr(model, "_fold", False) else "")
+                                                   + " + bias + GELU",
                      "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": (achieved / peaks["bf16_tflops"]) if achieved else None,
                      "traffic": traffic.get("ffn1_gemm_bytes_per_launch") if (B, L) == (32, 246000) else None,

@@ -372,11 +372,12 @@ class _B200Model:
             P[f"l{i}.ff2.w"] = _split(v[ff + "output_dense/kernel"].t(), lo)
         # LayerNorm folded into the Dense that follows it (QKV of layers >= 1 and every FFN1; include/w2v2.h ln_fold_*):
         #   LN(x) W + b = rstd (x (gamma o W)) - rstd mean colsum(gamma o W) + (beta W + b)
-        # OFF by default (W2V2_LN_FOLD=1 enables it): measured at B = 32 x 246000 it removes 0.63 ms of LayerNorm passes per step and
-        # gives 0.55 ms back to the epilogue-bound K = 768 GEMMs (FFN1 1.16 -> 1.29 ms, QKV 0.91 -> 0.95, residual GEMMs +0.2 for the
-        # extra planes / statistics): a ~1 % step gain that takes FFN1 / QKV from 0.70 - 0.76 to 0.62 - 0.69 of the tensor peak.
+        # ON by default (W2V2_LN_FOLD=0 disables it).  Same-box A/B at B = 32 x 246000 after the LayerNorm kernel became persistent:
+        # 8.58 - 8.66 -> 8.28 - 8.44 ms per step (large model 12.1 - 12.3 -> 11.5 - 11.7): the `layernorm` class drops from 0.66 to
+        # 0.08 ms (only the LayerNorms after the extractor / positional conv and the final one remain), the consuming GEMMs pay for it
+        # in their epilogue (FFN1 0.72 -> 0.66 of the tensor peak, QKV 0.70 -> 0.68) and the residual GEMMs write one more plane.
         self._fold = (self.precision != "bf16x3" and cfg.hidden_size % 64 == 0 and cfg.num_layers > 0
-                      and os.environ.get("W2V2_LN_FOLD", "0") == "1")
+                      and os.environ.get("W2V2_LN_FOLD", "1") == "1")
         if self._fold:
             pre = cfg.attention_norm_type == "prenorm"
             for i in range(cfg.num_layers):
