@@ -480,6 +480,7 @@ def main():
     # ---------------- per-kernel-class device times (CUDA events on the launching stream)
     model.enable_cuda_graph(False)             # per-kernel events need the eager launch sequence
     breakdown_eager, gemm_ffn1 = profile_classes(model, x, cfg, steps=min(K, 5))
+    base_launches = dict(_CLASS_LAUNCHES)
 
     # ---------------- the parity-green mode, timed on the same workload: precision="bf16x3" (the drop-in default)
     sub = {}
@@ -559,7 +560,8 @@ def main():
     # (eager launches lose the PDL overlap, so their raw sum exceeds ms_per_step - kept as breakdown_eager_ms)
     result["breakdown_ms"] = scale_breakdown(breakdown_eager, ms / K)
     result["breakdown_eager_ms"] = breakdown_eager
-    result["roofline_classes"] = class_rooflines(result["breakdown_ms"], cfg, B, L, peaks, passes=1 if args.precision == "bf16" else 3)
+    result["roofline_classes"] = class_rooflines(result["breakdown_ms"], cfg, B, L, peaks, passes=1 if args.precision == "bf16" else 3,
+                                                   launches=base_launches)
     if "bf16x3" in sub:
         _, _, bd3, ffn1_3 = sub["bf16x3"]
         ach3 = ffn1_flops / (ffn1_3 * 1e-3) / 1e12 if ffn1_3 else None
@@ -618,7 +620,10 @@ def scale_breakdown(eager, step_ms):
     return {k: round(v * step_ms / tot, 4) for k, v in eager.items()} if tot > 0 else {}
 
 
-def class_rooflines(breakdown, cfg, B, L, peaks, passes):
+_CLASS_LAUNCHES = {}
+
+
+def class_rooflines(breakdown, cfg, B, L, peaks, passes, launches=None):
     """Achieved fraction of the measured peak per kernel class: algorithmic FLOPs (2*MAC, counted once in 3-pass mode) against
     the cuBLAS bf16 burst peak for the tensor-core classes, algorithmic bytes against the measured copy bandwidth for the
     HBM-bound ones (conv0: 4 L in + 2 x 512 x T0 out per utterance; LayerNorm: 4 d in + 2 d out (+ planes) per row and launch)."""
@@ -629,7 +634,8 @@ def class_rooflines(breakdown, cfg, B, L, peaks, passes):
               "gemm ffn2": nl * fl["per_layer"]["ffn"] / 2, "gemm qkv": nl * fl["per_layer"]["qkv"],
               "gemm out_proj": nl * fl["per_layer"]["out"], "attention": nl * fl["per_layer"]["attn"],
               "posconv": fl["other"]["posconv"], "gemm proj": fl["other"]["proj"], "gemm lm_head": fl["other"]["lm_head"]}
-    ln_launches = 2 * nl + 2
+    # LayerNorm passes actually launched per forward (2 per layer + 2 without the fold; 3 with it: the others live in GEMM epilogues)
+    ln_launches = (launches or {}).get("layernorm", 2 * nl + 2)
     hbm = {"conv0": 4.0 * L + 2.0 * planes * cfg.filter_sizes[0] * fl["frames"][0],
            "conv0 stats+fold": 4.0 * L,
            "layernorm": ln_launches * T * d * (4.0 + 2.0 * planes)}
@@ -767,6 +773,8 @@ def profile_classes(model, x, cfg, steps):
         agg[label] = agg.get(label, 0.0) + s.elapsed_time(e)
         cnt[label] = cnt.get(label, 0) + 1
     out = {k: v / steps for k, v in agg.items()}
+    _CLASS_LAUNCHES.clear()
+    _CLASS_LAUNCHES.update({k: c / steps for k, c in cnt.items()})      # launches per forward (class_rooflines: LayerNorm passes made)
     ffn1 = agg.get("gemm ffn1", 0.0) / max(cnt.get("gemm ffn1", 1), 1)
     return {k: round(v, 4) for k, v in sorted(out.items(), key=lambda kv: -kv[1])}, ffn1
 
