@@ -38,22 +38,35 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
   for (int i = 0; i < MAXV; ++i)
     gm[i] = (EXACT || lane + 32 * i < nvec) ? __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
-    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)row * d);
-    float4 v[MAXV], g[MAXV];
-    float s = 0.0f;
+  // one CTA per SM (see the launcher): a warp keeps its NEXT row (x and dy, 8 d bytes) in flight while it reduces the current one
+  const int rstride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + warp;
+  float4 nv[MAXV], ng[MAXV];
+  auto fetch = [&](int r) {
+    const float4* xp = reinterpret_cast<const float4*>(x + (size_t)r * d);
+    const float4* dp = reinterpret_cast<const float4*>(dy + (size_t)r * d);
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int idx = lane + 32 * i;
       if (EXACT || idx < nvec) {
-        v[i] = __ldg(xp + idx);
-        g[i] = __ldg(dp + idx);
-        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        nv[i] = __ldg(xp + idx);
+        ng[i] = __ldg(dp + idx);
       } else {
-        v[i] = g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        nv[i] = ng[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
+  };
+  if (row < rows) fetch(row);
+  for (; row < rows; row += rstride) {
+    float4 v[MAXV], g[MAXV];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      v[i] = nv[i];
+      g[i] = ng[i];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    if (row + rstride < rows) fetch(row + rstride);
     const float mean = warp_sum(s) / (float)d;
     float q = 0.0f;
 #pragma unroll
@@ -168,28 +181,44 @@ dact_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict
   const int per = (rows + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int r = r0; r < r1; ++r) {
-    const size_t off = (size_t)r * cols + c;
-    const uint2 raw = __ldg(reinterpret_cast<const uint2*>(dy + off));
-    float4 g = make_float4(bf16_lo_to_f32(raw.x), bf16_hi_to_f32(raw.x), bf16_lo_to_f32(raw.y), bf16_hi_to_f32(raw.y));
-    if (dr.thr16) {   // gradient of a dropout that sat AFTER the activation (or after a Dense when pre == null)
-      const uint64_t bits = drop_bits4(dr, off >> 2);
-      g.x = drop_keep(bits, 0, dr.thr16) ? g.x * dr.scale : 0.0f;
-      g.y = drop_keep(bits, 1, dr.thr16) ? g.y * dr.scale : 0.0f;
-      g.z = drop_keep(bits, 2, dr.thr16) ? g.z * dr.scale : 0.0f;
-      g.w = drop_keep(bits, 3, dr.thr16) ? g.w * dr.scale : 0.0f;
+  // U rows per batch: all their loads are issued before the first use (a one-row-at-a-time loop is a chain of dependent HBM
+  // latencies: 25 us for a 9 MB column sum)
+  constexpr int U = 8;
+  for (int rb = r0; rb < r1; rb += U) {
+    uint2 raw[U];
+    float4 pv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = min(rb + u, r1 - 1);                 // clamped: the tail re-reads the last row, its result is discarded
+      const size_t off = (size_t)r * cols + c;
+      raw[u] = __ldg(reinterpret_cast<const uint2*>(dy + off));
+      if (pre != nullptr) pv[u] = __ldg(reinterpret_cast<const float4*>(pre + off));
     }
-    if (pre != nullptr) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(pre + off));
-      g.x *= gelu_grad(p.x); g.y *= gelu_grad(p.y); g.z *= gelu_grad(p.z); g.w *= gelu_grad(p.w);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = rb + u;
+      if (r >= r1) break;
+      const size_t off = (size_t)r * cols + c;
+      float4 g = make_float4(bf16_lo_to_f32(raw[u].x), bf16_hi_to_f32(raw[u].x), bf16_lo_to_f32(raw[u].y), bf16_hi_to_f32(raw[u].y));
+      if (dr.thr16) {   // gradient of a dropout that sat AFTER the activation (or after a Dense when pre == null)
+        const uint64_t bits = drop_bits4(dr, off >> 2);
+        g.x = drop_keep(bits, 0, dr.thr16) ? g.x * dr.scale : 0.0f;
+        g.y = drop_keep(bits, 1, dr.thr16) ? g.y * dr.scale : 0.0f;
+        g.z = drop_keep(bits, 2, dr.thr16) ? g.z * dr.scale : 0.0f;
+        g.w = drop_keep(bits, 3, dr.thr16) ? g.w * dr.scale : 0.0f;
+      }
+      if (pre != nullptr) {
+        const float4 p = pv[u];
+        g.x *= gelu_grad(p.x); g.y *= gelu_grad(p.y); g.z *= gelu_grad(p.z); g.w *= gelu_grad(p.w);
+      }
+      if (out_hi != nullptr) {
+        const uint2 o = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+        *reinterpret_cast<uint2*>(out_hi + off) = o;
+        // the bias gradient is the column sum of what the wgrad GEMM will see (the rounded values)
+        g = make_float4(bf16_lo_to_f32(o.x), bf16_hi_to_f32(o.x), bf16_lo_to_f32(o.y), bf16_hi_to_f32(o.y));
+      }
+      acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
     }
-    if (out_hi != nullptr) {
-      const uint2 o = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
-      *reinterpret_cast<uint2*>(out_hi + off) = o;
-      // the bias gradient is the column sum of what the wgrad GEMM will see (the rounded values)
-      g = make_float4(bf16_lo_to_f32(o.x), bf16_hi_to_f32(o.x), bf16_lo_to_f32(o.y), bf16_hi_to_f32(o.y));
-    }
-    acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
   }
   if (colsum != nullptr) {
     atomicAdd(colsum + c + 0, acc.x); atomicAdd(colsum + c + 1, acc.y);
@@ -301,8 +330,11 @@ extern "C" int w2v2_ln_bwd(const float* x, const float* gamma, const float* dy, 
   W2V2_CHECK_ARG(d > 0 && d % 4 == 0 && d <= 1024, "d must be a multiple of 4, at most 1024");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // every CTA ends in up to 3 d global atomics and same-address atomics serialise in L2: no more CTAs than SMs
+  // (W2V2_LNBWD_CTAS overrides, A/B switch)
+  static const int max_ctas = [] { const char* e = getenv("W2V2_LNBWD_CTAS"); const int v = e ? atoi(e) : 148; return v > 0 ? v : 148; }();
   int grid = (int)((rows + 7) / 8);
-  if (grid > 148 * 2) grid = 148 * 2;
+  if (grid > max_ctas) grid = max_ctas;
   auto* hi = reinterpret_cast<__nv_bfloat16*>(dx_hi);
   const size_t sm = 3 * d * sizeof(float);
   if (d == 512) ln_bwd_kernel<4, true><<<grid, 256, sm, s>>>(x, gamma, dy, eps, (int)rows, d, dx_f32, hi, dgamma, dbeta, colsum);
@@ -331,12 +363,107 @@ extern "C" int w2v2_gelu_rows(const float* pre, int64_t n, int fast, void* out_h
   return 0;
 }
 
+// Same operation for cols % 8 == 0.  The one-row-per-iteration kernel above ends in `cols` fp32 atomics per 16-row CTA: 384 adds
+// onto every address at 6144 rows, and same-address L2 atomics serialise (~20 of the 25 us of a 9 MB column sum).  Here a CTA is
+// 32 column threads (8 columns = one 16-byte bf16 load each: 256 columns) x 8 row lanes, walks `rows_per_cta` rows with U rows
+// per lane in flight, reduces its 8 lanes through shared memory and issues ONE atomic per column.
+__global__ void __launch_bounds__(256)
+dact_colsum8_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ pre, int rows, int cols, int rows_per_cta,
+                    __nv_bfloat16* __restrict__ out_hi, float* __restrict__ colsum, DropSpec dr) {
+  __shared__ float red[8][256 + 8];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + tx) * 8;
+  const bool col_ok = c < cols;
+  const int r0 = blockIdx.y * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  constexpr int U = 4;
+  if (col_ok) {
+    for (int rb = r0 + ty; rb < r1; rb += 8 * U) {
+      uint4 raw[U];
+      float4 p0[U], p1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const size_t off = (size_t)min(rb + 8 * u, r1 - 1) * cols + c;    // clamped: a tail lane re-reads the last row, result discarded
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(dy + off));
+        if (pre != nullptr) {
+          p0[u] = __ldg(reinterpret_cast<const float4*>(pre + off));
+          p1[u] = __ldg(reinterpret_cast<const float4*>(pre + off + 4));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = rb + 8 * u;
+        if (r >= r1) break;
+        const size_t off = (size_t)r * cols + c;
+        const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        float g[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          g[2 * i] = bf16_lo_to_f32(w[i]);
+          g[2 * i + 1] = bf16_hi_to_f32(w[i]);
+        }
+        if (dr.thr16) {   // gradient of a dropout that sat AFTER the activation (or after a Dense when pre == null)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint64_t bits = drop_bits4(dr, (off >> 2) + h);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) g[4 * h + e] = drop_keep(bits, e, dr.thr16) ? g[4 * h + e] * dr.scale : 0.0f;
+          }
+        }
+        if (pre != nullptr) {
+          g[0] *= gelu_grad(p0[u].x); g[1] *= gelu_grad(p0[u].y); g[2] *= gelu_grad(p0[u].z); g[3] *= gelu_grad(p0[u].w);
+          g[4] *= gelu_grad(p1[u].x); g[5] *= gelu_grad(p1[u].y); g[6] *= gelu_grad(p1[u].z); g[7] *= gelu_grad(p1[u].w);
+        }
+        if (out_hi != nullptr) {
+          uint32_t o[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            o[i] = pack_bf16x2(g[2 * i], g[2 * i + 1]);
+            // the bias gradient is the column sum of what the wgrad GEMM will see (the rounded values)
+            g[2 * i] = bf16_lo_to_f32(o[i]);
+            g[2 * i + 1] = bf16_hi_to_f32(o[i]);
+          }
+          *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += g[i];
+      }
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ty][8 * tx + i] = acc[i];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
+    float s_ = 0.0f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) s_ += red[l][threadIdx.x];
+    atomicAdd(colsum + cc, s_);
+  }
+}
+
 extern "C" int w2v2_dact_colsum(const void* dy_hi, const float* pre, int64_t rows, int cols, void* out_hi, float* colsum,
                                 float drop_p, uint64_t seed, uint32_t site, void* stream) {
   W2V2_CHECK_ARG(dy_hi && (out_hi || colsum), "null pointer");
   W2V2_CHECK_ARG(cols > 0 && cols % 4 == 0, "cols must be a multiple of 4");
   if (rows <= 0) return 0;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (cols % 8 == 0) {
+    // about two CTAs per SM, as few CTA rows as that allows: every CTA row adds once onto each column's address
+    const int gx8 = (cols + 255) / 256;
+    int gy8 = (296 + gx8 - 1) / gx8;
+    const int max_gy = (int)((rows + 31) / 32);
+    if (gy8 > max_gy) gy8 = max_gy;
+    const int rpc = (int)((rows + gy8 - 1) / gy8);
+    gy8 = (int)((rows + rpc - 1) / rpc);
+    dact_colsum8_kernel<<<dim3(gx8, gy8), 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy_hi), pre, (int)rows, cols, rpc,
+                                                       reinterpret_cast<__nv_bfloat16*>(out_hi), colsum, make_drop(drop_p, seed, site));
+    W2V2_CUDA(cudaGetLastError());
+    return 0;
+  }
   const int gx = (cols / 4 + 255) / 256;
   int gy = (int)((rows + 15) / 16);   // short dependent-load chains: many row chunks, 4 atomics per thread at the end
   if (gy > 1024) gy = 1024;
