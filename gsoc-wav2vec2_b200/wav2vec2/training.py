@@ -333,7 +333,6 @@ class Stage2Trainer:
         if p_drop:                                          # encoder.py:270
             ops.dropout_rows(xs_f32, self._drop(self.SITE_ENC), out_f32=xs_f32)
             resplit(xs_f32, xs)
-        tmp = A.get("t.tmp", (M, d), f32) if p_drop else None
         L = []
         for i in range(cfg.num_layers):
             lb = f"{enc}layers/{i}/"
@@ -344,9 +343,10 @@ class Stage2Trainer:
             y1 = A.get(f"t.y1.{i}", (M, d), f32)
             if p_drop:
                 ops.attn_fwd_train(qkv, B, T, H, dh, None, ctx, passes, self._drop(self.site_attn_probs(i)))
+                # y1 = x + dropout(out_proj(ctx)) (encoder.py:118-119): the dropout draws (same element stream as w2v2_dropout_rows:
+                # index = row * d + column) and the residual add happen in the GEMM epilogue
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
-                         out_f32=tmp, passes=passes)
-                ops.dropout_rows(tmp, self._drop(self.site_attn_out(i)), resid=xs_f32, out_f32=y1)     # encoder.py:118-119
+                         residual=xs_f32, out_f32=y1, passes=passes, drop=self._drop(self.site_attn_out(i)))
             else:
                 ops.attn_fwd(qkv, B, T, H, dh, None, ctx, passes)
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=v[lb + "attention/out_proj/bias"],
