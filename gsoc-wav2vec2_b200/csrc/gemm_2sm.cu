@@ -161,6 +161,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
       }
       reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(n >> 6) * ((size_t)p.batch * p.rows_per_batch) + orow0 + lane] = make_float2(s1, s2);
     }
+    if (p.row_stats_out != nullptr && p.stats_final != nullptr) row_stats_finalize_last(p, orow0, lane, rows_valid);
     if constexpr ((EPI & EPI_HI) != 0) {
       // operand planes of the SUM (the un-normalised LayerNorm input the next GEMM consumes): the two staging blocks are free
       // once the four fp32 slab stores have read them.  PASSES == 2 (fp16f8): fp16 + e4m3 pair plane; else bf16 or fp16 (out_format)
@@ -324,6 +325,7 @@ __device__ __forceinline__ void gemm2_epilogue_warp(const GemmParams& p, const G
     }
     reinterpret_cast<float2*>(p.row_stats_out)[(size_t)(n >> 6) * ((size_t)p.batch * p.rows_per_batch) + orow0 + lane] = make_float2(s1, s2);
   }
+  if (EPI < 0 && p.row_stats_out != nullptr && p.stats_final != nullptr) row_stats_finalize_last(p, orow0, lane, rows_valid);
 
   // ---- pass B: outputs, one 64-byte column slab per bulk store
   if (f_f32) {
@@ -687,6 +689,9 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
   // the rarely used epilogue options (tf-approximate GELU, dropout, SpecAugment row replacement) only exist in the run-time instance
   if ((a->flags & W2V2_GEMM_GELU_TANH) || a->row_replace_mask != nullptr || a->drop_p > 0.0f)
     return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
+  // row statistics are written by the TMA-residual recipes and by the run-time instance only
+  if (a->row_stats_out != nullptr && !(!gelu && res && f32 && a->N % 64 == 0 && a->ln_fold_stats == nullptr && !sc))
+    return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
   if (a->ln_fold_stats != nullptr) {   // LayerNorm folded into the GEMM (QKV, FFN1): the scale slot carries the column sums
     if (!res && !f32 && hi && lo == (PASSES != 1) && a->row_stats_out == nullptr) {
       if (gelu) return launch_gemm_2sm_t<PASSES, EPI_LNFOLD | EPI_SCALE | G | EPI_HI | LO>(a, s);
@@ -714,12 +719,15 @@ static int dispatch_2sm(const w2v2_gemm_args* a, cudaStream_t s) {
     return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32 | EPI_TMARES | EPI_HI | ((PASSES == 2) ? EPI_LO : 0)>(a, s);
   }
   if (lo == (PASSES != 1) || !hi) {
-    if (!gelu && res && f32 && !hi) return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32>(a, s);
+    if (!gelu && res && f32 && !hi && a->row_stats_out == nullptr) return launch_gemm_2sm_t<PASSES, EPI_RESID | EPI_F32>(a, s);
   }
   return launch_gemm_2sm_t<PASSES, EPI_RUNTIME>(a, s);
 }
 
+thread_local bool g_stats_final_in_kernel = false;   // set when the launched kernel finalises row_stats_final itself
+
 int launch_gemm_2sm(const w2v2_gemm_args* a, cudaStream_t stream) {
+  g_stats_final_in_kernel = (a->row_stats_final != nullptr);
   if (mode_f8(a->passes)) return dispatch_2sm<2, false>(a, stream);
   if (mode_passes(a->passes) == 3) return dispatch_2sm<3, false>(a, stream);
   return mode_fp16(a->passes) ? dispatch_2sm<1, false>(a, stream) : dispatch_2sm<1, true>(a, stream);

@@ -61,6 +61,9 @@ struct GemmParams {
   float ln_fold_inv_dim;       // 1 / K
   float ln_eps;
   float* row_stats_out;        // optional [N / 64][rows][2]: (sum, sum of squares) of the fp32 output per 64-column group
+  float2* stats_final;         // optional [rows]: (mean, rstd) over all N columns, written by the last column group of a 32-row block
+  unsigned* stats_counter;     // [ceil(rows / 32)] arrival counters of those blocks (zero between launches)
+  int stats_parts;             // N / 64
   int res_ln_parts;            // 0: ln_stats holds (mean, rstd) per row; > 0: partial sums over N columns in that many groups
   int fp16;               // 1: the 16-bit operand planes are fp16 (idesc format 0) instead of bf16
   float acc_scale;        // accumulator -> value: 1, or 2^-15 for the scaled fp16 operand planes (ACT_SCALE * WGT_SCALE)
@@ -91,6 +94,38 @@ __device__ __forceinline__ float2 mean_rstd_from_parts(const float* stats, size_
   const float mean = s1 * inv_dim;
   const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.0f);
   return make_float2(mean, rsqrtf(var + eps));
+}
+
+// Producer-side finalisation of the row statistics (w2v2.h row_stats_final): called by ALL lanes of a warp that has just written
+// its (sum, sum of squares) partial for the 32 rows orow0 .. orow0 + 31 (one 64-column group).  The warp that brings the block's
+// arrival counter to `stats_parts` sums the partials in index order - the arithmetic of w2v2_row_stats_finalize, bit for bit - writes
+// (mean, rstd) and re-arms the counter.  (threadFenceReduction pattern: partials -> fence -> counter; last arriver: fence -> L2 loads.)
+__device__ __forceinline__ void row_stats_finalize_last(const GemmParams& p, size_t orow0, int lane, int rows_valid) {
+  __threadfence();
+  __syncwarp();
+  unsigned prev = 0;
+  if (lane == 0) prev = atomicAdd(p.stats_counter + (orow0 >> 5), 1u);
+  prev = __shfl_sync(0xffffffffu, prev, 0);
+  if (prev + 1u != (unsigned)p.stats_parts) return;
+  __threadfence();
+  if (lane < rows_valid) {
+    const size_t rows_total = (size_t)p.batch * p.rows_per_batch;
+    const float2* p2 = reinterpret_cast<const float2*>(p.row_stats_out) + orow0 + lane;
+    float2 v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = (i < p.stats_parts) ? __ldcg(p2 + (size_t)i * rows_total) : make_float2(0.0f, 0.0f);
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      s1 += v[i].x;
+      s2 += v[i].y;
+    }
+    const float inv_dim = 1.0f / (float)p.N;
+    const float mean = s1 * inv_dim;
+    const float var = fmaxf(fmaf(-mean, mean, s2 * inv_dim), 0.0f);
+    p.stats_final[orow0 + lane] = make_float2(mean, rsqrtf(var + p.ln_eps));
+  }
+  if (lane == 0) p.stats_counter[orow0 >> 5] = 0u;
 }
 
 // Per-row LayerNorm constants of one output row, fetched BEFORE the epilogue waits for its accumulator (their load latency - up

@@ -310,6 +310,9 @@ GemmParams make_gemm_params(const w2v2_gemm_args* a, int block_n) {
   p.ln_fold_inv_dim = 1.0f / (float)a->K;
   p.ln_eps = a->ln_eps;
   p.row_stats_out = a->row_stats_out;
+  p.stats_final = reinterpret_cast<float2*>(a->row_stats_final);
+  p.stats_counter = a->row_stats_counter;
+  p.stats_parts = a->N / 64;
   p.res_ln_parts = a->res_ln_parts;
   p.vec_ok = (a->N % 8 == 0) ? 1 : 0;
   p.debug = (int)(a->flags >> 8) & 3;
@@ -397,7 +400,10 @@ static int launch_gemm(const w2v2_gemm_args* a, cudaStream_t stream) {
 
 }  // namespace w2v2
 
-extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
+namespace w2v2 { extern thread_local bool g_stats_final_in_kernel; }   // gemm_2sm.cu
+extern "C" int w2v2_row_stats_finalize(const float* parts, int nparts, int64_t rows, int dim, float eps, float* stats, void* stream);
+
+static int gemm_bf16_dispatch(const w2v2_gemm_args* a, void* stream) {
   using namespace w2v2;
   W2V2_CHECK_ARG(a != nullptr, "args is null");
   W2V2_CHECK_ARG(a->a_hi && a->w_hi, "A / W pointers must be non-null");
@@ -480,5 +486,19 @@ extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
   return fail(-1, "%s: unsupported block_n %ld", __func__, bn);
 }
 
+extern "C" int w2v2_gemm_bf16(const w2v2_gemm_args* a, void* stream) {
+  using namespace w2v2;
+  W2V2_CHECK_ARG(a != nullptr, "args is null");
+  W2V2_CHECK_ARG(a->row_stats_final == nullptr || (a->row_stats_out != nullptr && a->row_stats_counter != nullptr &&
+                                                   (a->batch == 1 || a->rows_per_batch % 32 == 0)),
+                 "row_stats_final needs row_stats_out, row_stats_counter and batch == 1 or rows_per_batch % 32 == 0");
+  g_stats_final_in_kernel = false;
+  const int rc = gemm_bf16_dispatch(a, stream);
+  if (rc != 0 || a->row_stats_final == nullptr || g_stats_final_in_kernel) return rc;
+  // tile shapes without the in-kernel finalisation: the separate launch, same stream, same arithmetic
+  return w2v2_row_stats_finalize(a->row_stats_out, a->N / 64, (int64_t)a->batch * a->rows_per_batch, a->N, a->ln_eps, a->row_stats_final,
+                                 stream);
+}
+
 extern "C" const char* w2v2_last_error_string(void) { return w2v2::g_last_error; }
-extern "C" int w2v2_version(void) { return 140; }   // 1.4: precision modes 17 / 19 / 25, output formats, LayerNorm fold (ln_fold_*, row_stats_out)
+extern "C" int w2v2_version(void) { return 141; }   // 1.41: row_stats_final; 1.4: precision modes 17 / 19 / 25, output formats, LayerNorm fold (ln_fold_*, row_stats_out)

@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("drop_p", C.c_float), ("drop_site", C.c_uint32), ("drop_seed", C.c_uint64),
         ("out_format", C.c_int32), ("ln_fold_parts", C.c_int32), ("ln_fold_stats", C.c_void_p),
         ("ln_eps", C.c_float), ("res_ln_parts", C.c_int32), ("row_stats_out", C.c_void_p),
+        ("row_stats_final", C.c_void_p), ("row_stats_counter", C.c_void_p),
     ]
 
 

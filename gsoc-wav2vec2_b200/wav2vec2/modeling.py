@@ -566,12 +566,18 @@ class _B200Model:
         fstats = [A.get(f"ln.fstats.{k}", (M, 2), f32) for k in "ab"] if fold else None   # ... reduced to (mean, rstd) per row
         cur, nstat = None, 0                    # (mean, rstd) of the current stream tensor (None: a real LayerNorm ran)
 
-        def finalize():
-            # one tiny launch per LayerNorm instead of P predicated loads per thread and tile in the consuming GEMMs; two buffers
-            # because the residual GEMM that reads one set of statistics is followed by the launch that writes the next
+        counters = A.get("ln.counters", ((M + 31) // 32,), torch.int32) if fold else None
+        if fold and not getattr(counters, "_w2v2_zeroed", False):
+            counters.zero_()                    # arrival counters of the in-kernel finalisation: zero once, the kernels re-arm them
+            counters._w2v2_zeroed = True
+
+        def stats_target():
+            # (mean, rstd) per row are produced by the residual GEMM itself (the last column group of a 32-row block reduces the
+            # partial sums: include/w2v2.h row_stats_final) - no launch between the producer and the GEMM that folds the LayerNorm.
+            # Two buffers: the residual GEMM that reads one set of statistics writes the next
             nonlocal nstat
             nstat += 1
-            return ops.row_stats_finalize(parts, d, eps, fstats[nstat & 1])
+            return fstats[nstat & 1]
         for i in range(nl):
             lb = f"{enc}layers/{i}/"
             g1, b1 = v[lb + "layer_norm/gamma"], v[lb + "layer_norm/beta"]
@@ -588,7 +594,8 @@ class _B200Model:
                          out_lo=qkv.lo, passes=passes, out_format=qfmt)
             ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, md.attn, out_format=ofmt)
             # ---- output projection + residual (encoder.py:117-121)
-            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts) if fold else {}
+            tgt = stats_target() if fold else None
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts, row_stats_final=(tgt, counters)) if fold else {}
             ob = v[lb + "attention/out_proj/bias"]
             if pre:     # x1 = x + out_proj(ctx)
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=xs_f32, out_f32=x1_f32,
@@ -598,7 +605,7 @@ class _B200Model:
                          passes=passes, ln_eps=eps, **po)
             # ---- feed forward (encoder.py:126-131) on LN(x1)
             if fold:
-                cur = finalize()
+                cur = tgt
                 ops.gemm(ys, P[f"l{i}.ff1.wf"], K=d, N=ffn, rows_per_batch=M, bias=P[f"l{i}.ff1.bf"], gelu=True, gelu_approx=approx,
                          out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt, ln_fold=(cur, P[f"l{i}.ff1.cs"]), ln_eps=eps)
                 res_ln = (cur, g1, b1)
@@ -610,7 +617,9 @@ class _B200Model:
                     res_ln = (st, g1, b1)
                 ops.gemm(xs, P[f"l{i}.ff1.w"], K=d, N=ffn, rows_per_batch=M, bias=v[lb + "feed_forward/intermediate_dense/bias"],
                          gelu=True, gelu_approx=approx, out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt)
-            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts) if (fold and not last) else {}
+            tgt = stats_target() if (fold and not last) else None
+            po = (dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts, row_stats_final=(tgt, counters))
+                  if (fold and not last) else {})
             fb = v[lb + "feed_forward/output_dense/bias"]
             if pre:
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=x1_f32, out_f32=xs_f32,
@@ -618,7 +627,7 @@ class _B200Model:
             else:       # y <- LN1(y) + FFN(x1)
                 ops.gemm(mid, P[f"l{i}.ff2.w"], K=ffn, N=d, rows_per_batch=M, bias=fb, residual=y, res_ln=res_ln, out_f32=y,
                          passes=passes, ln_eps=eps, **po)
-            cur = finalize() if po else None
+            cur = tgt if po else None
             if not pre:
                 if cur is not None:
                     res_ln = (cur, g2, b2)

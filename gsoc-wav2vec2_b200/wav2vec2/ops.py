@@ -62,7 +62,7 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
          row_valid=None, gelu=False,
          out_f32=None, out_hi=None, out_lo=None, passes=1, kb_split=0, block_n=0, max_ctas=0, cluster=0, debug=0,
          res_ln=None, mn_major=False, w_row_stride=0, gelu_approx=False, row_replace=None, drop=None, out_format=0,
-         ln_fold=None, row_stats_out=None, ln_eps=1e-5):
+         ln_fold=None, row_stats_out=None, ln_eps=1e-5, row_stats_final=None):
     """D = epilogue(A . W^T).  ``w.hi`` is [w_rows, K] bf16 row-major.
     ``res_ln = (stats, gamma, beta)``: the residual term is LayerNorm(residual) recomputed from ``ln_rows(..., stats=)``.
     ``mn_major``: D[m][n] = sum_r X[r][m] Y[r][n] with a = X [a_rows, ld a_row_stride], w = Y [a_rows, ld w_row_stride].
@@ -107,6 +107,9 @@ def gemm(a: Pair, w: Pair, *, K: int, N: int, rows_per_batch: int, batch: int = 
     if row_stats_out is not None:
         _need_cuda(row_stats_out)
         args.row_stats_out = _ptr(row_stats_out)
+    if row_stats_final is not None:       # (stats [rows, 2], counters [ceil(rows / 32)] uint32 zero-initialised): finalised by this call
+        _need_cuda(*row_stats_final)
+        args.row_stats_final, args.row_stats_counter = _ptr(row_stats_final[0]), _ptr(row_stats_final[1])
     _count(); _lib.check(_lib.load().w2v2_gemm_bf16(C.byref(args), _stream()), "w2v2_gemm_bf16")
 
 

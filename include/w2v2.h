@@ -129,6 +129,13 @@ typedef struct w2v2_gemm_args {
   int32_t res_ln_parts;            /* 0: res_ln_stats holds (mean, rstd) per row; > 0: that many partial (sum, sum of squares) pairs per row, laid out [parts][rows][2] */
   float* row_stats_out;            /* optional [N / 64][rows][2]: (sum, sum of squares) of the fp32 result per 64-column group
                                       (needs out_f32 semantics: the statistics are those of the value written to out_f32; N % 64 == 0) */
+  /* optional, with row_stats_out: the per-row (mean, rstd) [rows][2] over all N columns (biased variance, ln_eps) - what
+   * w2v2_row_stats_finalize computes from row_stats_out - produced by this call itself.  In the cta_group::2 kernel the LAST of the
+   * N / 64 column groups to finish a 32-row block (an arrival counter per block in row_stats_counter, [ceil(rows / 32)] uint32,
+   * zero before the first use; the kernel leaves it zero) sums the partials in index order: bit-identical to the separate
+   * launch, without it.  Other tile shapes run w2v2_row_stats_finalize on the same stream.  Needs batch == 1 or rows_per_batch % 32 == 0. */
+  float* row_stats_final;
+  uint32_t* row_stats_counter;
 } w2v2_gemm_args;
 
 int w2v2_gemm_bf16(const w2v2_gemm_args* args, void* stream);
