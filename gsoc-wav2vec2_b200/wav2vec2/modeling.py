@@ -376,8 +376,11 @@ class _B200Model:
         # 8.58 - 8.66 -> 8.28 - 8.44 ms per step (large model 12.1 - 12.3 -> 11.5 - 11.7): the `layernorm` class drops from 0.66 to
         # 0.08 ms (only the LayerNorms after the extractor / positional conv and the final one remain), the consuming GEMMs pay for it
         # in their epilogue (FFN1 0.72 -> 0.66 of the tensor peak, QKV 0.70 -> 0.68) and the residual GEMMs write one more plane.
-        self._fold = (self.precision != "bf16x3" and cfg.hidden_size % 64 == 0 and cfg.num_layers > 0
-                      and os.environ.get("W2V2_LN_FOLD", "1") == "1")
+        # W2V2_LN_FOLD: "1" (default) = both LayerNorms of a layer, "qkv" = only the one in front of the q / k / v projection (FFN1 keeps
+        # a real LayerNorm pass and its plain epilogue, out-proj writes no extra plane), "0" = none
+        fold_mode = os.environ.get("W2V2_LN_FOLD", "1")
+        self._fold = (self.precision != "bf16x3" and cfg.hidden_size % 64 == 0 and cfg.num_layers > 0 and fold_mode in ("1", "qkv"))
+        self._fold_ff1 = self._fold and fold_mode == "1"
         if self._fold:
             pre = cfg.attention_norm_type == "prenorm"
             for i in range(cfg.num_layers):
@@ -561,6 +564,7 @@ class _B200Model:
         # per-row partial (sum, sum of squares); QKV / FFN1 consume `ys` with gamma folded into their weights and apply mean / rstd
         # in their epilogue - no stand-alone LayerNorm pass between the positional conv and the final encoder output.
         fold = bool(getattr(self, "_fold", False))
+        fold_ff1 = fold and bool(getattr(self, "_fold_ff1", False))
         ys = A.planes("ys", (M, d), kind) if fold else None
         parts = A.get("ln.parts", (d // 64, M, 2), f32) if fold else None     # partial sums written by a residual GEMM ...
         fstats = [A.get(f"ln.fstats.{k}", (M, 2), f32) for k in "ab"] if fold else None   # ... reduced to (mean, rstd) per row
@@ -594,8 +598,8 @@ class _B200Model:
                          out_lo=qkv.lo, passes=passes, out_format=qfmt)
             ops.attn_fwd(qkv, B, T, H, dh, kv_len, ctx, md.attn, out_format=ofmt)
             # ---- output projection + residual (encoder.py:117-121)
-            tgt = stats_target() if fold else None
-            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts, row_stats_final=(tgt, counters)) if fold else {}
+            tgt = stats_target() if fold_ff1 else None
+            po = dict(out_hi=ys.hi, out_lo=ys.lo, out_format=ofmt, row_stats_out=parts, row_stats_final=(tgt, counters)) if fold_ff1 else {}
             ob = v[lb + "attention/out_proj/bias"]
             if pre:     # x1 = x + out_proj(ctx)
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=xs_f32, out_f32=x1_f32,
@@ -604,7 +608,7 @@ class _B200Model:
                 ops.gemm(ctx, P[f"l{i}.out.w"], K=d, N=d, rows_per_batch=M, bias=ob, residual=y, res_ln=res_ln, out_f32=y,
                          passes=passes, ln_eps=eps, **po)
             # ---- feed forward (encoder.py:126-131) on LN(x1)
-            if fold:
+            if fold_ff1:
                 cur = tgt
                 ops.gemm(ys, P[f"l{i}.ff1.wf"], K=d, N=ffn, rows_per_batch=M, bias=P[f"l{i}.ff1.bf"], gelu=True, gelu_approx=approx,
                          out_hi=mid.hi, out_lo=mid.lo, passes=passes, out_format=ofmt, ln_fold=(cur, P[f"l{i}.ff1.cs"]), ln_eps=eps)

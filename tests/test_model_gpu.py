@@ -275,12 +275,13 @@ def test_layernorm_fold_equals_the_unfolded_path(arch, precision, monkeypatch):
     x = torch.randn(2, 20000, generator=torch.Generator().manual_seed(4)) + 0.3
     ref = O.wav2vec2_for_ctc(x, params, cfg)
     errs = {}
-    for fold in ("1", "0"):
+    for fold in ("1", "qkv", "0"):          # both LayerNorms of a layer / only the one in front of q, k, v / none
         monkeypatch.setenv("W2V2_LN_FOLD", fold)
         m = Wav2Vec2ForCTC(cfg, precision=precision)
         m.set_variables(params)
         errs[fold] = (m(x.cuda()).cpu() - ref).abs().max().item()
-        assert m._fold == (fold == "1")
-    print(f"{arch}/{precision}: logits max-abs err folded {errs['1']:.3e}, unfolded {errs['0']:.3e}")
+        assert m._fold == (fold != "0") and m._fold_ff1 == (fold == "1")
+    print(f"{arch}/{precision}: logits max-abs err folded {errs['1']:.3e}, q/k/v only {errs['qkv']:.3e}, unfolded {errs['0']:.3e}")
     tol = {"bf16": 1e-1, "fp16": 6e-3, "fp16f8": 1e-3}[precision]
-    assert errs["1"] < tol and errs["1"] < 2.0 * errs["0"] + 1e-4
+    for mode in ("1", "qkv"):
+        assert errs[mode] < tol and errs[mode] < 2.0 * errs["0"] + 1e-4
