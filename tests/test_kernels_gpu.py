@@ -422,7 +422,25 @@ def test_gemm_layernorm_fold_and_row_statistics(passes):
     ops.gemm(planes_of(x), _split(w1, passes), K=K1, N=d, rows_per_batch=M, bias=b1, residual=y, out_f32=y, out_hi=ys.hi, out_lo=ys.lo,
              out_format=ofmt, row_stats_out=parts, passes=passes)
     stats = ops.row_stats_finalize(parts, d, 1e-5, torch.empty(M, 2, device=DEV))
-    torch.cuda.synchronize()
+    # the same producer finalising its statistics ITSELF (row_stats_final: the last column group of a 32-row block reduces the partials;
+    # cta_group::2 kernel at this size) must give the stand-alone launch's result bit for bit and leave its arrival counters at zero;
+    # a single-m-tile problem takes the other tile shape, where the call runs the stand-alone kernel on the same stream
+    for rows in (M, 100):
+        y2 = r[:rows].clone()
+        parts2 = torch.full((d // 64, rows, 2), float("nan"), device=DEV)
+        fin = torch.full((rows, 2), float("nan"), device=DEV)
+        counters = torch.zeros((rows + 31) // 32, dtype=torch.int32, device=DEV)
+        xr = planes_of(x[:rows].contiguous())
+        for _ in range(2):                                              # twice: the counters re-arm themselves
+            y2.copy_(r[:rows])
+            ops.gemm(xr, _split(w1, passes), K=K1, N=d, rows_per_batch=rows, bias=b1, residual=y2, out_f32=y2, out_hi=ys.hi[:rows],
+                     out_lo=None if ys.lo is None else ys.lo[:rows], out_format=ofmt, row_stats_out=parts2, passes=passes,
+                     row_stats_final=(fin, counters))
+        want = ops.row_stats_finalize(parts2, d, 1e-5, torch.empty(rows, 2, device=DEV))
+        torch.cuda.synchronize()
+        assert torch.equal(fin, want) and int(counters.abs().sum()) == 0
+        if rows == M:
+            assert torch.equal(fin, stats) and torch.equal(y2, y)
     y_ref = r.double() + x.double() @ w1.double().t() + b1.double()
     tol_y = {1: 5e-2, 17: 5e-3, 25: 3e-4}[passes]
     assert (y.double() - y_ref).abs().max().item() < tol_y
