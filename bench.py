@@ -606,6 +606,24 @@ def main():
                                     "frac": gbs / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": by,
                                     "frac_incl_stats_pass": with_stats / peaks["hbm_gbs"],
                                     "traffic": traffic.get("conv0_bytes_per_launch") if (B, L) == (32, 246000) else None}
+        # conv0 is 97 % stores.  MEASURED_PEAKS' HBM figure is a COPY (half reads, half writes); a pure-write stream is slower on
+        # this part, so the write ceiling is measured live with the library's own fill of a buffer of conv0's output size
+        try:
+            wbuf = torch.empty(int(B * 2.0 * 512 * fl["frames"][0]) // 2, dtype=torch.bfloat16, device=dev)
+            for _ in range(2):
+                wbuf.zero_()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for _ in range(5):
+                wbuf.zero_()
+            ev1.record()
+            torch.cuda.synchronize()
+            fill_gbs = wbuf.numel() * 2 / (ev0.elapsed_time(ev1) / 5 * 1e-3) / 1e9
+            result["roofline_conv0"]["write_only_fill_gbs"] = fill_gbs
+            result["roofline_conv0"]["frac_of_write_only_fill"] = gbs / fill_gbs
+            del wbuf
+        except Exception as e:          # the measurement is informative only
+            result["roofline_conv0"]["write_only_fill_gbs"] = f"unavailable: {e}"
     if not args.no_cpu_baseline:
         result.update(cpu_baseline_and_error(model, cfg, x_host, logits, args, {m: sub[m][1] for m in other_modes}))
         for m in result.get("modes", {}):
