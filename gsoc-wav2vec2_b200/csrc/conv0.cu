@@ -27,6 +27,9 @@ namespace w2v2 {
 constexpr int CM_TT = 256;                 // frames per CTA
 constexpr int CM_NS = CM_TT * 5 + 32;      // staged samples (window of the last frame + fragment over-read, zero filled)
 constexpr int CM_C = 512;
+#ifndef CONV0_STREAM_STORES
+#define CONV0_STREAM_STORES 1
+#endif
 
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -247,8 +250,13 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
       const int t = t0 + g + 8 * r;
       if (t < T0) {
         __nv_bfloat16* p = out_hi + out_base + (size_t)t * CM_C;
+        if (CONV0_STREAM_STORES) {
+          __stcs(reinterpret_cast<uint4*>(p), make_uint4(oh[r][0], oh[r][1], oh[r][2], oh[r][3]));
+          __stcs(reinterpret_cast<uint4*>(p + 32), make_uint4(oh[r][4], oh[r][5], oh[r][6], oh[r][7]));
+        } else {
         *reinterpret_cast<uint4*>(p) = make_uint4(oh[r][0], oh[r][1], oh[r][2], oh[r][3]);
         *reinterpret_cast<uint4*>(p + 32) = make_uint4(oh[r][4], oh[r][5], oh[r][6], oh[r][7]);
+        }
         if (OUT_FMT == 2) {
           // e4m3 pair plane [B*T0][2 * 512] bytes: the warp's 64 channels are one 128-byte group; this lane holds channels
           // 8q..8q+7 (n-tiles 0-3) and 32+8q.. (n-tiles 4-7): 8 lo bytes each, the hi bytes 64 further
