@@ -562,6 +562,12 @@ static int launch_attn(const void* qkv_hi, const void* qkv_lo, int B, int T, int
 
 }  // namespace w2v2
 
+namespace w2v2 {
+// attn2.cu: the two-tile, one-CTA-per-SM kernel of the single-pass modes
+int attn_fwd2(const void* qkv_hi, int B, int T, int H, const int* kv_len, void* out_hi, void* out_lo, bool fp16, int out_format,
+              DropSpec drop, cudaStream_t stream);
+}
+
 static int attn_fwd_impl(const void* qkv_hi, const void* qkv_lo, int batch, int frames, int num_heads, int head_size,
                          const int32_t* kv_len, void* out_hi, void* out_lo, int passes, int out_format, w2v2::DropSpec drop,
                          void* stream) {
@@ -574,6 +580,10 @@ static int attn_fwd_impl(const void* qkv_hi, const void* qkv_lo, int batch, int 
   W2V2_CHECK_ARG(out_format >= 0 && out_format <= 2 && (out_format != 2 || out_lo), "out_format must be 0, 1 or 2 (2 writes out_lo)");
   W2V2_CHECK_ARG(batch > 0 && frames > 0 && num_heads > 0, "batch, frames, num_heads must be positive");
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // single-pass modes: the two-tile kernel of attn2.cu (W2V2_ATTN_KERNEL=1 selects the one-tile kernel of this file: A/B switch)
+  static const int which = [] { const char* e = getenv("W2V2_ATTN_KERNEL"); return e ? atoi(e) : 2; }();
+  if (np == 1 && which == 2)
+    return attn_fwd2(qkv_hi, batch, frames, num_heads, kv_len, out_hi, out_lo, (passes & 16) != 0, out_format, drop, s);
 #define AT_LAUNCH(P, F) launch_attn<P, F>(qkv_hi, qkv_lo, batch, frames, num_heads, kv_len, out_hi, out_lo, out_format, drop, s)
   if (passes == 1) return AT_LAUNCH(1, false);
   if (passes == 17) return AT_LAUNCH(1, true);
