@@ -2,7 +2,9 @@
 // (q tiles 2i and 2i + 1 of one (utterance, head)) that share every K / V chunk.
 //     warpgroup 0 / 1 (warps 0-3 / 4-7): softmax of tile A / tile B, one score row per thread (208 registers)
 //     warpgroup 2 (warps 8-11): output warps - O / l -> context of a finished tile, while the softmax warps are in the next one
-//     warpgroup 3 (warps 12-15): warp 12 = TMEM alloc + TMA producer, warp 13 = MMA issuer (one elected thread each)
+//     warpgroup 3 (warps 12-15): warp 12 = TMEM alloc + TMA producer, warps 13 / 14 = MMA issuers of tile A / tile B (one elected
+//         thread each; ONE issuer walking both tiles in a fixed order makes the faster softmax warpgroup wait for the slower one
+//         at every chunk - ncu: 20 % of the softmax warps' samples on the S barrier)
 // TMEM (all 512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384) P_A [384,448) P_B [448,512).
 // Shared memory: Q_A, Q_B (32 KB) + a 6-stage K / V ring (192 KB): both tiles read the same K / V tiles - half the L2 traffic of
 // two independent CTAs.  Semantics, operand layouts and the lazy rescaling are those of attn.cu (reference: encoder.py:34-54,
@@ -19,6 +21,9 @@ constexpr int A2_THREADS = 512;
 constexpr int A2_REGS_SOFTMAX = 208, A2_REGS_OUTPUT = 48, A2_REGS_CONTROL = 48;   // 128 x (2 x 208 + 48 + 48) = 65536
 constexpr int A2_TILE = A2_BM * A2_DH * 2;       // 16 KB: one [128][64] 16-bit tile
 constexpr int A2_STAGES = 6;
+#ifndef A2_PINGPONG
+#define A2_PINGPONG 0
+#endif
 constexpr int A2_Q_OFF = 0;
 constexpr int A2_KV_OFF = 2 * A2_TILE;
 constexpr int A2_STAGE_BYTES = 2 * A2_TILE;      // K and V
@@ -71,10 +76,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
   if (warp == 12 && elect_one()) tma_prefetch_desc(&tm);
   if (warp == 13 && elect_one()) {
     mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
+    mbar_init(q_empty, 2);                 // both tiles' issuers release Q and every K / V stage
     for (int i = 0; i < A2_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], 2);
     }
     for (int w = 0; w < 2; ++w) {
       mbar_init(tb(w, S_FULL), 1);
@@ -124,8 +129,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
           }
         }
       }
-    } else if (warp == 13) {
-      // ---------------------------------------------------------------- MMA issuer
+    } else if (warp <= 14) {
+      // ---------------------------------------------------------------- MMA issuer of tile w
+      const int w = warp - 13;
       if (elect_one()) {
         constexpr uint32_t idesc_s = idesc_16bit(FP16, A2_BM, A2_BN, 0, 0);
         constexpr uint32_t idesc_pv = idesc_16bit(FP16, A2_BM, A2_DH, 0, 1);
@@ -135,8 +141,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
           item_coords(item, q0, h, b);
           return (item_kv_len(b) + A2_BN - 1) / A2_BN;
         };
-        // Q K^T of one chunk for tile w (S_w <- Q_w K^T)
-        auto issue_qk = [&](int w, int stage) {
+        // Q K^T of one chunk (S_w <- Q_w K^T)
+        auto issue_qk = [&](int stage) {
           const uint64_t dq = desc_kmajor_sw128(q_addr + w * A2_TILE);
           const uint64_t dk = desc_kmajor_sw128(smem_u32(smem + A2_KV_OFF + stage * A2_STAGE_BYTES));
 #pragma unroll
@@ -151,8 +157,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
           mbar_wait(q_full, 0);
           mbar_wait(&kv_full[0], 0);
           tc_fence_after();
-          issue_qk(0, 0);
-          issue_qk(1, 0);
+          issue_qk(0);
           if (nchunks == 1) umma_commit(q_empty);
         }
         for (; item < p.n_items; item += gridDim.x, ++it) {
@@ -171,28 +176,22 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
             if (same_item || nchunks_next > 0) {
               if (!same_item) mbar_wait(q_full, (it + 1) & 1);
               mbar_wait(&kv_full[nstage], nphase);
-#pragma unroll
-              for (int w = 0; w < 2; ++w) {
-                mbar_wait(tb(w, S_EMPTY), par);       // S_w(g) is in registers
-                tc_fence_after();
-                issue_qk(w, nstage);
-              }
+              mbar_wait(tb(w, S_EMPTY), par);       // S_w(g) is in registers
+              tc_fence_after();
+              issue_qk(nstage);
               if (same_item ? (j + 2 == nchunks) : (nchunks_next == 1)) umma_commit(q_empty);
             }
+            mbar_wait(tb(w, P_FULL), par);
+            if (j == 0 && it > 0) mbar_wait(tb(w, EPI_DONE), (it - 1) & 1);   // the output warps hold the previous O_w
+            tc_fence_after();
 #pragma unroll
-            for (int w = 0; w < 2; ++w) {
-              mbar_wait(tb(w, P_FULL), par);
-              if (j == 0 && it > 0) mbar_wait(tb(w, EPI_DONE), (it - 1) & 1);   // the output warps hold the previous O_w
-              tc_fence_after();
-#pragma unroll
-              for (int ks = 0; ks < A2_BN / 16; ++ks) {
-                const uint64_t dv = desc_mnmajor_sw128(v_addr + ks * 2048, 1024, 1024);
-                umma_f16_tmem_a(tmem_base + 256 + 64 * w, tmem_base + 384 + 64 * w + ks * 8, dv, idesc_pv, (j | ks) != 0);
-              }
-              umma_commit(tb(w, PV_DONE));
-              umma_commit(tb(w, P_EMPTY));
-              if (j + 1 == nchunks) umma_commit(tb(w, O_FULL));
+            for (int ks = 0; ks < A2_BN / 16; ++ks) {
+              const uint64_t dv = desc_mnmajor_sw128(v_addr + ks * 2048, 1024, 1024);
+              umma_f16_tmem_a(tmem_base + 256 + 64 * w, tmem_base + 384 + 64 * w + ks * 8, dv, idesc_pv, (j | ks) != 0);
             }
+            umma_commit(tb(w, PV_DONE));
+            umma_commit(tb(w, P_EMPTY));
+            if (j + 1 == nchunks) umma_commit(tb(w, O_FULL));
             umma_commit(&kv_empty[stage]);
             stage = nstage;
             kv_phase = nphase;
@@ -275,6 +274,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
     uint64_t* p_empty = tb(w, P_EMPTY);
     uint64_t* pv_done = tb(w, PV_DONE);
     uint32_t g = 0, it = 0;
+    // MUFU ping-pong: the two softmax warpgroups share the SM's 16 exp2 lanes per clock.  Left alone they fall into lockstep (one
+    // MMA thread, one K / V ring feed both) and then both sit in their exponential phase together (2 x 1024 MUFU cycles) and
+    // both outside it together.  Named barriers 1 (A may go) and 2 (B may go) make the exponential phases strictly alternate:
+    // while one warpgroup owns the MUFU the other does its TMEM load / max / pack / store.  B pre-arms A's barrier.
+    if (A2_PINGPONG && w == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       int q0, h, b;
       item_coords(item, q0, h, b);
@@ -345,6 +349,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
         uint64_t sum2[4] = {pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f), pack2(0.f, 0.f)};
         const bool drop_on = DROP && p.drop.thr16 != 0;
         const uint64_t rg = drop_on ? attn_row_group(b * p.H + h, q0 + r, p.T) + (uint64_t)(key0 >> 2) : 0;
+        if (A2_PINGPONG) {
+          if (w == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+          else asm volatile("bar.sync 2, 256;" ::: "memory");
+        }
         // probabilities, packed to 16 bits IN PLACE as they are produced: keys [0, 64) -> sr[0][0..31], keys [64, 128) -> sr[2][0..31]
 #pragma unroll
         for (int pc = 0; pc < 4; ++pc) {
@@ -366,6 +374,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
             sr[pc & 2][c] = FP16 ? pack_f16x2(a[0], a[1]) : pack_bf16x2(a[0], a[1]);
             sr[pc & 2][c + 1] = FP16 ? pack_f16x2(a[2], a[3]) : pack_bf16x2(a[2], a[3]);
           }
+        }
+        if (A2_PINGPONG) {
+          // hand the MUFU to the other warpgroup (B's very last hand-over would have no taker)
+          const bool last_chunk = (j + 1 == nchunks) && (item + (int)gridDim.x >= p.n_items);
+          if (w == 0) asm volatile("bar.arrive 2, 256;" ::: "memory");
+          else if (!last_chunk) asm volatile("bar.arrive 1, 256;" ::: "memory");
         }
         {
           float s0, s1, s2, s3, s4, s5, s6, s7;
