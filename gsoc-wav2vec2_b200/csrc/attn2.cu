@@ -274,10 +274,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
     uint64_t* p_empty = tb(w, P_EMPTY);
     uint64_t* pv_done = tb(w, PV_DONE);
     uint32_t g = 0, it = 0;
-    // MUFU ping-pong: the two softmax warpgroups share the SM's 16 exp2 lanes per clock.  Left alone they fall into lockstep (one
-    // MMA thread, one K / V ring feed both) and then both sit in their exponential phase together (2 x 1024 MUFU cycles) and
-    // both outside it together.  Named barriers 1 (A may go) and 2 (B may go) make the exponential phases strictly alternate:
-    // while one warpgroup owns the MUFU the other does its TMEM load / max / pack / store.  B pre-arms A's barrier.
+    // MUFU ping-pong (A2_PINGPONG, OFF): named barriers 1 (A may go) and 2 (B may go) make the exponential phases of the two
+    // softmax warpgroups strictly alternate, FA3-style.  Measured SLOWER here (87.9 -> 96.5 us per layer): one warp per scheduler
+    // does not saturate the MUFU on its own (its FFMA2 / pack / sum instructions interleave with the exp2s), so two overlapping
+    // exponential phases use the pipe better than two serialised ones.  Kept as a compile-time switch with that finding.
     if (A2_PINGPONG && w == 1) asm volatile("bar.arrive 1, 256;" ::: "memory");
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
       int q0, h, b;
