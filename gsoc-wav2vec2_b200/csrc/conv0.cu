@@ -264,13 +264,13 @@ conv0_mma_kernel(const float* __restrict__ wave, int L, int T0, const float* __r
 #pragma unroll
           for (int hb = 0; hb < 2; ++hb) {
             const uint32_t* o4 = &ol[r][4 * hb];
-            *reinterpret_cast<uint2*>(p8 + 32 * hb) = make_uint2((o4[0] & 0xFFFFu) | (o4[1] << 16), (o4[2] & 0xFFFFu) | (o4[3] << 16));
-            *reinterpret_cast<uint2*>(p8 + 32 * hb + 64) = make_uint2((o4[0] >> 16) | (o4[1] & 0xFFFF0000u), (o4[2] >> 16) | (o4[3] & 0xFFFF0000u));
+            __stcs(reinterpret_cast<uint2*>(p8 + 32 * hb), make_uint2((o4[0] & 0xFFFFu) | (o4[1] << 16), (o4[2] & 0xFFFFu) | (o4[3] << 16)));
+            __stcs(reinterpret_cast<uint2*>(p8 + 32 * hb + 64), make_uint2((o4[0] >> 16) | (o4[1] & 0xFFFF0000u), (o4[2] >> 16) | (o4[3] & 0xFFFF0000u)));
           }
         } else if (PASSES == 3 && OUT_FMT == 0) {
           __nv_bfloat16* pl = out_lo + out_base + (size_t)t * CM_C;
-          *reinterpret_cast<uint4*>(pl) = make_uint4(ol[r][0], ol[r][1], ol[r][2], ol[r][3]);
-          *reinterpret_cast<uint4*>(pl + 32) = make_uint4(ol[r][4], ol[r][5], ol[r][6], ol[r][7]);
+          __stcs(reinterpret_cast<uint4*>(pl), make_uint4(ol[r][0], ol[r][1], ol[r][2], ol[r][3]));
+          __stcs(reinterpret_cast<uint4*>(pl + 32), make_uint4(ol[r][4], ol[r][5], ol[r][6], ol[r][7]));
         }
       }
     }
