@@ -21,6 +21,9 @@ constexpr int A2_THREADS = 512;
 constexpr int A2_REGS_SOFTMAX = 208, A2_REGS_OUTPUT = 48, A2_REGS_CONTROL = 48;   // 128 x (2 x 208 + 48 + 48) = 65536
 constexpr int A2_TILE = A2_BM * A2_DH * 2;       // 16 KB: one [128][64] 16-bit tile
 constexpr int A2_STAGES = 6;
+#ifndef A2_POLY_EVERY
+#define A2_POLY_EVERY 0
+#endif
 #ifndef A2_PINGPONG
 #define A2_PINGPONG 0
 #endif
@@ -30,6 +33,24 @@ constexpr int A2_STAGE_BYTES = 2 * A2_TILE;      // K and V
 constexpr int A2_L_OFF = A2_KV_OFF + A2_STAGES * A2_STAGE_BYTES;   // row sums: [2 tiles][128] floats
 constexpr int A2_BAR_OFF = A2_L_OFF + 1024;
 constexpr int A2_SMEM = A2_BAR_OFF + 512;
+
+// 2^x for x <= ~9 on the FMA / ALU pipes (FA4's MUFU off-load): x = n + f with n = rint(x) from the 1.5 * 2^23 trick, |f| <= 0.5,
+// 2^f as a degree-3 minimax polynomial (1.0e-4 relative: below the 2^-9 / 2^-11 rounding of the bf16 / fp16 probabilities), 2^n by
+// adding n to the exponent field.  -inf (masked keys) clamps to 2^-125.
+__device__ __forceinline__ void ex2_poly_x2(float& a0, float& a1) {
+  const uint64_t x = pack2(fmaxf(a0, -125.0f), fmaxf(a1, -125.0f));
+  const uint64_t t = add2(x, pack2(12582912.0f, 12582912.0f));
+  const uint64_t nf = add2(t, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t f = fma2(nf, pack2(-1.0f, -1.0f), x);
+  uint64_t q = fma2(f, pack2(0.05500892922282219f, 0.05500892922282219f), pack2(0.24221095442771912f, 0.24221095442771912f));
+  q = fma2(q, f, pack2(0.6932829022407532f, 0.6932829022407532f));
+  q = fma2(q, f, pack2(1.0f, 1.0f));
+  float p0, p1, t0, t1;
+  unpack2(q, p0, p1);
+  unpack2(t, t0, t1);
+  a0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  a1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
 
 struct Attn2Params {
   int T, d, H;
@@ -361,8 +382,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
             float a[4];
             unpack2(fma2(pack2(__uint_as_float(sr[pc][i]), __uint_as_float(sr[pc][i + 1])), l2e2, mneg2), a[0], a[1]);
             unpack2(fma2(pack2(__uint_as_float(sr[pc][i + 2]), __uint_as_float(sr[pc][i + 3])), l2e2, mneg2), a[2], a[3]);
+            if (A2_POLY_EVERY > 0 && ((i >> 2) % A2_POLY_EVERY) == A2_POLY_EVERY - 1) {
+              ex2_poly_x2(a[0], a[1]);     // every A2_POLY_EVERY-th group of 4 keys leaves the MUFU alone
+              ex2_poly_x2(a[2], a[3]);
+            } else {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) a[e] = ex2_approx(a[e]);
+              for (int e = 0; e < 4; ++e) a[e] = ex2_approx(a[e]);
+            }
             sum2[(i >> 1) & 3] = add2(sum2[(i >> 1) & 3], pack2(a[0], a[1]));
             sum2[((i >> 1) + 1) & 3] = add2(sum2[((i >> 1) + 1) & 3], pack2(a[2], a[3]));
             if (drop_on) {
