@@ -21,8 +21,11 @@ constexpr int A2_THREADS = 512;
 constexpr int A2_REGS_SOFTMAX = 208, A2_REGS_OUTPUT = 48, A2_REGS_CONTROL = 48;   // 128 x (2 x 208 + 48 + 48) = 65536
 constexpr int A2_TILE = A2_BM * A2_DH * 2;       // 16 KB: one [128][64] 16-bit tile
 constexpr int A2_STAGES = 6;
-#ifndef A2_POLY_EVERY
-#define A2_POLY_EVERY 0
+// Groups of 4 keys (one bit per group of a 32-key block) whose exponentials run as a polynomial on the FMA pipe.  Measured per layer
+// at B = 32, T = 768: none 87.1 us, 1 of 8 86.7, 2 of 8 82.6 - 82.9 (groups 2 and 5; 84.4 for groups 3 and 7), 3 of 8 83.1 - 84.5,
+// 4 of 8 88.4.
+#ifndef A2_POLY_MASK
+#define A2_POLY_MASK 0x24
 #endif
 #ifndef A2_PINGPONG
 #define A2_PINGPONG 0
@@ -382,8 +385,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tm, const Attn2Params p) {
             float a[4];
             unpack2(fma2(pack2(__uint_as_float(sr[pc][i]), __uint_as_float(sr[pc][i + 1])), l2e2, mneg2), a[0], a[1]);
             unpack2(fma2(pack2(__uint_as_float(sr[pc][i + 2]), __uint_as_float(sr[pc][i + 3])), l2e2, mneg2), a[2], a[3]);
-            if (A2_POLY_EVERY > 0 && ((i >> 2) % A2_POLY_EVERY) == A2_POLY_EVERY - 1) {
-              ex2_poly_x2(a[0], a[1]);     // every A2_POLY_EVERY-th group of 4 keys leaves the MUFU alone
+            if (!DROP && ((A2_POLY_MASK >> (i >> 2)) & 1)) {     // (the training forward keeps the backward kernel's exp2)
+              ex2_poly_x2(a[0], a[1]);     // the groups of 4 keys selected by A2_POLY_MASK (one bit per group of a 32-key block) leave the MUFU alone
               ex2_poly_x2(a[2], a[3]);
             } else {
 #pragma unroll

@@ -310,9 +310,14 @@ def test_stage2_extractor_prefetch_gives_the_same_steps():
             nxt = xs[(i + 1) % 2] if prefetch else None
             losses.append(tr.step(xs[i % 2], labels, next_speech=nxt).item())
         runs.append((losses, tr.flat_w.clone(), m, before))
-    # (not bit-identical run to run: the split-K weight-gradient GEMMs accumulate with fp32 atomics)
-    assert max(abs(a - b) for a, b in zip(runs[0][0], runs[1][0])) < 1e-3
-    assert (runs[0][1] - runs[1][1]).abs().max().item() < 2e-5
+    # Not bit-identical run to run, with or without the prefetch: column sums and split-K weight gradients accumulate with fp32
+    # atomics, and a parameter whose true gradient is zero (the key bias: softmax ignores a constant added to every score) gets a
+    # gradient of pure rounding noise whose SIGN Adam turns into a full +- lr step.  Two plain runs already land in one of two
+    # states after three steps (tools/train_nondeterminism.py: third loss 171.2716 or 171.2617, weights 2.35e-4 = 2.35 lr apart), so
+    # the check is: losses agree to 3e-4 relative, no weight is further apart than 3 lr, and all but a sliver agree to 2e-5.
+    assert max(abs(a - b) / abs(a) for a, b in zip(runs[0][0], runs[1][0])) < 3e-4
+    wdiff = (runs[0][1] - runs[1][1]).abs()
+    assert wdiff.max().item() < 3e-4 and (wdiff > 2e-5).float().mean().item() < 1e-3
     m = runs[1][2]
     after = m(xs[0])
     assert (after - runs[1][3]).abs().max().item() > 1e-4          # the eval forward sees the trained weights ...
