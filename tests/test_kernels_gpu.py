@@ -285,6 +285,20 @@ def test_attention(passes, T):
     assert err < (2e-2 if passes == 1 else 1e-4)
 
 
+def test_attention_one_tile_reference_kernel():
+    """W2V2_ATTN_KERNEL=1 keeps the one-tile kernel of attn.cu as the A/B reference of the single-pass modes; the selection is read
+    once per process, so the same attention checks run in a child process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, W2V2_ATTN_KERNEL="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-k",
+                        "test_attention and not one_tile and not deterministic", "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "6 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 @pytest.mark.parametrize("drop", [None, (0.1, 1234, 7)])
 def test_attention_is_deterministic(drop):
     """The two-tile kernel hands S / P / O / row sums between five warp roles through mbarriers; a missing edge in that protocol
