@@ -7,6 +7,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "gsoc-wav2vec2_b200"))
 import torch  # noqa: E402
+from wav2vec2 import _lib  # noqa: E402
+if os.environ.get("W2V2_LIB_DIR"):       # A/B of compile-time variants: a library built into another directory
+    _lib.LIB_PATH = os.path.join(os.environ["W2V2_LIB_DIR"], "libw2v2_sm100.so")
 from wav2vec2 import ops  # noqa: E402
 from wav2vec2.ops import Pair  # noqa: E402
 
